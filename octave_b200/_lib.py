@@ -1,0 +1,99 @@
+"""ctypes binding of liboctave_b200.so — the C-ABI in include/octave_b200.h.
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc; if that
+fails the import error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "lib" / "liboctave_b200.so"
+_HEADER = _HERE.parent / "include" / "octave_b200.h"
+
+OK = 0
+ERR_INVALID = -1
+ERR_UNSUPPORTED = -2
+ERR_LAUNCH = -3
+
+DTYPE_F32 = 0
+DTYPE_BF16 = 1
+
+
+class OctaveError(RuntimeError):
+    """Non-zero return code of a C-ABI entry point."""
+
+    def __init__(self, fn: str, rc: int):
+        names = {ERR_INVALID: "OCT_ERR_INVALID", ERR_UNSUPPORTED: "OCT_ERR_UNSUPPORTED", ERR_LAUNCH: "OCT_ERR_LAUNCH"}
+        super().__init__(f"{fn} failed with {names.get(rc, rc)}")
+        self.rc = rc
+
+
+def declared_symbols() -> list[str]:
+    """Every function declared in include/octave_b200.h (used by the symbol-export test)."""
+    text = _HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(octave_[a-z0-9_]+)\s*\(", text)))
+
+
+def _load() -> C.CDLL:
+    if not _LIB_PATH.exists() or os.environ.get("OCTAVE_B200_REBUILD"):
+        from . import build as _build
+
+        _build.build()
+    return C.CDLL(str(_LIB_PATH))
+
+
+lib = _load()
+
+
+def check(fn: str, rc: int) -> None:
+    if rc != OK:
+        raise OctaveError(fn, rc)
+
+
+# ---------------------------------------------------------------------------------------------
+# struct mirrors
+# ---------------------------------------------------------------------------------------------
+class LossDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("flags", C.c_int32),
+        ("n_att", C.c_int32),
+        ("att_h", C.c_int32 * 5),
+        ("att_w", C.c_int32 * 5),
+        ("att_weight", C.c_float * 4),
+        ("sum_weights", C.c_float),
+        ("wpce_scale", C.c_float),
+        ("dice_eps", C.c_float),
+        ("n_real", C.c_int32), ("n_fake", C.c_int32),
+    ]
+
+
+LOSS_WPCE = 1 << 0
+LOSS_DICE = 1 << 1
+LOSS_KLD = 1 << 2
+LOSS_LSG = 1 << 3
+LOSS_LSD = 1 << 4
+LOSS_FROM_LOGITS = 1 << 5
+LOSS_WPCE_FULL = 1 << 6
+LOSS_KLD_STOPGRAD = 1 << 7
+LOSS_OUT_SLOTS = 8
+
+_vp = C.c_void_p
+
+lib.octave_abi_version.restype = C.c_int
+lib.octave_sm_count.restype = C.c_int
+lib.octave_loss_stats_bytes.restype = C.c_size_t
+lib.octave_loss_stats_bytes.argtypes = [C.POINTER(LossDesc)]
+lib.octave_loss_uses_fast_path.restype = C.c_int
+lib.octave_loss_uses_fast_path.argtypes = [C.POINTER(LossDesc)]
+lib.octave_loss_fwd.restype = C.c_int
+lib.octave_loss_fwd.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp]
+lib.octave_loss_bwd.restype = C.c_int
+lib.octave_loss_bwd.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
+                                C.POINTER(_vp), _vp, _vp, _vp]

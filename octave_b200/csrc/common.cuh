@@ -1,0 +1,144 @@
+// Shared device helpers for the octave_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define OCT_OK 0
+#define OCT_ERR_INVALID (-1)      // bad argument (null pointer, shape out of contract)
+#define OCT_ERR_UNSUPPORTED (-2)  // shape/dtype outside what this entry point handles
+#define OCT_ERR_LAUNCH (-3)       // cudaGetLastError() != success after the launch
+
+#define OCT_DTYPE_F32 0
+#define OCT_DTYPE_BF16 1
+
+#define OCT_CHECK_LAUNCH()                                   \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) return OCT_ERR_LAUNCH;           \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of NV values per thread. `red` must hold NV * (blockDim.x/32) floats.
+// Result valid in warp 0 lane 0 (returned to every thread of warp 0).
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[i * nw + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float t = lane < nw ? red[i * nw + lane] : 0.f;
+      v[i] = warp_sum(t);
+    }
+  }
+  __syncthreads();
+}
+
+// ---- vector loads/stores of N consecutive elements, converted to/from float ----
+template <typename T, int N> struct VecIO;
+
+template <> struct VecIO<float, 8> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct VecIO<float, 2> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = a.x; v[1] = a.y;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    reinterpret_cast<float2*>(p)[0] = make_float2(v[0], v[1]);
+  }
+};
+template <> struct VecIO<float, 1> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; }
+};
+
+__device__ __forceinline__ void bf16x2_unpack(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t bf16x2_pack(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <> struct VecIO<bf16, 8> {
+  static __device__ __forceinline__ void ld(const bf16* p, float* v) {
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    bf16x2_unpack(a.x, v[0], v[1]); bf16x2_unpack(a.y, v[2], v[3]);
+    bf16x2_unpack(a.z, v[4], v[5]); bf16x2_unpack(a.w, v[6], v[7]);
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float* v) {
+    uint4 a;
+    a.x = bf16x2_pack(v[0], v[1]); a.y = bf16x2_pack(v[2], v[3]);
+    a.z = bf16x2_pack(v[4], v[5]); a.w = bf16x2_pack(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = a;
+  }
+};
+template <> struct VecIO<bf16, 4> {
+  static __device__ __forceinline__ void ld(const bf16* p, float* v) {
+    uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+    bf16x2_unpack(a.x, v[0], v[1]); bf16x2_unpack(a.y, v[2], v[3]);
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float* v) {
+    uint2 a;
+    a.x = bf16x2_pack(v[0], v[1]); a.y = bf16x2_pack(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = a;
+  }
+};
+template <> struct VecIO<bf16, 2> {
+  static __device__ __forceinline__ void ld(const bf16* p, float* v) {
+    uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(p));
+    bf16x2_unpack(a, v[0], v[1]);
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float* v) {
+    *reinterpret_cast<uint32_t*>(p) = bf16x2_pack(v[0], v[1]);
+  }
+};
+template <> struct VecIO<bf16, 1> {
+  static __device__ __forceinline__ void ld(const bf16* p, float* v) { v[0] = __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(bf16* p, const float* v) { p[0] = __float2bfloat16_rn(v[0]); }
+};

@@ -1,0 +1,750 @@
+// K9 — fused loss kernels.
+//
+// One statistics pass + one gradient pass over the loss maps replace the reference's chains of
+// elementwise/reduce kernels:
+//   WeightedPartialCE   /root/reference/architectures/segmentor/losses.py:26-61
+//   DiceLoss            .../segmentor/losses.py:70-74
+//   InterlayerDivergence (KLD/mean)  .../segmentor/losses.py:111-147
+//   LSGeneratorLoss / LSDiscriminatorialLoss  .../discriminator/losses.py:11-24
+//
+// Layout: maps are NCHW planar exactly as the reference holds them.  Fast path: C == 2, H,W % 16 == 0,
+// attention pyramid att[k] = [B,2,H>>k,W>>k]; one warp owns a 16x16 full-resolution cell (lane ->
+// row l>>1, 8 consecutive pixels), so every load is a 16/32-byte vector, the nearest-neighbour
+// upsample (losses.py:126) is an index shift, and the coarse-level gradients are 2^k x 2^k box sums
+// done with warp shuffles — no atomics on the maps.  Generic path (any C <= 8, any map sizes, fp32):
+// one thread per pixel, fp32 atomics for coarse gradients.
+//
+// Algorithmic traffic (C=2): forward reads 6.664 elements/pixel, backward re-reads them and writes
+// 4.664 => 17.99 elements/pixel.
+#include "common.cuh"
+#include "../../include/octave_b200.h"
+
+namespace {
+
+constexpr int ST_N = 0;        // n_c      [8]
+constexpr int ST_S = 8;        // S_c      [8]  sum ys_c * log(arg_c + eps)
+constexpr int ST_KLD = 16;
+constexpr int ST_LSG = 17;     // sum (f-1)^2
+constexpr int ST_LSDR = 18;    // sum (r-1)^2
+constexpr int ST_LSDF = 19;    // sum (f+1)^2
+constexpr int ST_COUNTER = 20; // unsigned long long
+constexpr int ST_W = 24;       // class weights w_c [8], written by the finalising block
+constexpr int ST_DICE = 32;    // I_b [B], Card_b [B]
+
+constexpr float kEps = 1e-12f;  // literal in losses.py:37,52,112,135 (not self.eps)
+
+struct LossArgs {
+  const void* yhat;
+  const void* ys;
+  const void* att[OCT_LOSS_MAX_ATT];
+  const float* d_real;
+  const float* d_fake;
+  double* stats;
+  float* out;
+  // backward only
+  const float* gscale;
+  void* g_yhat;
+  void* g_att[OCT_LOSS_MAX_ATT];
+  float* g_real;
+  float* g_fake;
+  int B, C, H, W, flags, n_att;
+  int ah[OCT_LOSS_MAX_ATT], aw[OCT_LOSS_MAX_ATT];
+  float aw8[OCT_LOSS_MAX_ATT - 1];
+  float inv_sumw, wpce_scale, dice_eps;
+  int n_real, n_fake;
+};
+
+__device__ __forceinline__ void atomic_add_f64(double* p, float v) { atomicAdd(p, (double)v); }
+
+// Sum of LS-GAN squared errors, computed by one block (strided over threads).
+__device__ __forceinline__ void ls_partial(const LossArgs& a, float& lsg, float& lsdr, float& lsdf) {
+  lsg = lsdr = lsdf = 0.f;
+  if (a.flags & (OCT_LOSS_LSG | OCT_LOSS_LSD)) {
+    for (int i = threadIdx.x; i < a.n_fake; i += blockDim.x) {
+      float f = a.d_fake[i];
+      lsg += (f - 1.f) * (f - 1.f);
+      lsdf += (f + 1.f) * (f + 1.f);
+    }
+  }
+  if (a.flags & OCT_LOSS_LSD) {
+    for (int i = threadIdx.x; i < a.n_real; i += blockDim.x) {
+      float r = a.d_real[i];
+      lsdr += (r - 1.f) * (r - 1.f);
+    }
+  }
+}
+
+// Executed by the last block to retire: turns the accumulated sums into the five loss scalars.
+__device__ void finalize(const LossArgs& a) {
+  volatile double* st = a.stats;
+  float* out = a.out;
+  const double npix = (double)a.B * a.H * a.W;
+  double wpce = 0.0, dice = 0.0, kld = 0.0, lsg = 0.0, lsd = 0.0;
+  if (a.flags & OCT_LOSS_WPCE) {
+    // ni, n_tot, weights: losses.py:34-38 (fp32 in the reference; the sums are exact integers there)
+    float ntot = 0.f;
+    for (int c = 0; c < a.C; ++c) ntot += (float)st[ST_N + c];
+    double acc = 0.0;
+    for (int c = 0; c < a.C; ++c) {
+      float w = ntot / ((float)st[ST_N + c] + kEps);
+      st[ST_W + c] = (double)w;
+      acc += (double)w * st[ST_S + c];
+    }
+    wpce = -acc * (double)a.wpce_scale;
+  }
+  if (a.flags & OCT_LOSS_DICE) {
+    for (int b = 0; b < a.B; ++b) {
+      double I = st[ST_DICE + b], card = st[ST_DICE + a.B + b];
+      dice += 1.0 - 2.0 * I / (card + (double)a.dice_eps);
+    }
+    dice /= (double)a.B;
+  }
+  if (a.flags & OCT_LOSS_KLD) kld = st[ST_KLD] / npix;
+  if (a.flags & OCT_LOSS_LSG) lsg = 0.5 * st[ST_LSG] / (double)a.n_fake;
+  if (a.flags & OCT_LOSS_LSD)
+    lsd = 0.5 * st[ST_LSDR] / (double)a.n_real + 0.5 * st[ST_LSDF] / (double)a.n_fake;
+  out[OCT_LOSS_OUT_WPCE] = (float)wpce;
+  out[OCT_LOSS_OUT_DICE] = (float)dice;
+  out[OCT_LOSS_OUT_KLD] = (float)kld;
+  out[OCT_LOSS_OUT_LSG] = (float)lsg;
+  out[OCT_LOSS_OUT_LSD] = (float)lsd;
+  out[OCT_LOSS_OUT_NANFLAG] = (kld != kld) ? 1.f : 0.f;
+  out[6] = 0.f;
+  out[7] = 0.f;
+}
+
+__device__ __forceinline__ void retire_block(const LossArgs& a) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned long long total = (unsigned long long)gridDim.x * gridDim.y;
+    unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.stats + ST_COUNTER), 1ULL);
+    s_last = (prev == total - 1ULL);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    finalize(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path, C == 2.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct CellLoad {
+  float p0[8], p1[8];  // yhat as probabilities
+  float t0[8], t1[8];  // ys
+  float b0[8], b1[8];  // basis attention
+  float q1[2][4], q2[2][2], q3[2], q4[2];  // coarse attentions
+  float m0[8], m1[8];  // sum_k log(w_k q_k + eps)
+};
+
+__device__ __forceinline__ void softmax2(float& z0, float& z1) {
+  // softmax over dim=1 with C=2, same max-subtracted form torch uses
+  float m = fmaxf(z0, z1);
+  float e0 = __expf(z0 - m), e1 = __expf(z1 - m);
+  float inv = 1.f / (e0 + e1);
+  z0 = e0 * inv;
+  z1 = e1 * inv;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_cell(const LossArgs& a, int b, int y, int x0, CellLoad<T>& c) {
+  const size_t plane = (size_t)a.H * a.W;
+  const size_t off = (size_t)b * 2 * plane + (size_t)y * a.W + x0;
+  if (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+    const T* yh = reinterpret_cast<const T*>(a.yhat);
+    const T* ys = reinterpret_cast<const T*>(a.ys);
+    VecIO<T, 8>::ld(yh + off, c.p0);
+    VecIO<T, 8>::ld(yh + off + plane, c.p1);
+    VecIO<T, 8>::ld(ys + off, c.t0);
+    VecIO<T, 8>::ld(ys + off + plane, c.t1);
+    if (a.flags & OCT_LOSS_FROM_LOGITS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) softmax2(c.p0[j], c.p1[j]);
+    }
+  }
+  if (a.flags & OCT_LOSS_KLD) {
+    const T* a0 = reinterpret_cast<const T*>(a.att[0]);
+    VecIO<T, 8>::ld(a0 + off, c.b0);
+    VecIO<T, 8>::ld(a0 + off + plane, c.b1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c.m0[j] = c.m1[j] = 0.f;
+    if (a.n_att > 1 && a.aw8[0] != 0.f) {
+      const float w = a.aw8[0];
+      const size_t pl = plane >> 2;
+      const T* q = reinterpret_cast<const T*>(a.att[1]) + (size_t)b * 2 * pl +
+                   (size_t)(y >> 1) * (a.W >> 1) + (x0 >> 1);
+      VecIO<T, 4>::ld(q, c.q1[0]);
+      VecIO<T, 4>::ld(q + pl, c.q1[1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float l0 = __logf(w * c.q1[0][j] + kEps), l1 = __logf(w * c.q1[1][j] + kEps);
+        c.m0[2 * j] += l0; c.m0[2 * j + 1] += l0;
+        c.m1[2 * j] += l1; c.m1[2 * j + 1] += l1;
+      }
+    }
+    if (a.n_att > 2 && a.aw8[1] != 0.f) {
+      const float w = a.aw8[1];
+      const size_t pl = plane >> 4;
+      const T* q = reinterpret_cast<const T*>(a.att[2]) + (size_t)b * 2 * pl +
+                   (size_t)(y >> 2) * (a.W >> 2) + (x0 >> 2);
+      VecIO<T, 2>::ld(q, c.q2[0]);
+      VecIO<T, 2>::ld(q + pl, c.q2[1]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float l0 = __logf(w * c.q2[0][j] + kEps), l1 = __logf(w * c.q2[1][j] + kEps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { c.m0[4 * j + i] += l0; c.m1[4 * j + i] += l1; }
+      }
+    }
+    if (a.n_att > 3 && a.aw8[2] != 0.f) {
+      const float w = a.aw8[2];
+      const size_t pl = plane >> 6;
+      const T* q = reinterpret_cast<const T*>(a.att[3]) + (size_t)b * 2 * pl +
+                   (size_t)(y >> 3) * (a.W >> 3) + (x0 >> 3);
+      VecIO<T, 1>::ld(q, &c.q3[0]);
+      VecIO<T, 1>::ld(q + pl, &c.q3[1]);
+      float l0 = __logf(w * c.q3[0] + kEps), l1 = __logf(w * c.q3[1] + kEps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { c.m0[i] += l0; c.m1[i] += l1; }
+    }
+    if (a.n_att > 4 && a.aw8[3] != 0.f) {
+      const float w = a.aw8[3];
+      const size_t pl = plane >> 8;
+      const T* q = reinterpret_cast<const T*>(a.att[4]) + (size_t)b * 2 * pl +
+                   (size_t)(y >> 4) * (a.W >> 4) + (x0 >> 4);
+      VecIO<T, 1>::ld(q, &c.q4[0]);
+      VecIO<T, 1>::ld(q + pl, &c.q4[1]);
+      float l0 = __logf(w * c.q4[0] + kEps), l1 = __logf(w * c.q4[1] + kEps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { c.m0[i] += l0; c.m1[i] += l1; }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) loss_fast_fwd_kernel(const LossArgs a) {
+  __shared__ float red[10 * 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cw = a.W >> 4, cells = cw * (a.H >> 4);
+  const int cell = blockIdx.x * 8 + warp;
+  const int b = blockIdx.y;
+  // acc: n0 n1 S0 S1 kld I Card lsg lsdr lsdf
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+
+  if (cell < cells && (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD))) {
+    const int cy = cell / cw, cx = cell - cy * cw;
+    const int y = cy * 16 + (lane >> 1), x0 = cx * 16 + (lane & 1) * 8;
+    CellLoad<T> c;
+    load_cell<T>(a, b, y, x0, c);
+    if (a.flags & OCT_LOSS_WPCE) {
+      const bool full = a.flags & OCT_LOSS_WPCE_FULL;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a0 = full ? c.p0[j] : c.p0[j] * c.t0[j];
+        float a1 = full ? c.p1[j] : c.p1[j] * c.t1[j];
+        acc[0] += c.t0[j];
+        acc[1] += c.t1[j];
+        acc[2] += c.t0[j] * __logf(a0 + kEps);
+        acc[3] += c.t1[j] * __logf(a1 + kEps);
+      }
+    }
+    if (a.flags & OCT_LOSS_DICE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[5] += c.p0[j] * c.t0[j] + c.p1[j] * c.t1[j];
+        acc[6] += (c.p0[j] + c.t0[j]) + (c.p1[j] + c.t1[j]);
+      }
+    }
+    if (a.flags & OCT_LOSS_KLD) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[4] += c.b0[j] * (__logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw) +
+                  c.b1[j] * (__logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) ls_partial(a, acc[7], acc[8], acc[9]);
+
+  block_sum<10>(acc, red);
+  if (threadIdx.x == 0) {
+    double* st = a.stats;
+    if (a.flags & OCT_LOSS_WPCE) {
+      atomic_add_f64(st + ST_N + 0, acc[0]);
+      atomic_add_f64(st + ST_N + 1, acc[1]);
+      atomic_add_f64(st + ST_S + 0, acc[2]);
+      atomic_add_f64(st + ST_S + 1, acc[3]);
+    }
+    if (a.flags & OCT_LOSS_KLD) atomic_add_f64(st + ST_KLD, acc[4]);
+    if (a.flags & OCT_LOSS_DICE) {
+      atomic_add_f64(st + ST_DICE + b, acc[5]);
+      atomic_add_f64(st + ST_DICE + a.B + b, acc[6]);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      atomic_add_f64(st + ST_LSG, acc[7]);
+      atomic_add_f64(st + ST_LSDR, acc[8]);
+      atomic_add_f64(st + ST_LSDF, acc[9]);
+    }
+  }
+  retire_block(a);
+}
+
+// LS-GAN gradients, one block.
+__device__ __forceinline__ void ls_backward(const LossArgs& a) {
+  if (a.flags & OCT_LOSS_LSD) {
+    // 0.5*mean((r-1)^2) + 0.5*mean((f+1)^2): discriminator/losses.py:11-14
+    const float g = a.gscale[OCT_LOSS_OUT_LSD];
+    for (int i = threadIdx.x; i < a.n_real; i += blockDim.x)
+      a.g_real[i] = g * (a.d_real[i] - 1.f) / (float)a.n_real;
+    for (int i = threadIdx.x; i < a.n_fake; i += blockDim.x) {
+      float v = g * (a.d_fake[i] + 1.f) / (float)a.n_fake;
+      if (a.flags & OCT_LOSS_LSG)
+        v += a.gscale[OCT_LOSS_OUT_LSG] * (a.d_fake[i] - 1.f) / (float)a.n_fake;
+      a.g_fake[i] = v;
+    }
+  } else if (a.flags & OCT_LOSS_LSG) {
+    // 0.5*mean((f-1)^2): discriminator/losses.py:22-24
+    const float g = a.gscale[OCT_LOSS_OUT_LSG];
+    for (int i = threadIdx.x; i < a.n_fake; i += blockDim.x)
+      a.g_fake[i] = g * (a.d_fake[i] - 1.f) / (float)a.n_fake;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cw = a.W >> 4, cells = cw * (a.H >> 4);
+  const int cell = blockIdx.x * 8 + warp;
+  const int b = blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0) ls_backward(a);
+  if (cell >= cells || !(a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD))) return;
+
+  const int cy = cell / cw, cx = cell - cy * cw;
+  const int r = lane >> 1;
+  const int y = cy * 16 + r, x0 = cx * 16 + (lane & 1) * 8;
+  const size_t plane = (size_t)a.H * a.W;
+  const size_t off = (size_t)b * 2 * plane + (size_t)y * a.W + x0;
+  CellLoad<T> c;
+  load_cell<T>(a, b, y, x0, c);
+
+  if (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+    float g0[8], g1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g0[j] = g1[j] = 0.f;
+    if (a.flags & OCT_LOSS_WPCE) {
+      const bool full = a.flags & OCT_LOSS_WPCE_FULL;
+      const float k = -a.gscale[OCT_LOSS_OUT_WPCE] * a.wpce_scale;
+      const float w0 = k * (float)a.stats[ST_W + 0], w1 = k * (float)a.stats[ST_W + 1];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // d/dyhat [ w * ys * log(yhat*ys + eps) ] = w * ys * ys / (yhat*ys + eps)
+        float a0 = full ? c.p0[j] : c.p0[j] * c.t0[j];
+        float a1 = full ? c.p1[j] : c.p1[j] * c.t1[j];
+        float m0 = full ? c.t0[j] : c.t0[j] * c.t0[j];
+        float m1 = full ? c.t1[j] : c.t1[j] * c.t1[j];
+        g0[j] += w0 * m0 / (a0 + kEps);
+        g1[j] += w1 * m1 / (a1 + kEps);
+      }
+    }
+    if (a.flags & OCT_LOSS_DICE) {
+      // L = mean_b(1 - 2 I/(Card+eps)); dL/dp = (-2 t/(Card+eps) + 2 I/(Card+eps)^2)/B
+      const float I = (float)a.stats[ST_DICE + b];
+      const float card = (float)a.stats[ST_DICE + a.B + b] + a.dice_eps;
+      const float k = a.gscale[OCT_LOSS_OUT_DICE] / (float)a.B;
+      const float ka = -2.f * k / card, kb = 2.f * k * I / (card * card);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g0[j] += ka * c.t0[j] + kb;
+        g1[j] += ka * c.t1[j] + kb;
+      }
+    }
+    if (a.flags & OCT_LOSS_FROM_LOGITS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dot = g0[j] * c.p0[j] + g1[j] * c.p1[j];
+        g0[j] = c.p0[j] * (g0[j] - dot);
+        g1[j] = c.p1[j] * (g1[j] - dot);
+      }
+    }
+    T* gy = reinterpret_cast<T*>(a.g_yhat);
+    VecIO<T, 8>::st(gy + off, g0);
+    VecIO<T, 8>::st(gy + off + plane, g1);
+  }
+
+  if (a.flags & OCT_LOSS_KLD) {
+    const float gk = a.gscale[OCT_LOSS_OUT_KLD] / ((float)a.B * (float)a.H * (float)a.W);
+    {
+      float g0[8], g1[8];
+      const bool stop = a.flags & OCT_LOSS_KLD_STOPGRAD;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // d/db [ b (log(b+eps) - m) ] = log(b+eps) - m + b/(b+eps)
+        g0[j] = stop ? 0.f : gk * (__logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw + c.b0[j] / (c.b0[j] + kEps));
+        g1[j] = stop ? 0.f : gk * (__logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw + c.b1[j] / (c.b1[j] + kEps));
+      }
+      T* g = reinterpret_cast<T*>(a.g_att[0]);
+      VecIO<T, 8>::st(g + off, g0);
+      VecIO<T, 8>::st(g + off + plane, g1);
+    }
+    // Box sums of the basis over 2^k x 2^k blocks; d/dq_k = -gk/sum_w * w_k/(w_k q + eps) * boxsum(b)
+    const float kq = -gk * a.inv_sumw;
+    float v1[2][4], v2[2][2], v3[2], v4[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v1[0][j] = c.b0[2 * j] + c.b0[2 * j + 1];
+      v1[1][j] = c.b1[2 * j] + c.b1[2 * j + 1];
+    }
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v1[ch][j] += __shfl_xor_sync(0xffffffffu, v1[ch][j], 2);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        v2[ch][j] = v1[ch][2 * j] + v1[ch][2 * j + 1];
+        v2[ch][j] += __shfl_xor_sync(0xffffffffu, v2[ch][j], 4);
+      }
+      v3[ch] = v2[ch][0] + v2[ch][1];
+      v3[ch] += __shfl_xor_sync(0xffffffffu, v3[ch], 8);
+      v4[ch] = v3[ch] + __shfl_xor_sync(0xffffffffu, v3[ch], 1);
+      v4[ch] += __shfl_xor_sync(0xffffffffu, v4[ch], 16);
+    }
+    if (a.n_att > 1 && (r & 1) == 0) {
+      const size_t pl = plane >> 2;
+      T* g = reinterpret_cast<T*>(a.g_att[1]) + (size_t)b * 2 * pl + (size_t)(y >> 1) * (a.W >> 1) + (x0 >> 1);
+      const float w = a.aw8[0];
+      float o[2][4];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[ch][j] = (w != 0.f) ? kq * w / (w * c.q1[ch][j] + kEps) * v1[ch][j] : 0.f;
+      VecIO<T, 4>::st(g, o[0]);
+      VecIO<T, 4>::st(g + pl, o[1]);
+    }
+    if (a.n_att > 2 && (r & 3) == 0) {
+      const size_t pl = plane >> 4;
+      T* g = reinterpret_cast<T*>(a.g_att[2]) + (size_t)b * 2 * pl + (size_t)(y >> 2) * (a.W >> 2) + (x0 >> 2);
+      const float w = a.aw8[1];
+      float o[2][2];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) o[ch][j] = (w != 0.f) ? kq * w / (w * c.q2[ch][j] + kEps) * v2[ch][j] : 0.f;
+      VecIO<T, 2>::st(g, o[0]);
+      VecIO<T, 2>::st(g + pl, o[1]);
+    }
+    if (a.n_att > 3 && (r & 7) == 0) {
+      const size_t pl = plane >> 6;
+      T* g = reinterpret_cast<T*>(a.g_att[3]) + (size_t)b * 2 * pl + (size_t)(y >> 3) * (a.W >> 3) + (x0 >> 3);
+      const float w = a.aw8[2];
+      float o0 = (w != 0.f) ? kq * w / (w * c.q3[0] + kEps) * v3[0] : 0.f;
+      float o1 = (w != 0.f) ? kq * w / (w * c.q3[1] + kEps) * v3[1] : 0.f;
+      VecIO<T, 1>::st(g, &o0);
+      VecIO<T, 1>::st(g + pl, &o1);
+    }
+    if (a.n_att > 4 && lane == 0) {
+      const size_t pl = plane >> 8;
+      T* g = reinterpret_cast<T*>(a.g_att[4]) + (size_t)b * 2 * pl + (size_t)(y >> 4) * (a.W >> 4) + (x0 >> 4);
+      const float w = a.aw8[3];
+      float o0 = (w != 0.f) ? kq * w / (w * c.q4[0] + kEps) * v4[0] : 0.f;
+      float o1 = (w != 0.f) ? kq * w / (w * c.q4[1] + kEps) * v4[1] : 0.f;
+      VecIO<T, 1>::st(g, &o0);
+      VecIO<T, 1>::st(g + pl, &o1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic path: any C <= 8, any attention sizes (torch 'nearest': src = min(floor(dst*in/out), in-1)),
+// fp32 storage.  One thread per full-resolution pixel; blockIdx.y = sample.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, int in, int out) {
+  float scale = (float)in / (float)out;
+  int s = (int)floorf((float)dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+
+struct GenericPixel {
+  float p[OCT_LOSS_MAX_CLASSES];
+  float t[OCT_LOSS_MAX_CLASSES];
+  float bs[OCT_LOSS_MAX_CLASSES];
+  float m[OCT_LOSS_MAX_CLASSES];
+};
+
+__device__ __forceinline__ void generic_load(const LossArgs& a, int b, int y, int x, GenericPixel& px) {
+  const int C = a.C;
+  const size_t plane = (size_t)a.H * a.W;
+  const size_t off = (size_t)b * C * plane + (size_t)y * a.W + x;
+  if (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+    const float* yh = reinterpret_cast<const float*>(a.yhat);
+    const float* ys = reinterpret_cast<const float*>(a.ys);
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      px.p[c] = yh[off + c * plane];
+      px.t[c] = ys[off + c * plane];
+      mx = fmaxf(mx, px.p[c]);
+    }
+    if (a.flags & OCT_LOSS_FROM_LOGITS) {
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) { px.p[c] = __expf(px.p[c] - mx); s += px.p[c]; }
+      float inv = 1.f / s;
+      for (int c = 0; c < C; ++c) px.p[c] *= inv;
+    }
+  }
+  if (a.flags & OCT_LOSS_KLD) {
+    const float* a0 = reinterpret_cast<const float*>(a.att[0]);
+    for (int c = 0; c < C; ++c) { px.bs[c] = a0[off + c * plane]; px.m[c] = 0.f; }
+    for (int k = 1; k < a.n_att; ++k) {
+      const float w = a.aw8[k - 1];
+      if (w == 0.f) continue;
+      const int sy = nearest_src(y, a.ah[k], a.H), sx = nearest_src(x, a.aw[k], a.W);
+      const size_t pl = (size_t)a.ah[k] * a.aw[k];
+      const float* q = reinterpret_cast<const float*>(a.att[k]) + (size_t)b * C * pl + (size_t)sy * a.aw[k] + sx;
+      for (int c = 0; c < C; ++c) px.m[c] += __logf(w * q[c * pl] + kEps);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_generic_fwd_kernel(const LossArgs a) {
+  constexpr int NV = 2 * OCT_LOSS_MAX_CLASSES + 6;
+  __shared__ float red[NV * 8];
+  const int b = blockIdx.y, C = a.C;
+  const int hw = a.H * a.W;
+  float acc[NV];  // n[8] S[8] kld I Card lsg lsdr lsdf
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  const bool maps = a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; maps && i < hw; i += gridDim.x * blockDim.x) {
+    const int y = i / a.W, x = i - y * a.W;
+    GenericPixel px;
+    generic_load(a, b, y, x, px);
+    const bool full = a.flags & OCT_LOSS_WPCE_FULL;
+#pragma unroll
+    for (int c = 0; c < OCT_LOSS_MAX_CLASSES; ++c) {
+      if (c < C) {
+        if (a.flags & OCT_LOSS_WPCE) {
+          float arg = full ? px.p[c] : px.p[c] * px.t[c];
+          acc[c] += px.t[c];
+          acc[8 + c] += px.t[c] * __logf(arg + kEps);
+        }
+        if (a.flags & OCT_LOSS_DICE) {
+          acc[17] += px.p[c] * px.t[c];
+          acc[18] += px.p[c] + px.t[c];
+        }
+        if (a.flags & OCT_LOSS_KLD)
+          acc[16] += px.bs[c] * (__logf(px.bs[c] + kEps) - px.m[c] * a.inv_sumw);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) ls_partial(a, acc[19], acc[20], acc[21]);
+  block_sum<NV>(acc, red);
+  if (threadIdx.x == 0) {
+    double* st = a.stats;
+    if (a.flags & OCT_LOSS_WPCE)
+      for (int c = 0; c < C; ++c) {
+        atomic_add_f64(st + ST_N + c, acc[c]);
+        atomic_add_f64(st + ST_S + c, acc[8 + c]);
+      }
+    if (a.flags & OCT_LOSS_KLD) atomic_add_f64(st + ST_KLD, acc[16]);
+    if (a.flags & OCT_LOSS_DICE) {
+      atomic_add_f64(st + ST_DICE + b, acc[17]);
+      atomic_add_f64(st + ST_DICE + a.B + b, acc[18]);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      atomic_add_f64(st + ST_LSG, acc[19]);
+      atomic_add_f64(st + ST_LSDR, acc[20]);
+      atomic_add_f64(st + ST_LSDF, acc[21]);
+    }
+  }
+  retire_block(a);
+}
+
+__global__ void __launch_bounds__(256) loss_generic_bwd_kernel(const LossArgs a) {
+  const int b = blockIdx.y, C = a.C;
+  const int hw = a.H * a.W;
+  if (blockIdx.x == 0 && blockIdx.y == 0) ls_backward(a);
+  if (!(a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD))) return;
+  const size_t plane = (size_t)hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    const int y = i / a.W, x = i - y * a.W;
+    const size_t off = (size_t)b * C * plane + (size_t)i;
+    GenericPixel px;
+    generic_load(a, b, y, x, px);
+    if (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+      float g[OCT_LOSS_MAX_CLASSES];
+      const bool full = a.flags & OCT_LOSS_WPCE_FULL;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < OCT_LOSS_MAX_CLASSES; ++c) {
+        g[c] = 0.f;
+        if (c < C) {
+          if (a.flags & OCT_LOSS_WPCE) {
+            float arg = full ? px.p[c] : px.p[c] * px.t[c];
+            float mm = full ? px.t[c] : px.t[c] * px.t[c];
+            g[c] += -a.gscale[OCT_LOSS_OUT_WPCE] * a.wpce_scale * (float)a.stats[ST_W + c] * mm / (arg + kEps);
+          }
+          if (a.flags & OCT_LOSS_DICE) {
+            const float I = (float)a.stats[ST_DICE + b];
+            const float card = (float)a.stats[ST_DICE + a.B + b] + a.dice_eps;
+            const float k = a.gscale[OCT_LOSS_OUT_DICE] / (float)a.B;
+            g[c] += -2.f * k / card * px.t[c] + 2.f * k * I / (card * card);
+          }
+          dot += g[c] * px.p[c];
+        }
+      }
+      float* gy = reinterpret_cast<float*>(a.g_yhat);
+#pragma unroll
+      for (int c = 0; c < OCT_LOSS_MAX_CLASSES; ++c)
+        if (c < C) gy[off + c * plane] = (a.flags & OCT_LOSS_FROM_LOGITS) ? px.p[c] * (g[c] - dot) : g[c];
+    }
+    if (a.flags & OCT_LOSS_KLD) {
+      const float gk = a.gscale[OCT_LOSS_OUT_KLD] / ((float)a.B * (float)hw);
+      const bool stop = a.flags & OCT_LOSS_KLD_STOPGRAD;
+      float* g0 = reinterpret_cast<float*>(a.g_att[0]);
+#pragma unroll
+      for (int c = 0; c < OCT_LOSS_MAX_CLASSES; ++c)
+        if (c < C)
+          g0[off + c * plane] =
+              stop ? 0.f : gk * (__logf(px.bs[c] + kEps) - px.m[c] * a.inv_sumw + px.bs[c] / (px.bs[c] + kEps));
+      for (int k = 1; k < a.n_att; ++k) {
+        const float w = a.aw8[k - 1];
+        if (w == 0.f) continue;
+        const int sy = nearest_src(y, a.ah[k], a.H), sx = nearest_src(x, a.aw[k], a.W);
+        const size_t pl = (size_t)a.ah[k] * a.aw[k];
+        const size_t qo = (size_t)b * C * pl + (size_t)sy * a.aw[k] + sx;
+        const float* q = reinterpret_cast<const float*>(a.att[k]) + qo;
+        float* g = reinterpret_cast<float*>(a.g_att[k]) + qo;
+        for (int c = 0; c < C; ++c)
+          atomicAdd(g + c * pl, -gk * a.inv_sumw * w / (w * q[c * pl] + kEps) * px.bs[c]);
+      }
+    }
+  }
+}
+
+bool fast_ok(const OctaveLossDesc* d) {
+  const bool maps = d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
+  if (!maps) return true;  // LS-only launches take the fast kernel with a 1x1 grid
+  if (d->C != 2 || (d->H & 15) || (d->W & 15)) return false;
+  if (d->flags & OCT_LOSS_KLD) {
+    if (d->n_att < 2 || d->n_att > OCT_LOSS_MAX_ATT) return false;
+    for (int k = 0; k < d->n_att; ++k)
+      if (d->att_h[k] != (d->H >> k) || d->att_w[k] != (d->W >> k)) return false;
+  }
+  return true;
+}
+
+int validate(const OctaveLossDesc* d) {
+  if (!d) return OCT_ERR_INVALID;
+  if (d->dtype != OCT_DTYPE_F32 && d->dtype != OCT_DTYPE_BF16) return OCT_ERR_INVALID;
+  const bool maps = d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
+  if (maps) {
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->C > OCT_LOSS_MAX_CLASSES) return OCT_ERR_INVALID;
+    if (d->B > 65535) return OCT_ERR_UNSUPPORTED;
+  }
+  if ((d->flags & OCT_LOSS_KLD) && (d->n_att < 2 || d->n_att > OCT_LOSS_MAX_ATT)) return OCT_ERR_INVALID;
+  if ((d->flags & (OCT_LOSS_LSG | OCT_LOSS_LSD)) && d->n_fake <= 0) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_LSD) && d->n_real <= 0) return OCT_ERR_INVALID;
+  if (!fast_ok(d) && d->dtype != OCT_DTYPE_F32) return OCT_ERR_UNSUPPORTED;
+  return OCT_OK;
+}
+
+void fill_args(LossArgs& a, const OctaveLossDesc* d, const void* yhat, const void* ys, const void* const* att,
+               const float* d_real, const float* d_fake, void* stats) {
+  a.yhat = yhat; a.ys = ys; a.d_real = d_real; a.d_fake = d_fake;
+  a.stats = reinterpret_cast<double*>(stats);
+  a.B = d->B; a.C = d->C; a.H = d->H; a.W = d->W; a.flags = d->flags;
+  a.n_att = (d->flags & OCT_LOSS_KLD) ? d->n_att : 0;
+  for (int k = 0; k < OCT_LOSS_MAX_ATT; ++k) {
+    a.att[k] = (att && k < a.n_att) ? att[k] : nullptr;
+    a.ah[k] = d->att_h[k]; a.aw[k] = d->att_w[k];
+    a.g_att[k] = nullptr;
+  }
+  for (int k = 0; k < OCT_LOSS_MAX_ATT - 1; ++k) a.aw8[k] = (k + 1 < a.n_att) ? d->att_weight[k] : 0.f;
+  a.inv_sumw = d->sum_weights != 0.f ? 1.f / d->sum_weights : 0.f;
+  a.wpce_scale = d->wpce_scale; a.dice_eps = d->dice_eps;
+  a.n_real = d->n_real; a.n_fake = d->n_fake;
+  a.out = nullptr; a.gscale = nullptr; a.g_yhat = nullptr; a.g_real = nullptr; a.g_fake = nullptr;
+}
+
+}  // namespace
+
+extern "C" size_t octave_loss_stats_bytes(const OctaveLossDesc* d) {
+  if (!d) return 0;
+  int B = d->B > 0 ? d->B : 0;
+  return (size_t)(ST_DICE + 2 * B) * sizeof(double);
+}
+
+extern "C" int octave_loss_uses_fast_path(const OctaveLossDesc* d) { return d && fast_ok(d) ? 1 : 0; }
+
+extern "C" int octave_loss_fwd(const OctaveLossDesc* d, const void* yhat, const void* ys, const void* const* att,
+                               const float* d_real, const float* d_fake, void* stats, float* out, void* stream) {
+  int rc = validate(d);
+  if (rc != OCT_OK) return rc;
+  if (!stats || !out) return OCT_ERR_INVALID;
+  if ((d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) && (!yhat || !ys)) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_KLD) && !att) return OCT_ERR_INVALID;
+  if ((d->flags & (OCT_LOSS_LSG | OCT_LOSS_LSD)) && !d_fake) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_LSD) && !d_real) return OCT_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  LossArgs a;
+  fill_args(a, d, yhat, ys, att, d_real, d_fake, stats);
+  a.out = out;
+  if (cudaMemsetAsync(stats, 0, octave_loss_stats_bytes(d), s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  const bool maps = d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
+  if (fast_ok(d)) {
+    dim3 grid(1, 1);
+    if (maps) grid = dim3(((d->H >> 4) * (d->W >> 4) + 7) / 8, d->B);
+    if (d->dtype == OCT_DTYPE_F32) loss_fast_fwd_kernel<float><<<grid, 256, 0, s>>>(a);
+    else loss_fast_fwd_kernel<bf16><<<grid, 256, 0, s>>>(a);
+  } else {
+    int gx = (d->H * d->W + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    loss_generic_fwd_kernel<<<dim3(gx, d->B), 256, 0, s>>>(a);
+  }
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_loss_bwd(const OctaveLossDesc* d, const void* yhat, const void* ys, const void* const* att,
+                               const float* d_real, const float* d_fake, const void* stats, const float* gscale,
+                               void* g_yhat, void* const* g_att, float* g_real, float* g_fake, void* stream) {
+  int rc = validate(d);
+  if (rc != OCT_OK) return rc;
+  if (!stats || !gscale) return OCT_ERR_INVALID;
+  if ((d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) && (!yhat || !ys || !g_yhat)) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_KLD) && (!att || !g_att)) return OCT_ERR_INVALID;
+  if ((d->flags & (OCT_LOSS_LSG | OCT_LOSS_LSD)) && (!d_fake || !g_fake)) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_LSD) && (!d_real || !g_real)) return OCT_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  LossArgs a;
+  fill_args(a, d, yhat, ys, att, d_real, d_fake, const_cast<void*>(stats));
+  a.gscale = gscale; a.g_yhat = g_yhat; a.g_real = g_real; a.g_fake = g_fake;
+  if (d->flags & OCT_LOSS_KLD)
+    for (int k = 0; k < a.n_att; ++k) {
+      if (!g_att[k]) return OCT_ERR_INVALID;
+      a.g_att[k] = g_att[k];
+    }
+  const bool maps = d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
+  if (fast_ok(d)) {
+    dim3 grid(1, 1);
+    if (maps) grid = dim3(((d->H >> 4) * (d->W >> 4) + 7) / 8, d->B);
+    if (d->dtype == OCT_DTYPE_F32) loss_fast_bwd_kernel<float><<<grid, 256, 0, s>>>(a);
+    else loss_fast_bwd_kernel<bf16><<<grid, 256, 0, s>>>(a);
+  } else {
+    // coarse-level gradients are accumulated with atomics: zero them first
+    if (d->flags & OCT_LOSS_KLD)
+      for (int k = 1; k < a.n_att; ++k) {
+        size_t bytes = (size_t)d->B * d->C * d->att_h[k] * d->att_w[k] * sizeof(float);
+        if (cudaMemsetAsync(a.g_att[k], 0, bytes, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+      }
+    int gx = (d->H * d->W + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    loss_generic_bwd_kernel<<<dim3(gx, d->B), 256, 0, s>>>(a);
+  }
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
