@@ -90,6 +90,41 @@ int octave_loss_bwd(const OctaveLossDesc* d, const void* yhat, const void* ys,
                     const void* stats, const float* gscale, void* g_yhat, void* const* g_att,
                     float* g_real, float* g_fake, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K1/K2/K3 — convolutions.  Activations NHWC; a tensor argument is a *channel view*: base pointer,
+ * `ld` = elements per pixel of the underlying buffer, `coff` = first channel of the view (this is how the
+ * skip-concat of compose.py:141,155,162,169 is fused: producers write straight into channel slices).
+ * Replaces nn.Conv2d / nn.ConvTranspose2d inside
+ *   ResNet deep stem, Bottleneck, SplAtConv2d, ResNestDecoder, Upsampling  architectures/extra/resnest.py:18-138,170-267,326-334
+ *   DiscriminatorBlock convs                                              architectures/discriminator/blocks.py:46-50,91-109
+ * ---------------------------------------------------------------------------------------------- */
+#define OCT_CONV_MODE_CONV 0   /* Conv2d, stride 1 (tc path) or general (direct path) */
+#define OCT_CONV_MODE_CONVT 1  /* ConvTranspose2d k=2 s=2: GEMM + 2x2 pixel-shuffle store */
+
+typedef struct OctaveConvDesc {
+  int32_t B, H, W;        /* input pixel grid */
+  int32_t cin, cout, groups;
+  int32_t ksize;          /* square kernel (tc path: 1 or 3, padding ksize/2, stride 1) */
+  int32_t stride, pad;    /* direct path only; the tc path requires stride 1, pad ksize/2 */
+  int32_t x_ld, x_coff;   /* input view */
+  int32_t y_ld, y_coff;   /* output view */
+  int32_t Hout, Wout;     /* output pixel grid (ConvT: 2H,2W or cropped, compose.py:142-147) */
+  int32_t mode;           /* OCT_CONV_MODE_* */
+  int32_t relu;           /* fuse ReLU into the epilogue */
+  int32_t in_dtype;       /* direct path: storage type of x / w */
+  int32_t out_dtype;      /* storage type of y */
+} OctaveConvDesc;
+
+/* tcgen05 path (bf16 in, fp32 accumulate).  `wpack` is bf16 [taps][Cout][Cin/groups] (ConvT: [4*Cout][Cin],
+ * row = (i*2+j)*Cout + co).  Data gradient = the same entry point with the dgrad pack and cin/cout swapped. */
+int octave_conv_tc_supported(const OctaveConvDesc* d);
+int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
+                       void* stream);
+/* dwpack: fp32 [taps][Cout][Cin/groups], overwritten.  x = forward input view, dy = output-gradient view
+ * (x_* / y_* of the descriptor). */
+int octave_conv_tc_wgrad_supported(const OctaveConvDesc* d);
+int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dwpack, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,3 +97,29 @@ lib.octave_loss_fwd.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _
 lib.octave_loss_bwd.restype = C.c_int
 lib.octave_loss_bwd.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
                                 C.POINTER(_vp), _vp, _vp, _vp]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32), ("groups", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("x_ld", C.c_int32), ("x_coff", C.c_int32),
+        ("y_ld", C.c_int32), ("y_coff", C.c_int32),
+        ("Hout", C.c_int32), ("Wout", C.c_int32),
+        ("mode", C.c_int32), ("relu", C.c_int32),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+    ]
+
+
+CONV_MODE_CONV = 0
+CONV_MODE_CONVT = 1
+
+lib.octave_conv_tc_supported.restype = C.c_int
+lib.octave_conv_tc_supported.argtypes = [C.POINTER(ConvDesc)]
+lib.octave_conv_tc_fwd.restype = C.c_int
+lib.octave_conv_tc_fwd.argtypes = [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]
+lib.octave_conv_tc_wgrad_supported.restype = C.c_int
+lib.octave_conv_tc_wgrad_supported.argtypes = [C.POINTER(ConvDesc)]
+lib.octave_conv_tc_wgrad.restype = C.c_int
+lib.octave_conv_tc_wgrad.argtypes = [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]

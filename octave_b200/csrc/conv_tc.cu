@@ -1,0 +1,568 @@
+// K1/K2/K3 — implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), bf16 in,
+// fp32 accumulate.  Replaces the stride-1 3x3 / 1x1 Conv2d and the k2s2 ConvTranspose2d of
+//   ResNestDecoder / SplAtConv2d / Bottleneck / Upsampling   /root/reference/architectures/extra/resnest.py:18-138,170-267
+// (forward, data-gradient and weight-gradient).
+//
+// Formulation.  Activations are NHWC bf16.  The GEMM M dimension runs over output pixels: one CTA owns a
+// TW x TH spatial patch of one image (TW*TH <= 128 rows of a 128-row UMMA tile).  For each filter tap the A
+// operand is the same patch shifted by the tap offset, fetched by ONE 4-D TMA box load (channels, w, h, n)
+// whose out-of-bounds elements are zero-filled by the hardware => padding costs nothing and there is no
+// im2col buffer.  A box lands in shared memory as [pixel][BK channels] rows of 128 B (64 B for BK=32) with
+// the matching TMA/UMMA swizzle, i.e. exactly the canonical K-major UMMA operand.  Weights are pre-packed
+// [tap][Cout][Cin_g] (K-major B operand) and fetched by a 3-D TMA box.  Accumulators live in TMEM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one
+// lane), warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> bf16/fp32 -> global).  A STAGES-deep mbarrier
+// ring couples producer and MMA; tcgen05.commit releases stages and publishes the accumulator.
+//
+// Weight gradient: dW[tap][co][ci] = sum_pixels dy[p][co] * x[p + tap][ci] is a GEMM whose K dimension is
+// the pixel index, so both operands are MN-major views of the very same TMA boxes; partial sums over
+// pixel-tile slices are reduced with fp32 red.global.add.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/octave_b200.h"
+
+namespace {
+
+constexpr int kThreads = 192;
+
+struct ConvTcParams {
+  int taps;
+  int tap_dh[9], tap_dw[9];
+  int kchunks;   // Cin_g / BK
+  int cin_g, cout_g;
+  int tiles_w, tiles_h, TW, TH;
+  int H, W;      // extent of the pixel grid the GEMM M dimension runs over
+  // output addressing: pixel (n, oh, ow) -> out + ((n*Hout + oh)*Wout + ow)*ldc + c_off + channel
+  void* out;
+  long long ldc;
+  int c_off, Hout, Wout;
+  int scatter;       // 1: ConvTranspose k2s2 — GEMM column n = tap*cout_total + co, pixel (2h+i, 2w+j)
+  int cout_total;    // channels per tap in scatter mode
+  const float* bias;
+  int relu, out_f32;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB,
+                                                          const ConvTcParams p) {
+  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SWZ = BK * 2;  // bytes per smem row = swizzle span
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  // tile coordinates
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int img = blockIdx.x / tiles_per_img;
+  const int trem = blockIdx.x - img * tiles_per_img;
+  const int th_i = trem / p.tiles_w;
+  const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+  const int n0 = blockIdx.y * BN;
+  const int g = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    tc::mbar_init(tc::smem_u32(&acc_bar), 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async();
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_slot));
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int total_k = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * SWZ + B_BYTES);
+      for (int it = 0; it < total_k; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = tc::smem_u32(&full_bar[s]);
+        tc::mbar_arrive_expect_tx(fb, tx_bytes);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        tc::tma_load_4d(sa, &tmA, fb, g * p.cin_g + kc * BK, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
+        tc::tma_load_3d(sa + A_BYTES, &tmB, fb, kc * BK, g * p.cout_g + n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 0, 0);
+      for (int it = 0; it < total_k; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
+        tc::fence_after_sync();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint64_t da = tc::umma_smem_desc(sa, SWZ, 16);
+        const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, SWZ, 16);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          tc::umma_bf16(tmem_base, tc::umma_desc_advance(da, k * 32), tc::umma_desc_advance(db, k * 32), idesc,
+                        (it | k) != 0);
+        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+      }
+      tc::umma_commit(tc::smem_u32(&acc_bar));
+    }
+  } else {
+    // ---- epilogue: TMEM lane quarter q <-> GEMM rows [32q, 32q+32)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int th = r / p.TW, tw = r - th * p.TW;
+    const int h = h0 + th, w = w0 + tw;
+    bool valid = (r < p.TW * p.TH) && (h < p.H) && (w < p.W);
+    int oh = h, ow = w, cbase = g * p.cout_g + n0;
+    if (p.scatter) {
+      const int tap = cbase / p.cout_total;
+      cbase -= tap * p.cout_total;
+      oh = 2 * h + (tap >> 1);
+      ow = 2 * w + (tap & 1);
+      valid = valid && (oh < p.Hout) && (ow < p.Wout);
+    }
+    const long long pix = ((long long)img * p.Hout + oh) * p.Wout + ow;
+    tc::mbar_wait(tc::smem_u32(&acc_bar), 0);
+    tc::fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int nvalid = min(BN, p.cout_g - n0);  // columns of this tile that exist
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(taddr + c0, v);
+      tc::tmem_ld_wait();
+      if (valid && c0 < nvalid) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          f[i] = __uint_as_float(v[i]);
+          if (p.bias) f[i] += __ldg(p.bias + cbase + c0 + i);
+          if (p.relu) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + pix * p.ldc + p.c_off + cbase + c0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldc + p.c_off + cbase + c0;
+          uint4 u0, u1;
+          u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
+          u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
+          u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
+          u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
+          *reinterpret_cast<uint4*>(o) = u0;
+          *reinterpret_cast<uint4*>(o + 8) = u1;
+        }
+      }
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient kernel.  D[128 x BN] (rows = output channels, cols = input channels of one tap)
+// accumulates over the pixel tiles of this CTA's slice; operands are MN-major.
+// ---------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int tap_dh, tap_dw_unused;  // (kept for alignment)
+  int taps;
+  int tap_dhs[9], tap_dws[9];
+  int cin_g, cout_g;
+  int tiles_w, tiles_h, TW, TH, B;
+  int n_ci_tiles;    // Cin_g tiles of BN
+  int tiles_per_cta; // pixel tiles handled by one CTA (split-K slice)
+  int total_tiles;   // B * tiles_w * tiles_h
+  float* dw;         // [taps][Cout][Cin_g] fp32, pre-zeroed
+  int cout_total;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                                const __grid_constant__ CUtensorMap tmX,
+                                                                const WgradParams p) {
+  constexpr int CHUNK_BYTES = 128 * 128;             // one [128 pixel][64 ch] box region
+  constexpr int A_BYTES = 2 * CHUNK_BYTES;           // 128 output channels
+  constexpr int B_BYTES = (BN / 64) * CHUNK_BYTES;   // BN input channels
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const int co_tile = blockIdx.y / p.n_ci_tiles, ci_tile = blockIdx.y - co_tile * p.n_ci_tiles;
+  const int co0 = co_tile * 128, ci0 = ci_tile * BN;
+  const int tap = blockIdx.z % p.taps, g = blockIdx.z / p.taps;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(t_begin + p.tiles_per_cta, p.total_tiles);
+  const int n_iter = t_end - t_begin;
+  const int rows = p.TW * p.TH;            // pixel rows written by one box
+  const int ksteps = (rows + 15) >> 4;     // UMMA K = 16 pixels
+
+  // Rows [rows, 16*ksteps) of every box region are read by the MMA but never written by TMA: zero them.
+  {
+    uint8_t* base = smem_raw + (smem_base - tc::smem_u32(smem_raw));
+    const int regions = STAGES * (STAGE_BYTES / CHUNK_BYTES);
+    const int tail_bytes = (ksteps * 16 - rows) * 128;
+    for (int rgn = 0; rgn < regions; ++rgn) {
+      uint8_t* q = base + rgn * CHUNK_BYTES + rows * 128;
+      for (int i = threadIdx.x * 16; i < tail_bytes; i += kThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    tc::mbar_init(tc::smem_u32(&acc_bar), 1);
+    tc::fence_barrier_init();
+    tc::tma_prefetch_desc(&tmDY);
+    tc::tma_prefetch_desc(&tmX);
+  }
+  tc::fence_proxy_async();  // generic-proxy zero fill above must be visible to the tensor-core (async) proxy
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_slot));
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  if (n_iter <= 0) {  // uniform across the CTA
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    return;
+  }
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  // number of 64-channel boxes that exist on each side (the rest of the 128 x BN tile is never stored)
+  const int a_boxes = min(2, (p.cout_g - co0 + 63) / 64);
+  const int b_boxes = min(BN / 64, (p.cin_g - ci0 + 63) / 64);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(rows * 128 * (a_boxes + b_boxes));
+      const int dh = p.tap_dhs[tap], dw = p.tap_dws[tap];
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = tc::smem_u32(&full_bar[s]);
+        tc::mbar_arrive_expect_tx(fb, tx_bytes);
+        const int t = t_begin + it;
+        const int img = t / tiles_per_img;
+        const int trem = t - img * tiles_per_img;
+        const int th_i = trem / p.tiles_w;
+        const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        for (int j = 0; j < a_boxes; ++j)
+          tc::tma_load_4d(sa + j * CHUNK_BYTES, &tmDY, fb, g * p.cout_g + co0 + 64 * j, w0, h0, img);
+        for (int j = 0; j < b_boxes; ++j)
+          tc::tma_load_4d(sa + A_BYTES + j * CHUNK_BYTES, &tmX, fb, g * p.cin_g + ci0 + 64 * j, w0 + dw, h0 + dh, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 1, 1);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
+        tc::fence_after_sync();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint64_t da = tc::umma_smem_desc(sa, 128, CHUNK_BYTES);
+        const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, 128, CHUNK_BYTES);
+        for (int k = 0; k < ksteps; ++k)
+          tc::umma_bf16(tmem_base, tc::umma_desc_advance(da, k * 2048), tc::umma_desc_advance(db, k * 2048), idesc,
+                        (it | k) != 0);
+        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+      }
+      tc::umma_commit(tc::smem_u32(&acc_bar));
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // output channel within the tile
+    const bool valid = (co0 + r) < p.cout_g;
+    tc::mbar_wait(tc::smem_u32(&acc_bar), 0);
+    tc::fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* o = p.dw + ((long long)tap * p.cout_total + g * p.cout_g + co0 + r) * p.cin_g + ci0;
+    const int nvalid = min(BN, p.cin_g - ci0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(taddr + c0, v);
+      tc::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < nvalid) atomicAdd(o + c0 + i, __uint_as_float(v[i]));
+      }
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// NHWC activation view -> 4-D map (C, W, H, B); box (box_c, TW, TH, 1).
+bool make_act_map(CUtensorMap* m, const void* base, int C_extent, int W, int H, int B, long long ld, int box_c, int TW,
+                  int TH, int swizzle_bytes) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C_extent, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * W, (cuuint64_t)ld * 2 * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// packed weights [taps][rows][K] -> 3-D map (K, rows, taps); box (BK, BN, 1).
+bool make_w_map(CUtensorMap* m, const void* base, int K, int rows, int taps, int BK, int BN, int swizzle_bytes) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * rows};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// Pick the spatial patch TW x TH (<= 128 pixels, TW,TH <= 256) that wastes the fewest UMMA rows.
+void pick_patch(int H, int W, int* TW, int* TH) {
+  double best = -1.0;
+  int bw = 1, bh = 1;
+  for (int tw = 1; tw <= (W < 128 ? W : 128); ++tw) {
+    int th = 128 / tw;
+    if (th > H) th = H;
+    if (th > 256) th = 256;
+    long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    double eff = (double)H * W / ((double)tiles * 128.0);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
+      best = eff; bw = tw; bh = th;
+    }
+  }
+  *TW = bw; *TH = bh;
+}
+
+template <int BN, int BK, int STAGES>
+int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return OCT_ERR_LAUNCH;
+    attr_done = true;
+  }
+  conv_tc_kernel<BN, BK, STAGES><<<grid, kThreads, smem, s>>>(tmA, tmB, p);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+template <int BN, int STAGES>
+int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int smem = STAGES * (2 + BN / 64) * 128 * 128 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return OCT_ERR_LAUNCH;
+    attr_done = true;
+  }
+  conv_tc_wgrad_kernel<BN, STAGES><<<grid, kThreads, smem, s>>>(tmDY, tmX, p);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+int validate_conv(const OctaveConvDesc* d) {
+  if (!d) return OCT_ERR_INVALID;
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->cin <= 0 || d->cout <= 0 || d->groups <= 0) return OCT_ERR_INVALID;
+  if (d->cin % d->groups || d->cout % d->groups) return OCT_ERR_INVALID;
+  if (d->ksize != 1 && d->ksize != 3) return OCT_ERR_UNSUPPORTED;
+  if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return OCT_ERR_UNSUPPORTED;
+  return OCT_OK;
+}
+
+}  // namespace
+
+extern "C" int octave_conv_tc_supported(const OctaveConvDesc* d) {
+  if (validate_conv(d) != OCT_OK) return 0;
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  if (d->mode == OCT_CONV_MODE_CONVT && (d->groups != 1 || d->ksize != 1)) return 0;
+  if (cin_g % 32) return 0;                 // K chunk of 64 (SW128) or 32 (SW64)
+  if (cout_g % 16) return 0;                // epilogue vector width
+  if (d->groups > 1 && cout_g % 32) return 0;
+  return 1;
+}
+
+extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
+                                  void* stream) {
+  int rc = validate_conv(d);
+  if (rc != OCT_OK) return rc;
+  if (!octave_conv_tc_supported(d)) return OCT_ERR_UNSUPPORTED;
+  if (!x || !wpack || !y) return OCT_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  const bool convt = d->mode == OCT_CONV_MODE_CONVT;
+  const int n_cols_g = convt ? 4 * d->cout : cout_g;  // GEMM N per group
+  ConvTcParams p{};
+  p.taps = d->ksize * d->ksize;
+  for (int t = 0; t < p.taps; ++t) {
+    p.tap_dh[t] = d->ksize == 3 ? t / 3 - 1 : 0;
+    p.tap_dw[t] = d->ksize == 3 ? t % 3 - 1 : 0;
+  }
+  const int BK = (cin_g % 64 == 0) ? 64 : 32;
+  p.kchunks = cin_g / BK;
+  p.cin_g = cin_g;
+  p.cout_g = n_cols_g;
+  // 1x1: flatten all pixels into one long row so that every tile is full
+  int H = d->H, W = d->W, B = d->B;
+  const bool flat = d->ksize == 1 && !convt;
+  if (flat) { W = d->B * d->H * d->W; H = 1; B = 1; }
+  pick_patch(H, W, &p.TW, &p.TH);
+  p.tiles_w = (W + p.TW - 1) / p.TW;
+  p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.H = H; p.W = W;
+  p.out = y; p.ldc = d->y_ld; p.c_off = d->y_coff;
+  p.Hout = flat ? 1 : d->Hout; p.Wout = flat ? W : d->Wout;
+  p.scatter = convt ? 1 : 0; p.cout_total = d->cout;
+  p.bias = bias; p.relu = d->relu; p.out_f32 = d->out_dtype == OCT_DTYPE_F32;
+  int BN = 128;
+  if (n_cols_g % 128) BN = (n_cols_g % 64 == 0) ? 64 : ((n_cols_g % 32 == 0) ? 32 : 16);
+  if (convt && d->cout % BN) BN = (d->cout % 64 == 0) ? 64 : 32;  // a column tile must stay inside one tap
+  if (convt && d->cout % BN) return OCT_ERR_UNSUPPORTED;
+  CUtensorMap tmA, tmB;
+  const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
+  if (!make_act_map(&tmA, xb, d->cin, W, H, B, d->x_ld, BK, p.TW, p.TH, BK * 2)) return OCT_ERR_LAUNCH;
+  if (!make_w_map(&tmB, wpack, cin_g, d->groups * n_cols_g, p.taps, BK, BN, BK * 2)) return OCT_ERR_LAUNCH;
+  dim3 grid(p.tiles_w * p.tiles_h * B, (n_cols_g + BN - 1) / BN, d->groups);
+  if (BK == 64) {
+    switch (BN) {
+      case 128: return launch_fwd<128, 64, 4>(tmA, tmB, p, grid, s);
+      case 64: return launch_fwd<64, 64, 4>(tmA, tmB, p, grid, s);
+      case 32: return launch_fwd<32, 64, 4>(tmA, tmB, p, grid, s);
+      default: return launch_fwd<16, 64, 4>(tmA, tmB, p, grid, s);
+    }
+  } else {
+    switch (BN) {
+      case 128: return launch_fwd<128, 32, 4>(tmA, tmB, p, grid, s);
+      case 64: return launch_fwd<64, 32, 4>(tmA, tmB, p, grid, s);
+      case 32: return launch_fwd<32, 32, 4>(tmA, tmB, p, grid, s);
+      default: return launch_fwd<16, 32, 4>(tmA, tmB, p, grid, s);
+    }
+  }
+}
+
+extern "C" int octave_conv_tc_wgrad_supported(const OctaveConvDesc* d) {
+  if (validate_conv(d) != OCT_OK) return 0;
+  if (d->mode != OCT_CONV_MODE_CONV) return 0;
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  // 64-channel TMA boxes on both operands; a box may not run past the tensor's channel extent
+  if (d->cin < 64 || d->cout < 64) return 0;
+  if (cin_g % 64 || cout_g % 64) return 0;
+  return 1;
+}
+
+extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dwpack,
+                                    void* stream) {
+  int rc = validate_conv(d);
+  if (rc != OCT_OK) return rc;
+  if (!octave_conv_tc_wgrad_supported(d)) return OCT_ERR_UNSUPPORTED;
+  if (!x || !dy || !dwpack) return OCT_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  WgradParams p{};
+  p.taps = d->ksize * d->ksize;
+  for (int t = 0; t < p.taps; ++t) {
+    p.tap_dhs[t] = d->ksize == 3 ? t / 3 - 1 : 0;
+    p.tap_dws[t] = d->ksize == 3 ? t % 3 - 1 : 0;
+  }
+  p.cin_g = cin_g; p.cout_g = cout_g; p.cout_total = d->cout;
+  int H = d->H, W = d->W, B = d->B;
+  if (d->ksize == 1) { W = d->B * d->H * d->W; H = 1; B = 1; }
+  pick_patch(H, W, &p.TW, &p.TH);
+  p.tiles_w = (W + p.TW - 1) / p.TW;
+  p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.B = B;
+  p.total_tiles = B * p.tiles_w * p.tiles_h;
+  const int BN = (cin_g % 256 == 0) ? 256 : ((cin_g % 128 == 0) ? 128 : 64);
+  p.n_ci_tiles = (cin_g + BN - 1) / BN;
+  const int n_co_tiles = (cout_g + 127) / 128;
+  const int out_tiles = n_co_tiles * p.n_ci_tiles * p.taps * d->groups;
+  int sms = octave_sm_count();
+  if (sms <= 0) sms = 148;
+  int split = (2 * sms + out_tiles - 1) / out_tiles;
+  if (split < 1) split = 1;
+  if (split > p.total_tiles) split = p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + split - 1) / split;
+  split = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.dw = dwpack;
+  CUtensorMap tmDY, tmX;
+  const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
+  const bf16* dyb = reinterpret_cast<const bf16*>(dy) + d->y_coff;
+  if (!make_act_map(&tmX, xb, d->cin, W, H, B, d->x_ld, 64, p.TW, p.TH, 128)) return OCT_ERR_LAUNCH;
+  if (!make_act_map(&tmDY, dyb, d->cout, W, H, B, d->y_ld, 64, p.TW, p.TH, 128)) return OCT_ERR_LAUNCH;
+  if (cudaMemsetAsync(dwpack, 0, (size_t)p.taps * d->cout * cin_g * sizeof(float), s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  dim3 grid(split, n_co_tiles * p.n_ci_tiles, p.taps * d->groups);
+  switch (BN) {
+    case 256: return launch_wgrad<256, 2>(tmDY, tmX, p, grid, s);
+    case 128: return launch_wgrad<128, 3>(tmDY, tmX, p, grid, s);
+    default: return launch_wgrad<64, 4>(tmDY, tmX, p, grid, s);
+  }
+}
