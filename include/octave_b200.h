@@ -113,6 +113,8 @@ typedef struct OctaveConvDesc {
   int32_t relu;           /* fuse ReLU into the epilogue */
   int32_t in_dtype;       /* direct path: storage type of x / w */
   int32_t out_dtype;      /* storage type of y */
+  int32_t accumulate;     /* y += result (fwd/dgrad); dw += result (wgrad) instead of overwrite */
+  int32_t real_groups;    /* wgrad: groups of the torch weight when `groups` was merged into dense groups (0 = groups) */
 } OctaveConvDesc;
 
 /* tcgen05 path (bf16 in, fp32 accumulate).  `wpack` is bf16 [taps][Cout][Cin/groups] (ConvT: [4*Cout][Cin],
@@ -120,10 +122,134 @@ typedef struct OctaveConvDesc {
 int octave_conv_tc_supported(const OctaveConvDesc* d);
 int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
                        void* stream);
-/* dwpack: fp32 [taps][Cout][Cin/groups], overwritten.  x = forward input view, dy = output-gradient view
- * (x_* / y_* of the descriptor). */
+/* dw: fp32 gradient in the torch parameter layout ([Cout][Cin/real_groups][k][k]; ConvT: [Cin][Cout][2][2]),
+ * overwritten unless `accumulate`.  x = forward input view, dy = output-gradient view (x_* / y_* of the descriptor;
+ * for ConvT dy is the space-to-depth view with 4*cout channels). */
 int octave_conv_tc_wgrad_supported(const OctaveConvDesc* d);
-int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dwpack, void* stream);
+int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dw, void* stream);
+
+/* CUDA-core direct convolution (any k / stride / pad / groups, any channel count; fp32 or bf16 storage, fp32
+ * accumulate; weights fp32 in the torch layout).  Used for the fp32 mode, the 3-channel stem conv
+ * (resnest.py:327) and the narrow discriminator convs (discriminator/blocks.py:46-50,91-109).
+ * d->relu selects the fused activation: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 sigmoid, 4 tanh. */
+int octave_conv_direct_fwd(const OctaveConvDesc* d, const void* x, const float* w, const float* bias, void* y,
+                           void* stream);
+int octave_conv_direct_dgrad(const OctaveConvDesc* d, const void* dy, const float* w, void* dx, void* stream);
+/* dw overwritten unless d->accumulate; dbias nullable */
+int octave_conv_direct_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dw, float* dbias,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4-K8 — bandwidth-bound glue.  An OctaveAct is an NHWC channel view: pixel p, channel c lives at
+ * data + (p*ld + coff + c) elements.  C must be a multiple of 8 (16-byte vectors) unless stated.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OctaveAct {
+  void* data;
+  int32_t B, H, W, C;
+  int32_t ld, coff;
+  int32_t dtype; /* OCT_DTYPE_* */
+} OctaveAct;
+
+/* dy <- dy * act'(y) for the activations fused by conv_direct_fwd (y is the stored activation output) */
+int octave_act_bwd(const OctaveAct* y, const OctaveAct* dy, int32_t act, const OctaveAct* dz, void* stream);
+
+/* K4 BatchNorm2d (train: batch statistics + running-stat update; eval: running stats) and K7 residual.
+ *   nn.BatchNorm2d at resnest.py:25,35,86,101-105,182,224,338,394; residual add + ReLU resnest.py:42,264-265 */
+int octave_chan_stats(const OctaveAct* x, double* sums /* [2C]: sum, sum of squares; overwritten */, void* stream);
+int octave_bn_prepare(int32_t C, double count, const double* sums, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked, float eps, float momentum,
+                      int32_t training, float* ab /* [2C] scale, shift */, float* mean_invstd /* [2C] */, void* stream);
+/* y = act(x*a[c] + b[c] + res); ab NULL => identity; gap (nullable, fp32 [B][C/2], pre-zeroed by the callee):
+ * gap[b][c % (C/2)] += sum_pixels y  — the radix-sum + global-average-pool of resnest.py:106-116. */
+int octave_affine_act(const OctaveAct* x, const float* ab, const OctaveAct* res, int32_t relu, const OctaveAct* y,
+                      float* gap, void* stream);
+/* dz = dy * (mask > 0) (mask nullable).  sums2[c] = sum dz, sums2[C+c] = sum dz * xhat. */
+int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* x, const float* mean_invstd,
+                         double* sums2, void* stream);
+/* dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or gamma*invstd*dz (eval, mean_invstd then
+ * holds the running statistics).  dgamma = sum dz*xhat, dbeta = sum dz (nullable) are overwritten. */
+int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* x, const float* mean_invstd,
+                        const float* gamma, const double* sums2, int32_t training, const OctaveAct* dx, float* dgamma,
+                        float* dbeta, void* stream);
+/* dst += src (same shape); used where gradients of two branches merge. */
+int octave_add_inplace(const OctaveAct* dst, const OctaveAct* src, void* stream);
+/* dst = src * (mask > 0) */
+int octave_relu_bwd(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* dx, void* stream);
+
+/* K5 split-attention (SplAtConv2d.forward resnest.py:106-138), radix 2.  U has 2C channels, out has C.
+ *   out[p][c] = att[b][c]*U[p][c] + att[b][C+c]*U[p][C+c]  (+ReLU for the decoder, resnest.py:29) */
+int octave_splat_combine(const OctaveAct* U, const float* att /* [B][2C] */, int32_t relu, const OctaveAct* out,
+                         void* stream);
+/* datt[b][r*C+c] = sum_p dout[p][c]*(mask[p][c]>0)*U[p][r*C+c]  (overwritten) */
+int octave_splat_bwd_reduce(const OctaveAct* dout, const OctaveAct* mask, const OctaveAct* U, float* datt, void* stream);
+/* dU[p][r*C+c] = att[b][r*C+c]*dout[p][c]*(mask>0) + dgap[b][c]*gap_scale */
+int octave_splat_bwd_du(const OctaveAct* dout, const OctaveAct* mask, const float* att, const float* dgap,
+                        float gap_scale, const OctaveAct* dU, void* stream);
+
+/* K6 pools (NHWC).  kind 0: MaxPool2d; 1: AvgPool2d.  Exact torch semantics incl. ceil_mode and
+ * count_include_pad (resnest.py:340 maxpool 3/2/1; :189 avd AvgPool 3/s/1; :383 shortcut AvgPool s/s ceil, no pad count). */
+typedef struct OctavePoolDesc {
+  int32_t kind, k, stride, pad, ceil_mode, count_include_pad;
+} OctavePoolDesc;
+int octave_pool_out_size(const OctavePoolDesc* p, int32_t in);
+/* argmax: uint8 [B][Ho][Wo][C] (max pool only; nullable for avg) */
+int octave_pool_fwd(const OctavePoolDesc* p, const OctaveAct* x, const OctaveAct* y, uint8_t* argmax, void* stream);
+int octave_pool_bwd(const OctavePoolDesc* p, const OctaveAct* dy, const uint8_t* argmax, const OctaveAct* dx,
+                    void* stream);
+
+/* K8 pointwise heads: 1x1 conv C -> K (K <= 8) with bias, emitting NCHW-planar fp32 maps.
+ *   mode 0 (linear): out = W x + b                      — ResnestUNet.fc, compose.py:79,181
+ *   mode 1 (gate)  : y_hat = softmax(W x + b); gated = x * sum_{k>=1} y_hat_k; out = y_hat
+ *                                                       — AdversarialAttentionGate.forward, segmentor/blocks.py:38-46 */
+int octave_head_fwd(const OctaveAct* x, const float* w /* [K][C] */, const float* b /* [K] */, int32_t K, int32_t mode,
+                    float* out /* [B][K][H][W] */, const OctaveAct* gated /* mode 1 */, void* stream);
+/* dout nullable (no gradient reached the map).  dlogits: fp32 [B][K][H][W] scratch, overwritten (input of head_wgrad). */
+int octave_head_bwd(const OctaveAct* x, const float* w, const float* b, int32_t K, int32_t mode, const float* dout,
+                    const OctaveAct* dgated, const OctaveAct* dx, float* dlogits, void* stream);
+int octave_head_wgrad(const OctaveAct* x, const float* dlogits, int32_t K, float* dw /* [K][C] */, float* db /* [K] */,
+                      void* stream);
+
+/* Layout plumbing. */
+int octave_nchw_to_nhwc(const float* src, int32_t C_src, const OctaveAct* dst /* C >= C_src, extra channels zeroed */,
+                        void* stream);
+int octave_nhwc_to_nchw(const OctaveAct* src, float* dst, int32_t accumulate, void* stream);
+/* dst(h,w) = [accumulate ? dst : 0] + (h < src.H && w < src.W ? src(h,w) : 0): zero-pad (compose.py:125-130) and crop. */
+int octave_copy_window(const OctaveAct* src, const OctaveAct* dst, int32_t accumulate, void* stream);
+/* space-to-depth by 2: dst[h][w][(i*2+j)*C + c] = src[2h+i][2w+j][c] (0 outside src) — data-gradient view of ConvT k2s2 */
+int octave_space_to_depth(const OctaveAct* src, const OctaveAct* dst, void* stream);
+/* inverse: dst[2h+i][2w+j][c] = src[h][w][(i*2+j)*C + c] for the pixels that exist in dst (fp32-mode ConvT k2s2) */
+int octave_depth_to_space(const OctaveAct* src, const OctaveAct* dst, void* stream);
+
+/* K5 (small part): the per-sample attention branch of SplAtConv2d on [B][C] vectors, fp32
+ * (resnest.py:116-127: GAP -> fc1 (grouped 1x1) -> BatchNorm over the batch -> ReLU -> fc2 -> view(B,radix,C) -> softmax(dim=1)). */
+/* out[b][j] = bias[j] + in_scale * sum_i in[b][g(j)*Kg + i] * w[j][i],  g(j) = j / (N/groups) */
+int octave_glinear_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t K_total, int32_t N,
+                       int32_t groups, float in_scale, float* out, void* stream);
+/* din[b][i] = in_scale * sum_{j in group(i)} dout[b][j] * w[j][i - g*Kg]   (overwritten) */
+int octave_glinear_bwd_data(const float* dout, const float* w, int32_t B, int32_t K_total, int32_t N, int32_t groups,
+                            float in_scale, float* din, void* stream);
+/* dw[j][i] = in_scale * sum_b dout[b][j] * in[b][g*Kg+i]; dbias[j] = sum_b dout[b][j]   (overwritten) */
+int octave_glinear_bwd_weight(const float* dout, const float* in, int32_t B, int32_t K_total, int32_t N, int32_t groups,
+                              float in_scale, float* dw, float* dbias, void* stream);
+/* BatchNorm over the batch of a [B][C] matrix followed by ReLU (SplAtConv2d.bn1 + relu, resnest.py:120-122) */
+int octave_bn1d_relu_fwd(const float* x, int32_t B, int32_t C, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, int64_t* num_batches_tracked, float eps, float momentum, int32_t training,
+                         float* y, float* mean_invstd /* [2C] */, void* stream);
+int octave_bn1d_relu_bwd(const float* dy, const float* x, const float* y, int32_t B, int32_t C, const float* gamma,
+                         const float* mean_invstd, int32_t training, float* dx, float* dgamma, float* dbeta, void* stream);
+/* att[b][r*C+c] = softmax_r(logits[b][r*C+c]), radix R */
+int octave_rsoftmax_fwd(const float* logits, int32_t B, int32_t R, int32_t C, float* att, void* stream);
+int octave_rsoftmax_bwd(const float* datt, const float* att, int32_t B, int32_t R, int32_t C, float* dlogits, void* stream);
+
+/* Weight re-packing fp32 [Cout][Cin/groups][k][k] (torch layout) -> bf16 operand of the tcgen05 kernels.
+ * `dense_groups` <= groups: groups are merged into block-diagonal dense groups (zeros off the diagonal) when the
+ * per-group channel count is too small for a UMMA tile. */
+#define OCT_PACK_FWD 0          /* [taps][Cout][Cin/dense_groups] */
+#define OCT_PACK_DGRAD 1        /* [taps][Cin][Cout/dense_groups], taps flipped */
+#define OCT_PACK_CONVT_FWD 2    /* w [Cin][Cout][2][2] -> [4*Cout][Cin] */
+#define OCT_PACK_CONVT_DGRAD 3  /* w [Cin][Cout][2][2] -> [Cin][4*Cout] */
+int octave_pack_weight(const float* w, int32_t mode, int32_t cout, int32_t cin, int32_t groups, int32_t dense_groups,
+                       int32_t ksize, void* out_bf16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,7 @@ class ConvDesc(C.Structure):
         ("Hout", C.c_int32), ("Wout", C.c_int32),
         ("mode", C.c_int32), ("relu", C.c_int32),
         ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("accumulate", C.c_int32), ("real_groups", C.c_int32),
     ]
 
 

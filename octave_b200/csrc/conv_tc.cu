@@ -42,7 +42,7 @@ struct ConvTcParams {
   int scatter;       // 1: ConvTranspose k2s2 — GEMM column n = tap*cout_total + co, pixel (2h+i, 2w+j)
   int cout_total;    // channels per tap in scatter mode
   const float* bias;
-  int relu, out_f32;
+  int relu, out_f32, accumulate;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -163,10 +163,21 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         }
         if (p.out_f32) {
           float* o = reinterpret_cast<float*>(p.out) + pix * p.ldc + p.c_off + cbase + c0;
+          if (p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += o[i];
+          }
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
         } else {
           bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldc + p.c_off + cbase + c0;
+          if (p.accumulate) {
+            float e[16];
+            VecIO<bf16, 8>::ld(o, e);
+            VecIO<bf16, 8>::ld(o + 8, e + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += e[i];
+          }
           uint4 u0, u1;
           u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
           u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
@@ -191,25 +202,29 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 // accumulates over the pixel tiles of this CTA's slice; operands are MN-major.
 // ---------------------------------------------------------------------------------------------------
 struct WgradParams {
-  int tap_dh, tap_dw_unused;  // (kept for alignment)
   int taps;
   int tap_dhs[9], tap_dws[9];
-  int cin_g, cout_g;
+  int cin_g, cout_g;          // per (dense) group
+  int real_cin_g, real_cout_g;  // per real group (<= dense group): only diagonal blocks are stored
   int tiles_w, tiles_h, TW, TH, B;
   int n_ci_tiles;    // Cin_g tiles of BN
   int tiles_per_cta; // pixel tiles handled by one CTA (split-K slice)
   int total_tiles;   // B * tiles_w * tiles_h
-  float* dw;         // [taps][Cout][Cin_g] fp32, pre-zeroed
+  float* dw;         // torch layout [Cout][Cin/groups][k][k] (conv) or [Cin][Cout][2][2] (convT), pre-zeroed
   int cout_total;
+  int convt;         // 1: GEMM rows are n = t*Cout + co of a ConvTranspose k2s2
+  int convt_cout;
 };
 
-template <int BN, int STAGES>
+template <int BN, int CWA, int CWB, int STAGES>
 __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
                                                                 const __grid_constant__ CUtensorMap tmX,
                                                                 const WgradParams p) {
-  constexpr int CHUNK_BYTES = 128 * 128;             // one [128 pixel][64 ch] box region
-  constexpr int A_BYTES = 2 * CHUNK_BYTES;           // 128 output channels
-  constexpr int B_BYTES = (BN / 64) * CHUNK_BYTES;   // BN input channels
+  constexpr int PITCH_A = CWA * 2, PITCH_B = CWB * 2;   // bytes per pixel row of one box
+  constexpr int CHUNK_A = 128 * PITCH_A, CHUNK_B = 128 * PITCH_B;
+  constexpr int NCH_A = 128 / CWA, NCH_B = (BN + CWB - 1) / CWB;
+  constexpr int A_BYTES = NCH_A * CHUNK_A;
+  constexpr int B_BYTES = NCH_B * CHUNK_B;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
@@ -234,11 +249,16 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
   // Rows [rows, 16*ksteps) of every box region are read by the MMA but never written by TMA: zero them.
   {
     uint8_t* base = smem_raw + (smem_base - tc::smem_u32(smem_raw));
-    const int regions = STAGES * (STAGE_BYTES / CHUNK_BYTES);
-    const int tail_bytes = (ksteps * 16 - rows) * 128;
-    for (int rgn = 0; rgn < regions; ++rgn) {
-      uint8_t* q = base + rgn * CHUNK_BYTES + rows * 128;
-      for (int i = threadIdx.x * 16; i < tail_bytes; i += kThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
+    const int tail_rows = ksteps * 16 - rows;
+    for (int st = 0; st < STAGES; ++st) {
+      for (int rgn = 0; rgn < NCH_A; ++rgn) {
+        uint8_t* q = base + st * STAGE_BYTES + rgn * CHUNK_A + rows * PITCH_A;
+        for (int i = threadIdx.x * 16; i < tail_rows * PITCH_A; i += kThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
+      }
+      for (int rgn = 0; rgn < NCH_B; ++rgn) {
+        uint8_t* q = base + st * STAGE_BYTES + A_BYTES + rgn * CHUNK_B + rows * PITCH_B;
+        for (int i = threadIdx.x * 16; i < tail_rows * PITCH_B; i += kThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
+      }
     }
   }
   if (threadIdx.x == 0) {
@@ -263,13 +283,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
     return;
   }
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  // number of 64-channel boxes that exist on each side (the rest of the 128 x BN tile is never stored)
-  const int a_boxes = min(2, (p.cout_g - co0 + 63) / 64);
-  const int b_boxes = min(BN / 64, (p.cin_g - ci0 + 63) / 64);
+  // number of channel boxes that exist on each side (the rest of the 128 x BN tile is never stored)
+  const int a_boxes = min(NCH_A, (p.cout_g - co0 + CWA - 1) / CWA);
+  const int b_boxes = min(NCH_B, (p.cin_g - ci0 + CWB - 1) / CWB);
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(rows * 128 * (a_boxes + b_boxes));
+      const uint32_t tx_bytes = (uint32_t)(rows * (PITCH_A * a_boxes + PITCH_B * b_boxes));
       const int dh = p.tap_dhs[tap], dw = p.tap_dws[tap];
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % STAGES;
@@ -284,9 +304,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
         const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         for (int j = 0; j < a_boxes; ++j)
-          tc::tma_load_4d(sa + j * CHUNK_BYTES, &tmDY, fb, g * p.cout_g + co0 + 64 * j, w0, h0, img);
+          tc::tma_load_4d(sa + j * CHUNK_A, &tmDY, fb, g * p.cout_g + co0 + CWA * j, w0, h0, img);
         for (int j = 0; j < b_boxes; ++j)
-          tc::tma_load_4d(sa + A_BYTES + j * CHUNK_BYTES, &tmX, fb, g * p.cin_g + ci0 + 64 * j, w0 + dw, h0 + dh, img);
+          tc::tma_load_4d(sa + A_BYTES + j * CHUNK_B, &tmX, fb, g * p.cin_g + ci0 + CWB * j, w0 + dw, h0 + dh, img);
       }
     }
   } else if (warp == 1) {
@@ -298,11 +318,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
         tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
         tc::fence_after_sync();
         const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint64_t da = tc::umma_smem_desc(sa, 128, CHUNK_BYTES);
-        const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, 128, CHUNK_BYTES);
+        const uint64_t da = tc::umma_smem_desc(sa, PITCH_A, CHUNK_A);
+        const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, PITCH_B, CHUNK_B);
         for (int k = 0; k < ksteps; ++k)
-          tc::umma_bf16(tmem_base, tc::umma_desc_advance(da, k * 2048), tc::umma_desc_advance(db, k * 2048), idesc,
-                        (it | k) != 0);
+          tc::umma_bf16(tmem_base, tc::umma_desc_advance(da, k * 16 * PITCH_A), tc::umma_desc_advance(db, k * 16 * PITCH_B),
+                        idesc, (it | k) != 0);
         tc::umma_commit(tc::smem_u32(&empty_bar[s]));
       }
       tc::umma_commit(tc::smem_u32(&acc_bar));
@@ -314,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
     tc::mbar_wait(tc::smem_u32(&acc_bar), 0);
     tc::fence_after_sync();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* o = p.dw + ((long long)tap * p.cout_total + g * p.cout_g + co0 + r) * p.cin_g + ci0;
+    const int co = g * p.cout_g + co0 + r;           // global GEMM row
     const int nvalid = min(BN, p.cin_g - ci0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -323,8 +343,17 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
       tc::tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < nvalid) atomicAdd(o + c0 + i, __uint_as_float(v[i]));
+        for (int i = 0; i < 16; ++i) {
+          if (c0 + i < nvalid) {
+            const int ci = g * p.cin_g + ci0 + c0 + i;  // global input channel
+            if (p.convt) {
+              const int t = co / p.convt_cout, cc = co - t * p.convt_cout;
+              atomicAdd(p.dw + ((long long)ci * p.convt_cout + cc) * 4 + t, __uint_as_float(v[i]));
+            } else if (ci / p.real_cin_g == co / p.real_cout_g) {
+              atomicAdd(p.dw + ((long long)co * p.real_cin_g + (ci % p.real_cin_g)) * p.taps + tap, __uint_as_float(v[i]));
+            }
+          }
+        }
       }
     }
     tc::fence_before_sync();
@@ -416,16 +445,16 @@ int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParam
   return OCT_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int CWA, int CWB, int STAGES>
 int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& p, dim3 grid, cudaStream_t s) {
-  constexpr int smem = STAGES * (2 + BN / 64) * 128 * 128 + 1024;
+  constexpr int smem = STAGES * (128 * 128 * 2 + ((BN + CWB - 1) / CWB) * 128 * CWB * 2) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, CWA, CWB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return OCT_ERR_LAUNCH;
     attr_done = true;
   }
-  conv_tc_wgrad_kernel<BN, STAGES><<<grid, kThreads, smem, s>>>(tmDY, tmX, p);
+  conv_tc_wgrad_kernel<BN, CWA, CWB, STAGES><<<grid, kThreads, smem, s>>>(tmDY, tmX, p);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -482,7 +511,7 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
   p.out = y; p.ldc = d->y_ld; p.c_off = d->y_coff;
   p.Hout = flat ? 1 : d->Hout; p.Wout = flat ? W : d->Wout;
   p.scatter = convt ? 1 : 0; p.cout_total = d->cout;
-  p.bias = bias; p.relu = d->relu; p.out_f32 = d->out_dtype == OCT_DTYPE_F32;
+  p.bias = bias; p.relu = d->relu; p.out_f32 = d->out_dtype == OCT_DTYPE_F32; p.accumulate = d->accumulate;
   int BN = 128;
   if (n_cols_g % 128) BN = (n_cols_g % 64 == 0) ? 64 : ((n_cols_g % 32 == 0) ? 32 : 16);
   if (convt && d->cout % BN) BN = (d->cout % 64 == 0) ? 64 : 32;  // a column tile must stay inside one tap
@@ -511,29 +540,33 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
 
 extern "C" int octave_conv_tc_wgrad_supported(const OctaveConvDesc* d) {
   if (validate_conv(d) != OCT_OK) return 0;
-  if (d->mode != OCT_CONV_MODE_CONV) return 0;
-  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
-  // 64-channel TMA boxes on both operands; a box may not run past the tensor's channel extent
-  if (d->cin < 64 || d->cout < 64) return 0;
-  if (cin_g % 64 || cout_g % 64) return 0;
+  const int cin_g = d->cin / d->groups;
+  const int cout_g = (d->mode == OCT_CONV_MODE_CONVT ? 4 * d->cout : d->cout) / d->groups;
+  if (d->mode == OCT_CONV_MODE_CONVT && (d->groups != 1 || d->ksize != 1)) return 0;
+  // 64- or 32-channel TMA boxes on both operands
+  if (cin_g % 32 || cout_g % 32) return 0;
   return 1;
 }
 
-extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dwpack,
-                                    void* stream) {
+extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dw, void* stream) {
   int rc = validate_conv(d);
   if (rc != OCT_OK) return rc;
   if (!octave_conv_tc_wgrad_supported(d)) return OCT_ERR_UNSUPPORTED;
-  if (!x || !dy || !dwpack) return OCT_ERR_INVALID;
+  if (!x || !dy || !dw) return OCT_ERR_INVALID;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  const bool convt = d->mode == OCT_CONV_MODE_CONVT;
+  const int cout_all = convt ? 4 * d->cout : d->cout;
+  const int cin_g = d->cin / d->groups, cout_g = cout_all / d->groups;
+  const int real_groups = d->real_groups > 0 ? d->real_groups : d->groups;
   WgradParams p{};
   p.taps = d->ksize * d->ksize;
   for (int t = 0; t < p.taps; ++t) {
     p.tap_dhs[t] = d->ksize == 3 ? t / 3 - 1 : 0;
     p.tap_dws[t] = d->ksize == 3 ? t % 3 - 1 : 0;
   }
-  p.cin_g = cin_g; p.cout_g = cout_g; p.cout_total = d->cout;
+  p.cin_g = cin_g; p.cout_g = cout_g; p.cout_total = cout_all;
+  p.real_cin_g = d->cin / real_groups; p.real_cout_g = cout_all / real_groups;
+  p.convt = convt ? 1 : 0; p.convt_cout = d->cout;
   int H = d->H, W = d->W, B = d->B;
   if (d->ksize == 1) { W = d->B * d->H * d->W; H = 1; B = 1; }
   pick_patch(H, W, &p.TW, &p.TH);
@@ -541,7 +574,12 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   p.tiles_h = (H + p.TH - 1) / p.TH;
   p.B = B;
   p.total_tiles = B * p.tiles_w * p.tiles_h;
-  const int BN = (cin_g % 256 == 0) ? 256 : ((cin_g % 128 == 0) ? 128 : 64);
+  const int CWA = (cout_g % 64 == 0) ? 64 : 32;
+  const int CWB = (cin_g % 64 == 0) ? 64 : 32;
+  int BN;
+  if (CWB == 32) BN = 32;
+  else if (CWA == 32) BN = 64;
+  else BN = (cin_g % 256 == 0) ? 256 : ((cin_g % 128 == 0) ? 128 : 64);
   p.n_ci_tiles = (cin_g + BN - 1) / BN;
   const int n_co_tiles = (cout_g + 127) / 128;
   const int out_tiles = n_co_tiles * p.n_ci_tiles * p.taps * d->groups;
@@ -552,17 +590,23 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   if (split > p.total_tiles) split = p.total_tiles;
   p.tiles_per_cta = (p.total_tiles + split - 1) / split;
   split = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  p.dw = dwpack;
+  p.dw = dw;
   CUtensorMap tmDY, tmX;
   const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
   const bf16* dyb = reinterpret_cast<const bf16*>(dy) + d->y_coff;
-  if (!make_act_map(&tmX, xb, d->cin, W, H, B, d->x_ld, 64, p.TW, p.TH, 128)) return OCT_ERR_LAUNCH;
-  if (!make_act_map(&tmDY, dyb, d->cout, W, H, B, d->y_ld, 64, p.TW, p.TH, 128)) return OCT_ERR_LAUNCH;
-  if (cudaMemsetAsync(dwpack, 0, (size_t)p.taps * d->cout * cin_g * sizeof(float), s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  if (!make_act_map(&tmX, xb, d->cin, W, H, B, d->x_ld, CWB, p.TW, p.TH, CWB * 2)) return OCT_ERR_LAUNCH;
+  if (!make_act_map(&tmDY, dyb, cout_all, W, H, B, d->y_ld, CWA, p.TW, p.TH, CWA * 2)) return OCT_ERR_LAUNCH;
+  const size_t wbytes = (size_t)cout_all * p.real_cin_g * p.taps * sizeof(float);
+  if (!d->accumulate && cudaMemsetAsync(dw, 0, wbytes, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   dim3 grid(split, n_co_tiles * p.n_ci_tiles, p.taps * d->groups);
-  switch (BN) {
-    case 256: return launch_wgrad<256, 2>(tmDY, tmX, p, grid, s);
-    case 128: return launch_wgrad<128, 3>(tmDY, tmX, p, grid, s);
-    default: return launch_wgrad<64, 4>(tmDY, tmX, p, grid, s);
+  if (CWA == 64 && CWB == 64) {
+    switch (BN) {
+      case 256: return launch_wgrad<256, 64, 64, 2>(tmDY, tmX, p, grid, s);
+      case 128: return launch_wgrad<128, 64, 64, 3>(tmDY, tmX, p, grid, s);
+      default: return launch_wgrad<64, 64, 64, 4>(tmDY, tmX, p, grid, s);
+    }
   }
+  if (CWA == 32 && CWB == 64) return launch_wgrad<64, 32, 64, 4>(tmDY, tmX, p, grid, s);
+  if (CWA == 64 && CWB == 32) return launch_wgrad<32, 64, 32, 4>(tmDY, tmX, p, grid, s);
+  return launch_wgrad<32, 32, 32, 4>(tmDY, tmX, p, grid, s);
 }

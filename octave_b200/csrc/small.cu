@@ -1,0 +1,257 @@
+// Small fp32 kernels: the per-sample attention branch of SplAtConv2d
+// (/root/reference/architectures/extra/resnest.py:116-127) and the weight re-packing for the tcgen05 kernels.
+#include "common.cuh"
+#include "../../include/octave_b200.h"
+
+namespace {
+
+constexpr int BCHUNK = 8;  // batch rows processed per pass of a warp
+
+// one warp per output feature j; lanes stride over the K inputs of j's group
+__global__ void glinear_fwd_kernel(const float* in, const float* w, const float* bias, int B, int Kt, int N, int groups,
+                                   float scale, float* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const int Kg = Kt / groups, g = warp / (N / groups);
+  const float* wr = w + (long long)warp * Kg;
+  for (int b0 = 0; b0 < B; b0 += BCHUNK) {
+    float acc[BCHUNK];
+#pragma unroll
+    for (int r = 0; r < BCHUNK; ++r) acc[r] = 0.f;
+    for (int i = lane; i < Kg; i += 32) {
+      const float wv = wr[i];
+#pragma unroll
+      for (int r = 0; r < BCHUNK; ++r)
+        if (b0 + r < B) acc[r] += wv * in[(long long)(b0 + r) * Kt + g * Kg + i];
+    }
+#pragma unroll
+    for (int r = 0; r < BCHUNK; ++r) {
+      const float s = warp_sum(acc[r]);
+      if (lane == 0 && b0 + r < B) out[(long long)(b0 + r) * N + warp] = s * scale + (bias ? bias[warp] : 0.f);
+    }
+  }
+}
+
+// one thread per (b, i)
+__global__ void glinear_bwd_data_kernel(const float* dout, const float* w, int B, int Kt, int N, int groups, float scale,
+                                        float* din) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Kt) return;
+  const int b = (int)(idx / Kt), i = (int)(idx % Kt);
+  const int Kg = Kt / groups, Ng = N / groups, g = i / Kg, il = i - g * Kg;
+  float acc = 0.f;
+  for (int j = 0; j < Ng; ++j) acc += dout[(long long)b * N + g * Ng + j] * w[(long long)(g * Ng + j) * Kg + il];
+  din[idx] = acc * scale;
+}
+
+// one thread per (j, i)
+__global__ void glinear_bwd_weight_kernel(const float* dout, const float* in, int B, int Kt, int N, int groups,
+                                          float scale, float* dw, float* dbias) {
+  const int Kg = Kt / groups, Ng = N / groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Kg) return;
+  const int j = (int)(idx / Kg), il = (int)(idx % Kg), g = j / Ng;
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float d = dout[(long long)b * N + j];
+    acc += d * in[(long long)b * Kt + g * Kg + il];
+    accb += d;
+  }
+  dw[idx] = acc * scale;
+  if (il == 0 && dbias) dbias[j] = accb;
+}
+
+__global__ void bn1d_relu_fwd_kernel(const float* x, int B, int C, const float* gamma, const float* beta, float* rm,
+                                     float* rv, long long* nbt, float eps, float mom, int training, float* y, float* mi) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < B; ++b) { const double v = x[(long long)b * C + c]; s += v; q += v * v; }
+    const double m = s / B;
+    double var = q / B - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (rm) rm[c] = (1.f - mom) * rm[c] + mom * mean;
+    if (rv) rv[c] = (1.f - mom) * rv[c] + mom * (float)(B > 1 ? var * B / (B - 1.0) : var);
+    if (c == 0 && nbt) *nbt += 1;
+  } else {
+    mean = rm[c];
+    invstd = 1.f / sqrtf(rv[c] + eps);
+  }
+  mi[c] = mean;
+  mi[C + c] = invstd;
+  const float g = gamma[c], bt = beta[c];
+  for (int b = 0; b < B; ++b) {
+    const float v = (x[(long long)b * C + c] - mean) * invstd * g + bt;
+    y[(long long)b * C + c] = fmaxf(v, 0.f);
+  }
+}
+
+__global__ void bn1d_relu_bwd_kernel(const float* dy, const float* x, const float* y, int B, int C, const float* gamma,
+                                     const float* mi, int training, float* dx, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = mi[c], invstd = mi[C + c];
+  float sd = 0.f, sdx = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const long long o = (long long)b * C + c;
+    const float d = y[o] > 0.f ? dy[o] : 0.f;
+    sd += d;
+    sdx += d * (x[o] - mean) * invstd;
+  }
+  if (dgamma) dgamma[c] = sdx;
+  if (dbeta) dbeta[c] = sd;
+  const float k1 = training ? sd / B : 0.f, k2 = training ? sdx / B : 0.f, ag = gamma[c] * invstd;
+  for (int b = 0; b < B; ++b) {
+    const long long o = (long long)b * C + c;
+    const float d = y[o] > 0.f ? dy[o] : 0.f;
+    dx[o] = ag * (d - k1 - (x[o] - mean) * invstd * k2);
+  }
+}
+
+__global__ void rsoftmax_fwd_kernel(const float* logits, int B, int R, int C, float* att) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * C) return;
+  const int b = (int)(idx / C), c = (int)(idx % C);
+  const float* l = logits + (long long)b * R * C + c;
+  float mx = -INFINITY;
+  for (int r = 0; r < R; ++r) mx = fmaxf(mx, l[r * C]);
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += expf(l[r * C] - mx);
+  for (int r = 0; r < R; ++r) att[(long long)b * R * C + r * C + c] = expf(l[r * C] - mx) / s;
+}
+
+__global__ void rsoftmax_bwd_kernel(const float* datt, const float* att, int B, int R, int C, float* dlogits) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * C) return;
+  const int b = (int)(idx / C), c = (int)(idx % C);
+  const long long base = (long long)b * R * C + c;
+  float dot = 0.f;
+  for (int r = 0; r < R; ++r) dot += datt[base + r * C] * att[base + r * C];
+  for (int r = 0; r < R; ++r) dlogits[base + r * C] = att[base + r * C] * (datt[base + r * C] - dot);
+}
+
+__global__ void pack_weight_kernel(const float* w, int mode, int cout, int cin, int groups, int dg, int k, bf16* out) {
+  const int taps = k * k;
+  const int cin_g = cin / groups, cout_g = cout / groups;
+  const int cin_d = cin / dg, cout_d = cout / dg;
+  long long total;
+  if (mode == OCT_PACK_FWD) total = (long long)taps * cout * cin_d;
+  else if (mode == OCT_PACK_DGRAD) total = (long long)taps * cin * cout_d;
+  else total = (long long)4 * cout * cin;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (mode == OCT_PACK_FWD) {
+      const int ci_d = (int)(idx % cin_d);
+      const int co = (int)((idx / cin_d) % cout);
+      const int tap = (int)(idx / ((long long)cin_d * cout));
+      const int ci = (co / cout_d) * cin_d + ci_d;  // global input channel
+      if (ci / cin_g == co / cout_g) v = w[((long long)co * cin_g + (ci % cin_g)) * taps + tap];
+    } else if (mode == OCT_PACK_DGRAD) {
+      const int co_d = (int)(idx % cout_d);
+      const int ci = (int)((idx / cout_d) % cin);
+      const int tap = (int)(idx / ((long long)cout_d * cin));
+      const int co = (ci / cin_d) * cout_d + co_d;
+      if (ci / cin_g == co / cout_g) v = w[((long long)co * cin_g + (ci % cin_g)) * taps + (taps - 1 - tap)];
+    } else if (mode == OCT_PACK_CONVT_FWD) {
+      // out[(t*cout + co)][ci] = w[ci][co][t]
+      const int ci = (int)(idx % cin);
+      const int co = (int)((idx / cin) % cout);
+      const int t = (int)(idx / ((long long)cin * cout));
+      v = w[((long long)ci * cout + co) * 4 + t];
+    } else {
+      // out[ci][t*cout + co] = w[ci][co][t]
+      const int co = (int)(idx % cout);
+      const int t = (int)((idx / cout) % 4);
+      const int ci = (int)(idx / ((long long)4 * cout));
+      v = w[((long long)ci * cout + co) * 4 + t];
+    }
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace
+
+extern "C" int octave_glinear_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t Kt, int32_t N,
+                                  int32_t groups, float in_scale, float* out, void* stream) {
+  if (!in || !w || !out || B <= 0 || Kt <= 0 || N <= 0 || groups <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
+  const int warps_per_block = 8;
+  glinear_fwd_kernel<<<(N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+      in, w, bias, B, Kt, N, groups, in_scale, out);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_glinear_bwd_data(const float* dout, const float* w, int32_t B, int32_t Kt, int32_t N, int32_t groups,
+                                       float in_scale, float* din, void* stream) {
+  if (!dout || !w || !din || B <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
+  const long long total = (long long)B * Kt;
+  glinear_bwd_data_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dout, w, B, Kt, N, groups, in_scale, din);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_glinear_bwd_weight(const float* dout, const float* in, int32_t B, int32_t Kt, int32_t N, int32_t groups,
+                                         float in_scale, float* dw, float* dbias, void* stream) {
+  if (!dout || !in || !dw || B <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
+  const long long total = (long long)N * (Kt / groups);
+  glinear_bwd_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dout, in, B, Kt, N, groups, in_scale, dw, dbias);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_bn1d_relu_fwd(const float* x, int32_t B, int32_t C, const float* gamma, const float* beta, float* rm,
+                                    float* rv, int64_t* nbt, float eps, float momentum, int32_t training, float* y,
+                                    float* mean_invstd, void* stream) {
+  if (!x || !gamma || !beta || !y || !mean_invstd || B <= 0 || C <= 0) return OCT_ERR_INVALID;
+  if (!training && (!rm || !rv)) return OCT_ERR_INVALID;
+  bn1d_relu_fwd_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, B, C, gamma, beta, rm, rv, (long long*)nbt, eps,
+                                                                        momentum, training, y, mean_invstd);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_bn1d_relu_bwd(const float* dy, const float* x, const float* y, int32_t B, int32_t C, const float* gamma,
+                                    const float* mean_invstd, int32_t training, float* dx, float* dgamma, float* dbeta,
+                                    void* stream) {
+  if (!dy || !x || !y || !gamma || !mean_invstd || !dx) return OCT_ERR_INVALID;
+  bn1d_relu_bwd_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dy, x, y, B, C, gamma, mean_invstd, training, dx, dgamma, dbeta);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_rsoftmax_fwd(const float* logits, int32_t B, int32_t R, int32_t C, float* att, void* stream) {
+  if (!logits || !att || B <= 0 || R <= 0 || C <= 0) return OCT_ERR_INVALID;
+  const long long total = (long long)B * C;
+  rsoftmax_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, B, R, C, att);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_rsoftmax_bwd(const float* datt, const float* att, int32_t B, int32_t R, int32_t C, float* dlogits, void* stream) {
+  if (!datt || !att || !dlogits) return OCT_ERR_INVALID;
+  const long long total = (long long)B * C;
+  rsoftmax_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(datt, att, B, R, C, dlogits);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_pack_weight(const float* w, int32_t mode, int32_t cout, int32_t cin, int32_t groups, int32_t dense_groups,
+                                  int32_t ksize, void* out, void* stream) {
+  if (!w || !out || cout <= 0 || cin <= 0 || groups <= 0 || dense_groups <= 0) return OCT_ERR_INVALID;
+  if (mode < 0 || mode > 3) return OCT_ERR_INVALID;
+  if (mode <= OCT_PACK_DGRAD && (cin % groups || cout % groups || groups % dense_groups)) return OCT_ERR_INVALID;
+  long long total;
+  const int taps = ksize * ksize;
+  if (mode == OCT_PACK_FWD) total = (long long)taps * cout * (cin / dense_groups);
+  else if (mode == OCT_PACK_DGRAD) total = (long long)taps * cin * (cout / dense_groups);
+  else total = 4LL * cout * cin;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_weight_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, mode, cout, cin, groups, dense_groups, ksize, (bf16*)out);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}

@@ -1,0 +1,504 @@
+"""Thin Python wrappers over the C-ABI (include/octave_b200.h).  Everything here works on `Act`, an NHWC
+channel view of a torch buffer; torch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib
+
+_vp = C.c_void_p
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return _lib.DTYPE_F32
+    if dtype == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    raise TypeError(f"octave_b200 supports float32 / bfloat16 activations, got {dtype}")
+
+
+class ActStruct(C.Structure):
+    _fields_ = [("data", _vp), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("ld", C.c_int32), ("coff", C.c_int32), ("dtype", C.c_int32)]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("ceil_mode", C.c_int32), ("count_include_pad", C.c_int32)]
+
+
+class Act:
+    """NHWC channel view: pixel p, channel c at buf.data_ptr + (p*ld + coff + c) elements."""
+    __slots__ = ("buf", "B", "H", "W", "C", "ld", "coff")
+
+    def __init__(self, buf: torch.Tensor, B: int, H: int, W: int, C_: int, ld: Optional[int] = None, coff: int = 0):
+        self.buf, self.B, self.H, self.W, self.C = buf, B, H, W, C_
+        self.ld = C_ if ld is None else ld
+        self.coff = coff
+
+    @staticmethod
+    def empty(B: int, H: int, W: int, C_: int, dtype: torch.dtype, device) -> "Act":
+        return Act(torch.empty((B, H, W, C_), dtype=dtype, device=device), B, H, W, C_)
+
+    @staticmethod
+    def zeros(B: int, H: int, W: int, C_: int, dtype: torch.dtype, device) -> "Act":
+        return Act(torch.zeros((B, H, W, C_), dtype=dtype, device=device), B, H, W, C_)
+
+    def like(self, C_: Optional[int] = None) -> "Act":
+        return Act.empty(self.B, self.H, self.W, self.C if C_ is None else C_, self.buf.dtype, self.buf.device)
+
+    def slice(self, c0: int, c: int) -> "Act":
+        assert c0 + c <= self.C
+        return Act(self.buf, self.B, self.H, self.W, c, self.ld, self.coff + c0)
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.buf.dtype
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    @property
+    def npix(self) -> int:
+        return self.B * self.H * self.W
+
+    def struct(self) -> ActStruct:
+        return ActStruct(self.buf.data_ptr(), self.B, self.H, self.W, self.C, self.ld, self.coff, _dt(self.buf.dtype))
+
+    def to_nchw(self) -> torch.Tensor:
+        """Debug/test helper (torch ops): materialise the view as an NCHW fp32 tensor."""
+        t = self.buf.reshape(self.B, self.H, self.W, self.ld)[..., self.coff:self.coff + self.C]
+        return t.permute(0, 3, 1, 2).float().contiguous()
+
+
+def _ref(a: Optional[Act]):
+    return None if a is None else C.byref(a.struct())
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(name: str, rc: int) -> None:
+    if rc != 0:
+        raise _lib.OctaveError(name, rc)
+
+
+# --- bind the remaining entry points ---------------------------------------------------------------
+_A = C.POINTER(ActStruct)
+_sigs = {
+    "octave_conv_direct_fwd": [C.POINTER(_lib.ConvDesc), _vp, _vp, _vp, _vp, _vp],
+    "octave_conv_direct_dgrad": [C.POINTER(_lib.ConvDesc), _vp, _vp, _vp, _vp],
+    "octave_conv_direct_wgrad": [C.POINTER(_lib.ConvDesc), _vp, _vp, _vp, _vp, _vp],
+    "octave_act_bwd": [_A, _A, C.c_int32, _A, _vp],
+    "octave_chan_stats": [_A, _vp, _vp],
+    "octave_bn_prepare": [C.c_int32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_int32, _vp, _vp, _vp],
+    "octave_affine_act": [_A, _vp, _A, C.c_int32, _A, _vp, _vp],
+    "octave_bn_bwd_reduce": [_A, _A, _A, _vp, _vp, _vp],
+    "octave_bn_bwd_apply": [_A, _A, _A, _vp, _vp, _vp, C.c_int32, _A, _vp, _vp, _vp],
+    "octave_add_inplace": [_A, _A, _vp],
+    "octave_relu_bwd": [_A, _A, _A, _vp],
+    "octave_splat_combine": [_A, _vp, C.c_int32, _A, _vp],
+    "octave_splat_bwd_reduce": [_A, _A, _A, _vp, _vp],
+    "octave_splat_bwd_du": [_A, _A, _vp, _vp, C.c_float, _A, _vp],
+    "octave_pool_out_size": [C.POINTER(PoolDesc), C.c_int32],
+    "octave_pool_fwd": [C.POINTER(PoolDesc), _A, _A, _vp, _vp],
+    "octave_pool_bwd": [C.POINTER(PoolDesc), _A, _vp, _A, _vp],
+    "octave_head_fwd": [_A, _vp, _vp, C.c_int32, C.c_int32, _vp, _A, _vp],
+    "octave_head_bwd": [_A, _vp, _vp, C.c_int32, C.c_int32, _vp, _A, _A, _vp, _vp],
+    "octave_head_wgrad": [_A, _vp, C.c_int32, _vp, _vp, _vp],
+    "octave_nchw_to_nhwc": [_vp, C.c_int32, _A, _vp],
+    "octave_nhwc_to_nchw": [_A, _vp, C.c_int32, _vp],
+    "octave_copy_window": [_A, _A, C.c_int32, _vp],
+    "octave_space_to_depth": [_A, _A, _vp],
+    "octave_depth_to_space": [_A, _A, _vp],
+    "octave_glinear_fwd": [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp, _vp],
+    "octave_glinear_bwd_data": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp, _vp],
+    "octave_glinear_bwd_weight": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp, _vp, _vp],
+    "octave_bn1d_relu_fwd": [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_int32, _vp, _vp, _vp],
+    "octave_bn1d_relu_bwd": [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp],
+    "octave_rsoftmax_fwd": [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+    "octave_rsoftmax_bwd": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+    "octave_pack_weight": [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+}
+for _n, _a in _sigs.items():
+    getattr(lib, _n).restype = C.c_int
+    getattr(lib, _n).argtypes = _a
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+
+
+# --- BatchNorm -------------------------------------------------------------------------------------
+def chan_stats(x: Act) -> torch.Tensor:
+    sums = torch.empty(2 * x.C, dtype=torch.float64, device=x.device)
+    _chk("octave_chan_stats", lib.octave_chan_stats(_ref(x), sums.data_ptr(), stream_ptr()))
+    return sums
+
+
+def bn_prepare(C_: int, count: float, sums, gamma, beta, rm, rv, nbt, eps: float, momentum: float, training: bool, device):
+    ab = torch.empty(2 * C_, dtype=torch.float32, device=device)
+    mi = torch.empty(2 * C_, dtype=torch.float32, device=device)
+    _chk("octave_bn_prepare", lib.octave_bn_prepare(C_, float(count), _p(sums), _p(gamma), _p(beta), _p(rm), _p(rv), _p(nbt),
+                                                    eps, momentum, int(training), ab.data_ptr(), mi.data_ptr(), stream_ptr()))
+    return ab, mi
+
+
+def affine_act(x: Act, ab: Optional[torch.Tensor], res: Optional[Act], relu: bool, out: Optional[Act] = None,
+               want_gap: bool = False):
+    y = out if out is not None else x.like()
+    gap = torch.empty((x.B, x.C // 2), dtype=torch.float32, device=x.device) if want_gap else None
+    _chk("octave_affine_act", lib.octave_affine_act(_ref(x), _p(ab), _ref(res), int(relu), _ref(y), _p(gap), stream_ptr()))
+    return y, gap
+
+
+def bn_bwd(dy: Act, mask: Optional[Act], x: Act, mi: torch.Tensor, gamma: Optional[torch.Tensor], training: bool,
+           out: Optional[Act] = None):
+    """-> dx, dgamma, dbeta"""
+    sums2 = torch.empty(2 * x.C, dtype=torch.float64, device=x.device)
+    _chk("octave_bn_bwd_reduce", lib.octave_bn_bwd_reduce(_ref(dy), _ref(mask), _ref(x), mi.data_ptr(), sums2.data_ptr(), stream_ptr()))
+    dx = out if out is not None else x.like()
+    dgamma = torch.empty(x.C, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(x.C, dtype=torch.float32, device=x.device)
+    _chk("octave_bn_bwd_apply", lib.octave_bn_bwd_apply(_ref(dy), _ref(mask), _ref(x), mi.data_ptr(), _p(gamma), sums2.data_ptr(),
+                                                        int(training), _ref(dx), dgamma.data_ptr(), dbeta.data_ptr(), stream_ptr()))
+    return dx, dgamma, dbeta
+
+
+def add_inplace(dst: Act, src: Act) -> None:
+    _chk("octave_add_inplace", lib.octave_add_inplace(_ref(dst), _ref(src), stream_ptr()))
+
+
+def relu_bwd(dy: Act, mask: Act, out: Optional[Act] = None) -> Act:
+    dx = out if out is not None else dy.like()
+    _chk("octave_relu_bwd", lib.octave_relu_bwd(_ref(dy), _ref(mask), _ref(dx), stream_ptr()))
+    return dx
+
+
+def act_bwd(y: Act, dy: Act, act: int, out: Optional[Act] = None) -> Act:
+    dz = out if out is not None else dy.like()
+    _chk("octave_act_bwd", lib.octave_act_bwd(_ref(y), _ref(dy), act, _ref(dz), stream_ptr()))
+    return dz
+
+
+# --- split attention ---------------------------------------------------------------------------------
+def splat_combine(U: Act, att: torch.Tensor, relu: bool, out: Optional[Act] = None) -> Act:
+    o = out if out is not None else U.like(U.C // 2)
+    _chk("octave_splat_combine", lib.octave_splat_combine(_ref(U), att.data_ptr(), int(relu), _ref(o), stream_ptr()))
+    return o
+
+
+def splat_bwd_reduce(dout: Act, mask: Optional[Act], U: Act) -> torch.Tensor:
+    datt = torch.empty((dout.B, 2 * dout.C), dtype=torch.float32, device=dout.device)
+    _chk("octave_splat_bwd_reduce", lib.octave_splat_bwd_reduce(_ref(dout), _ref(mask), _ref(U), datt.data_ptr(), stream_ptr()))
+    return datt
+
+
+def splat_bwd_du(dout: Act, mask: Optional[Act], att: torch.Tensor, dgap: Optional[torch.Tensor], gap_scale: float) -> Act:
+    dU = dout.like(2 * dout.C)
+    _chk("octave_splat_bwd_du", lib.octave_splat_bwd_du(_ref(dout), _ref(mask), att.data_ptr(), _p(dgap), gap_scale, _ref(dU), stream_ptr()))
+    return dU
+
+
+def glinear_fwd(inp: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], groups: int, in_scale: float) -> torch.Tensor:
+    B, Kt = inp.shape
+    N = w.shape[0]
+    out = torch.empty((B, N), dtype=torch.float32, device=inp.device)
+    _chk("octave_glinear_fwd", lib.octave_glinear_fwd(inp.data_ptr(), w.data_ptr(), _p(bias), B, Kt, N, groups, in_scale, out.data_ptr(), stream_ptr()))
+    return out
+
+
+def glinear_bwd(dout: torch.Tensor, inp: torch.Tensor, w: torch.Tensor, groups: int, in_scale: float):
+    """-> din, dw (same shape as w), dbias"""
+    B, Kt = inp.shape
+    N = w.shape[0]
+    din = torch.empty_like(inp)
+    _chk("octave_glinear_bwd_data", lib.octave_glinear_bwd_data(dout.data_ptr(), w.data_ptr(), B, Kt, N, groups, in_scale, din.data_ptr(), stream_ptr()))
+    dw = torch.empty_like(w)
+    db = torch.empty(N, dtype=torch.float32, device=inp.device)
+    _chk("octave_glinear_bwd_weight", lib.octave_glinear_bwd_weight(dout.data_ptr(), inp.data_ptr(), B, Kt, N, groups, in_scale, dw.data_ptr(), db.data_ptr(), stream_ptr()))
+    return din, dw, db
+
+
+def bn1d_relu_fwd(x: torch.Tensor, gamma, beta, rm, rv, nbt, eps: float, momentum: float, training: bool):
+    B, C_ = x.shape
+    y = torch.empty_like(x)
+    mi = torch.empty(2 * C_, dtype=torch.float32, device=x.device)
+    _chk("octave_bn1d_relu_fwd", lib.octave_bn1d_relu_fwd(x.data_ptr(), B, C_, gamma.data_ptr(), beta.data_ptr(), _p(rm), _p(rv), _p(nbt),
+                                                          eps, momentum, int(training), y.data_ptr(), mi.data_ptr(), stream_ptr()))
+    return y, mi
+
+
+def bn1d_relu_bwd(dy, x, y, gamma, mi, training: bool):
+    B, C_ = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.empty(C_, dtype=torch.float32, device=x.device)
+    db = torch.empty(C_, dtype=torch.float32, device=x.device)
+    _chk("octave_bn1d_relu_bwd", lib.octave_bn1d_relu_bwd(dy.data_ptr(), x.data_ptr(), y.data_ptr(), B, C_, gamma.data_ptr(), mi.data_ptr(),
+                                                          int(training), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), stream_ptr()))
+    return dx, dg, db
+
+
+def rsoftmax_fwd(logits: torch.Tensor, R: int) -> torch.Tensor:
+    B, RC = logits.shape
+    att = torch.empty_like(logits)
+    _chk("octave_rsoftmax_fwd", lib.octave_rsoftmax_fwd(logits.data_ptr(), B, R, RC // R, att.data_ptr(), stream_ptr()))
+    return att
+
+
+def rsoftmax_bwd(datt: torch.Tensor, att: torch.Tensor, R: int) -> torch.Tensor:
+    B, RC = att.shape
+    dl = torch.empty_like(att)
+    _chk("octave_rsoftmax_bwd", lib.octave_rsoftmax_bwd(datt.data_ptr(), att.data_ptr(), B, R, RC // R, dl.data_ptr(), stream_ptr()))
+    return dl
+
+
+# --- pools ---------------------------------------------------------------------------------------------
+def pool_desc(kind: str, k: int, stride: int, pad: int, ceil_mode: bool = False, count_include_pad: bool = True) -> PoolDesc:
+    return PoolDesc(0 if kind == "max" else 1, k, stride, pad, int(ceil_mode), int(count_include_pad))
+
+
+def pool_fwd(pd: PoolDesc, x: Act):
+    Ho = lib.octave_pool_out_size(C.byref(pd), x.H)
+    Wo = lib.octave_pool_out_size(C.byref(pd), x.W)
+    y = Act.empty(x.B, Ho, Wo, x.C, x.dtype, x.device)
+    arg = torch.empty((x.B, Ho, Wo, x.C), dtype=torch.uint8, device=x.device) if pd.kind == 0 else None
+    _chk("octave_pool_fwd", lib.octave_pool_fwd(C.byref(pd), _ref(x), _ref(y), _p(arg), stream_ptr()))
+    return y, arg
+
+
+def pool_bwd(pd: PoolDesc, dy: Act, arg: Optional[torch.Tensor], H: int, W: int) -> Act:
+    dx = Act.empty(dy.B, H, W, dy.C, dy.dtype, dy.device)
+    _chk("octave_pool_bwd", lib.octave_pool_bwd(C.byref(pd), _ref(dy), _p(arg), _ref(dx), stream_ptr()))
+    return dx
+
+
+# --- heads ---------------------------------------------------------------------------------------------
+def head_fwd(x: Act, w: torch.Tensor, b: torch.Tensor, mode: int):
+    """w [K, C] fp32.  -> (out [B,K,H,W] fp32, gated Act or None)"""
+    K = w.shape[0]
+    out = torch.empty((x.B, K, x.H, x.W), dtype=torch.float32, device=x.device)
+    gated = x.like() if mode == 1 else None
+    _chk("octave_head_fwd", lib.octave_head_fwd(_ref(x), w.data_ptr(), b.data_ptr(), K, mode, out.data_ptr(), _ref(gated), stream_ptr()))
+    return out, gated
+
+
+def head_bwd(x: Act, w: torch.Tensor, b: torch.Tensor, mode: int, dout: Optional[torch.Tensor], dgated: Optional[Act]):
+    """-> dx Act, dw [K,C], db [K]"""
+    K = w.shape[0]
+    dx = x.like()
+    dlogits = torch.empty((x.B, K, x.H, x.W), dtype=torch.float32, device=x.device)
+    _chk("octave_head_bwd", lib.octave_head_bwd(_ref(x), w.data_ptr(), b.data_ptr(), K, mode, _p(dout), _ref(dgated), _ref(dx),
+                                                dlogits.data_ptr(), stream_ptr()))
+    dw = torch.empty((K, x.C), dtype=torch.float32, device=x.device)
+    db = torch.empty(K, dtype=torch.float32, device=x.device)
+    _chk("octave_head_wgrad", lib.octave_head_wgrad(_ref(x), dlogits.data_ptr(), K, dw.data_ptr(), db.data_ptr(), stream_ptr()))
+    return dx, dw, db
+
+
+# --- layout ----------------------------------------------------------------------------------------------
+def nchw_to_nhwc(src: torch.Tensor, dtype: torch.dtype, pad_to: int = 8) -> Act:
+    B, Cs, H, W = src.shape
+    Cd = ((Cs + pad_to - 1) // pad_to) * pad_to
+    dst = Act.empty(B, H, W, Cd, dtype, src.device)
+    s = src.contiguous().float()
+    _chk("octave_nchw_to_nhwc", lib.octave_nchw_to_nhwc(s.data_ptr(), Cs, _ref(dst), stream_ptr()))
+    return Act(dst.buf, B, H, W, Cs, Cd, 0)
+
+
+def nhwc_to_nchw(src: Act, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    dst = out if out is not None else torch.empty((src.B, src.C, src.H, src.W), dtype=torch.float32, device=src.device)
+    _chk("octave_nhwc_to_nchw", lib.octave_nhwc_to_nchw(_ref(src), dst.data_ptr(), int(accumulate), stream_ptr()))
+    return dst
+
+
+def copy_window(src: Act, dst: Act, accumulate: bool = False) -> None:
+    _chk("octave_copy_window", lib.octave_copy_window(_ref(src), _ref(dst), int(accumulate), stream_ptr()))
+
+
+def space_to_depth(src: Act, H: int, W: int) -> Act:
+    dst = Act.empty(src.B, H, W, 4 * src.C, src.dtype, src.device)
+    _chk("octave_space_to_depth", lib.octave_space_to_depth(_ref(src), _ref(dst), stream_ptr()))
+    return dst
+
+
+# --- convolutions ------------------------------------------------------------------------------------------
+class ConvSpec:
+    """Geometry + parameters of one Conv2d / ConvTranspose2d(k2,s2) and the cache of its bf16 operand packs."""
+
+    def __init__(self, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter], cin: int, cout: int, k: int,
+                 stride: int = 1, pad: int = 0, groups: int = 1, transposed: bool = False):
+        self.weight, self.bias = weight, bias
+        self.cin, self.cout, self.k, self.stride, self.pad, self.groups = cin, cout, k, stride, pad, groups
+        self.transposed = transposed
+        self._packs = {}
+        # merge tiny groups into block-diagonal dense groups until a group fills a UMMA K/N chunk
+        m = 1
+        if not transposed:
+            cg, og = cin // groups, cout // groups
+            while (cg * m) % 32 or (og * m) % 32:
+                m *= 2
+                if m > groups or groups % m:
+                    m = 0
+                    break
+        self.dense_groups = groups // m if m else 0
+
+    def tc_ok(self, dtype: torch.dtype) -> bool:
+        if dtype != torch.bfloat16:
+            return False
+        if self.transposed:
+            return self.cin % 32 == 0 and self.cout % 32 == 0
+        return self.dense_groups > 0 and self.stride == 1 and self.k in (1, 3) and self.pad == self.k // 2
+
+    def pack(self, mode: int) -> torch.Tensor:
+        w = self.weight
+        key = (mode, w._version, w.data_ptr())
+        hit = self._packs.get(mode)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        taps = self.k * self.k
+        if mode == _lib_pack.FWD:
+            n = taps * self.cout * (self.cin // self.dense_groups)
+        elif mode == _lib_pack.DGRAD:
+            n = taps * self.cin * (self.cout // self.dense_groups)
+        else:
+            n = 4 * self.cout * self.cin
+        out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+        wd = w.detach()
+        if wd.dtype != torch.float32 or not wd.is_contiguous():
+            wd = wd.float().contiguous()
+        _chk("octave_pack_weight", lib.octave_pack_weight(wd.data_ptr(), mode, self.cout, self.cin, self.groups,
+                                                          max(self.dense_groups, 1), self.k, out.data_ptr(), stream_ptr()))
+        self._packs[mode] = (key, out)
+        return out
+
+
+class _lib_pack:
+    FWD, DGRAD, CONVT_FWD, CONVT_DGRAD = 0, 1, 2, 3
+
+
+def _conv_desc(B, H, W, cin, cout, groups, k, stride, pad, x: Act, y: Act, Hout, Wout, mode=0, act=0, accumulate=False,
+               real_groups=0) -> _lib.ConvDesc:
+    d = _lib.ConvDesc()
+    d.B, d.H, d.W, d.cin, d.cout, d.groups, d.ksize, d.stride, d.pad = B, H, W, cin, cout, groups, k, stride, pad
+    d.x_ld, d.x_coff, d.y_ld, d.y_coff = x.ld, x.coff, y.ld, y.coff
+    d.Hout, d.Wout, d.mode, d.relu = Hout, Wout, mode, act
+    d.in_dtype, d.out_dtype = _dt(x.dtype), _dt(y.dtype)
+    d.accumulate, d.real_groups = int(accumulate), real_groups
+    return d
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def conv_out_hw(spec: ConvSpec, H: int, W: int) -> Tuple[int, int]:
+    if spec.transposed:
+        return 2 * H, 2 * W
+    return (H + 2 * spec.pad - spec.k) // spec.stride + 1, (W + 2 * spec.pad - spec.k) // spec.stride + 1
+
+
+def conv_fwd(x: Act, spec: ConvSpec, out: Optional[Act] = None, act: int = 0) -> Act:
+    """Conv2d / ConvTranspose2d forward (+bias, + fused activation).  `out` may be a channel slice of a concat
+    buffer and, for the transposed conv, may be spatially cropped."""
+    Ho, Wo = conv_out_hw(spec, x.H, x.W)
+    if out is None:
+        out = Act.empty(x.B, Ho, Wo, spec.cout, x.dtype, x.device)
+    bias = _f32(spec.bias)
+    if spec.tc_ok(x.dtype) and act in (0, 1):
+        if spec.transposed:
+            d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, 1, 1, 1, 0, x, out, out.H, out.W, mode=_lib.CONV_MODE_CONVT, act=act)
+            wp = spec.pack(_lib_pack.CONVT_FWD)
+        else:
+            d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.dense_groups, spec.k, 1, spec.k // 2, x, out, out.H, out.W, act=act)
+            wp = spec.pack(_lib_pack.FWD)
+        _chk("octave_conv_tc_fwd", lib.octave_conv_tc_fwd(C.byref(d), x.buf.data_ptr(), wp.data_ptr(), _p(bias), out.buf.data_ptr(), stream_ptr()))
+        return out
+    if spec.transposed:
+        # CUDA-core path: 1x1 conv to [B,H,W,4*Cout] (+bias), then 2x2 pixel shuffle into the (cropped) output view
+        w4 = _f32(spec.weight).permute(2, 3, 1, 0).reshape(4 * spec.cout, spec.cin, 1, 1).contiguous()
+        b4 = bias.repeat(4) if bias is not None else None
+        tmp = Act.empty(x.B, x.H, x.W, 4 * spec.cout, x.dtype, x.device)
+        d = _conv_desc(x.B, x.H, x.W, spec.cin, 4 * spec.cout, 1, 1, 1, 0, x, tmp, x.H, x.W, act=act)
+        _chk("octave_conv_direct_fwd", lib.octave_conv_direct_fwd(C.byref(d), x.buf.data_ptr(), w4.data_ptr(), _p(b4), tmp.buf.data_ptr(), stream_ptr()))
+        _chk("octave_depth_to_space", lib.octave_depth_to_space(_ref(tmp), _ref(out), stream_ptr()))
+        return out
+    d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, x, out, out.H, out.W, act=act)
+    _chk("octave_conv_direct_fwd", lib.octave_conv_direct_fwd(C.byref(d), x.buf.data_ptr(), _f32(spec.weight).data_ptr(), _p(bias),
+                                                              out.buf.data_ptr(), stream_ptr()))
+    return out
+
+
+def conv_dgrad(dy: Act, spec: ConvSpec, H: int, W: int, out: Optional[Act] = None, accumulate: bool = False) -> Act:
+    """Gradient w.r.t. the conv input ([B,H,W,cin]).  dy is the gradient of the pre-activation output."""
+    if out is None:
+        out = Act.empty(dy.B, H, W, spec.cin, dy.dtype, dy.device)
+    if spec.tc_ok(dy.dtype):
+        # same implicit GEMM with cin/cout swapped and the flipped/transposed pack
+        d = _conv_desc(dy.B, H, W, spec.cout, spec.cin, spec.dense_groups, spec.k, 1, spec.k // 2, dy, out, H, W, accumulate=accumulate)
+        wp = spec.pack(_lib_pack.DGRAD)
+        _chk("octave_conv_tc_fwd(dgrad)", lib.octave_conv_tc_fwd(C.byref(d), dy.buf.data_ptr(), wp.data_ptr(), None, out.buf.data_ptr(), stream_ptr()))
+        return out
+    d = _conv_desc(dy.B, H, W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, out, dy, dy.H, dy.W, accumulate=accumulate)
+    _chk("octave_conv_direct_dgrad", lib.octave_conv_direct_dgrad(C.byref(d), dy.buf.data_ptr(), _f32(spec.weight).data_ptr(),
+                                                                  out.buf.data_ptr(), stream_ptr()))
+    return out
+
+
+def conv_wgrad(x: Act, dy: Act, spec: ConvSpec):
+    """-> (dW in the torch parameter layout fp32, dbias or None)"""
+    dw = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
+    db = None
+    if spec.tc_ok(x.dtype):
+        d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.dense_groups, spec.k, 1, spec.k // 2, x, dy, dy.H, dy.W,
+                       real_groups=spec.groups)
+        _chk("octave_conv_tc_wgrad", lib.octave_conv_tc_wgrad(C.byref(d), x.buf.data_ptr(), dy.buf.data_ptr(), dw.data_ptr(), stream_ptr()))
+        if spec.bias is not None:
+            db = chan_stats(dy)[:spec.cout].float()
+        return dw, db
+    if spec.bias is not None:
+        db = torch.empty(spec.cout, dtype=torch.float32, device=x.device)
+    d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, x, dy, dy.H, dy.W)
+    _chk("octave_conv_direct_wgrad", lib.octave_conv_direct_wgrad(C.byref(d), x.buf.data_ptr(), dy.buf.data_ptr(), dw.data_ptr(), _p(db), stream_ptr()))
+    return dw, db
+
+
+def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
+    """Backward of ConvTranspose2d(k=2,s=2): dy (possibly cropped view [B,Ho,Wo,cout]) -> (dx, dW [Cin,Cout,2,2], dbias)."""
+    dys = space_to_depth(dy, x.H, x.W)  # [B,H,W,4*cout], zeros where dy was cropped
+    if not spec.tc_ok(x.dtype):
+        w4 = _f32(spec.weight).permute(2, 3, 1, 0).reshape(4 * spec.cout, spec.cin, 1, 1).contiguous()
+        dw4 = torch.empty_like(w4)
+        db4 = torch.empty(4 * spec.cout, dtype=torch.float32, device=x.device) if spec.bias is not None else None
+        d = _conv_desc(x.B, x.H, x.W, spec.cin, 4 * spec.cout, 1, 1, 1, 0, x, dys, x.H, x.W)
+        _chk("octave_conv_direct_wgrad", lib.octave_conv_direct_wgrad(C.byref(d), x.buf.data_ptr(), dys.buf.data_ptr(), dw4.data_ptr(), _p(db4), stream_ptr()))
+        dw = dw4.reshape(2, 2, spec.cout, spec.cin).permute(3, 2, 0, 1).contiguous()
+        db = db4.reshape(4, spec.cout).sum(0) if db4 is not None else None
+        dx = None
+        if need_dx:
+            dx = Act.empty(x.B, x.H, x.W, spec.cin, x.dtype, x.device)
+            _chk("octave_conv_direct_dgrad", lib.octave_conv_direct_dgrad(C.byref(_conv_desc(x.B, x.H, x.W, spec.cin, 4 * spec.cout, 1, 1, 1, 0, dx, dys, x.H, x.W)),
+                                                                          dys.buf.data_ptr(), w4.data_ptr(), dx.buf.data_ptr(), stream_ptr()))
+        return dx, dw, db
+    dw = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
+    d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, 1, 1, 1, 0, x, dys, x.H, x.W, mode=_lib.CONV_MODE_CONVT)
+    _chk("octave_conv_tc_wgrad(convT)", lib.octave_conv_tc_wgrad(C.byref(d), x.buf.data_ptr(), dys.buf.data_ptr(), dw.data_ptr(), stream_ptr()))
+    db = chan_stats(dy)[:spec.cout].float() if spec.bias is not None else None
+    dx = None
+    if need_dx:
+        dx = Act.empty(x.B, x.H, x.W, spec.cin, x.dtype, x.device)
+        dd = _conv_desc(x.B, x.H, x.W, 4 * spec.cout, spec.cin, 1, 1, 1, 0, dys, dx, x.H, x.W)
+        wp = spec.pack(_lib_pack.CONVT_DGRAD)
+        _chk("octave_conv_tc_fwd(convT dgrad)", lib.octave_conv_tc_fwd(C.byref(dd), dys.buf.data_ptr(), wp.data_ptr(), None, dx.buf.data_ptr(), stream_ptr()))
+    return dx, dw, db
