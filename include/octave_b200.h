@@ -213,6 +213,13 @@ int octave_head_wgrad(const OctaveAct* x, const float* dlogits, int32_t K, float
 int octave_nchw_to_nhwc(const float* src, int32_t C_src, const OctaveAct* dst /* C >= C_src, extra channels zeroed */,
                         void* stream);
 int octave_nhwc_to_nchw(const OctaveAct* src, float* dst, int32_t accumulate, void* stream);
+/* InstanceNoise fused into the layout change (discriminator/blocks.py:149-154): dst = clip(src + noise[h][w], 0, 1);
+ * noise (fp32 [H][W], one plane broadcast over batch and channel) and clip are optional. */
+int octave_nchw_to_nhwc_noise(const float* src, int32_t C_src, const float* noise, int32_t clip, const OctaveAct* dst,
+                              void* stream);
+/* its backward: dst = src * 1[0 <= x + noise <= 1] (x: the forward input, NCHW fp32) */
+int octave_nhwc_to_nchw_clipmask(const OctaveAct* src, const float* x, const float* noise, int32_t clip, float* dst,
+                                 void* stream);
 /* dst(h,w) = [accumulate ? dst : 0] + (h < src.H && w < src.W ? src(h,w) : 0): zero-pad (compose.py:125-130) and crop. */
 int octave_copy_window(const OctaveAct* src, const OctaveAct* dst, int32_t accumulate, void* stream);
 /* space-to-depth by 2: dst[h][w][(i*2+j)*C + c] = src[2h+i][2w+j][c] (0 outside src) — data-gradient view of ConvT k2s2 */

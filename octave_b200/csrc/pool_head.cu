@@ -353,14 +353,35 @@ __global__ void head_wgrad_kernel(const OctaveAct x, const float* dlogits, int K
 
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* src, int Cs, const OctaveAct dst) {
+__global__ void nchw_to_nhwc_kernel(const float* src, int Cs, const OctaveAct dst, const float* noise, int clip) {
   const long long hw = (long long)dst.H * dst.W, total = (long long)dst.B * hw * dst.C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % dst.C);
     const long long pix = idx / dst.C;
     const long long n = pix / hw, q = pix - n * hw;
-    const float v = c < Cs ? src[(n * Cs + c) * hw + q] : 0.f;
+    float v = 0.f;
+    if (c < Cs) {
+      v = src[(n * Cs + c) * hw + q];
+      if (noise) v += noise[q];
+      if (clip) v = fminf(fmaxf(v, 0.f), 1.f);
+    }
     *at<T>(dst, pix, c) = from_f<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_clipmask_kernel(const OctaveAct src, const float* x, const float* noise, int clip, float* dst) {
+  const long long hw = (long long)src.H * src.W, total = (long long)src.B * hw * src.C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long q = idx % hw;
+    const int c = (int)((idx / hw) % src.C);
+    const long long n = idx / (hw * src.C);
+    float g = to_f(*at<T>(src, n * hw + q, c));
+    if (clip) {
+      const float v = x[idx] + (noise ? noise[q] : 0.f);
+      if (!(v >= 0.f && v <= 1.f)) g = 0.f;
+    }
+    dst[idx] = g;
   }
 }
 
@@ -554,7 +575,25 @@ extern "C" int octave_head_wgrad(const OctaveAct* x, const float* dlogits, int32
 extern "C" int octave_nchw_to_nhwc(const float* src, int32_t C_src, const OctaveAct* dst, void* stream) {
   if (!src || !view_ok(dst, 1) || C_src > dst->C) return OCT_ERR_INVALID;
   const long long total = (long long)dst->B * dst->H * dst->W * dst->C;
-  DISPATCH_T(dst->dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, C_src, *dst)));
+  DISPATCH_T(dst->dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, C_src, *dst, nullptr, 0)));
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_nchw_to_nhwc_noise(const float* src, int32_t C_src, const float* noise, int32_t clip, const OctaveAct* dst,
+                                         void* stream) {
+  if (!src || !view_ok(dst, 1) || C_src > dst->C) return OCT_ERR_INVALID;
+  const long long total = (long long)dst->B * dst->H * dst->W * dst->C;
+  DISPATCH_T(dst->dtype, (nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, C_src, *dst, noise, clip)));
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_nhwc_to_nchw_clipmask(const OctaveAct* src, const float* x, const float* noise, int32_t clip, float* dst,
+                                            void* stream) {
+  if (!view_ok(src, 1) || !dst || (clip && !x)) return OCT_ERR_INVALID;
+  const long long total = (long long)src->B * src->H * src->W * src->C;
+  DISPATCH_T(src->dtype, (nhwc_to_nchw_clipmask_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src, x, noise, clip, dst)));
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

@@ -1,0 +1,243 @@
+"""Multi-scale LSGAN mask critic on the sm_100a kernels (reference: /root/reference/architectures/discriminator/blocks.py:12-185).
+
+Module tree, parameter names (incl. the legacy spectral-norm `weight_orig/_u/_v`) and init order mirror the reference
+so that state_dicts are interchangeable and a seeded construction gives identical weights.
+
+Noise handling: the reference draws `torch.normal(size=(H,W))` (InstanceNoise, :150) and `FloatTensor(1).uniform_()`
+(LabelNoise via utils.rand_uniform, utils.py:20-22) on the CPU generator per call, moves them to the GPU and — for the
+label flip — reads the comparison back (a device sync).  Here the same CPU draws are made in the same order, the noise
+plane is uploaded asynchronously and the flip decision is taken on the host: same RNG stream, no device sync.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn, Tensor
+from torch.nn.init import kaiming_normal_, xavier_uniform_
+from torch.nn.utils import spectral_norm
+
+from . import ops
+from .network import Grads, _acc, compute_dtype
+from .ops import Act, ConvSpec
+
+
+def rand_uniform(x: Optional[Tensor] = None):
+    """reference utils.py:20-22 — CPU draw; kept on the host (the caller only compares it with a constant)."""
+    return torch.FloatTensor(1).uniform_(0, 1)
+
+
+class InstanceNoise(nn.Module):
+    def __init__(self, input_shape, mean: float, std: float, clipping: bool, is_training: bool):
+        super().__init__()
+        self.mean, self.std, self.clipping = mean, std, clipping
+        self.size = (input_shape[2], input_shape[3])
+        self.is_training = is_training
+
+    def draw(self) -> Tensor:
+        return torch.normal(mean=self.mean, std=self.std, size=self.size)   # blocks.py:150 (CPU generator)
+
+
+class LabelNoise(nn.Module):
+    def __init__(self, prob: float = 0.1, mode: str = 'sign'):
+        super().__init__()
+        self.prob, self.mode = prob, mode
+        if mode != 'sign':
+            raise NotImplementedError("octave_b200: LabelNoise mode 'label' is not constructed by DiscriminatorBlock (blocks.py:77)")
+
+    def draw_flip(self) -> bool:
+        return bool(rand_uniform() < self.prob)                               # blocks.py:165-167
+
+
+class _DiscFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net: "DiscriminatorBlock", n_maps: int, *args):
+        maps, params = args[:n_maps], args[n_maps:]
+        logits, tape = net._fwd(maps)
+        ctx.net, ctx.tape, ctx.params, ctx.n_maps = net, tape, params, n_maps
+        ctx.set_materialize_grads(False)
+        return logits
+
+    @staticmethod
+    def backward(ctx, g):
+        net = ctx.net
+        need_params = any(ctx.needs_input_grad[2 + ctx.n_maps:])
+        need_maps = any(ctx.needs_input_grad[2:2 + ctx.n_maps])
+        grads: Grads = {}
+        gmaps = net._bwd(ctx.tape, g, grads, need_params, need_maps)
+        ctx.tape = None
+        return (None, None, *gmaps, *[grads.get(p) for p in ctx.params])
+
+
+class DiscriminatorBlock(nn.Module):
+    def __init__(self, input_shape, is_training: bool, depth: int = 3, num_filters: int = 64,
+                 instance_noise: bool = True, label_noise: bool = True):
+        super().__init__()
+        self.num_filters, self.is_training, self.depth = num_filters, is_training, depth
+        in_channels = input_shape[1]
+        self.in_channels = in_channels
+        modules = []
+        if instance_noise:
+            modules.append(InstanceNoise(input_shape=input_shape, is_training=is_training, mean=.0, std=.2, clipping=True))
+        conv_0 = nn.Conv2d(in_channels, num_filters, kernel_size=4, stride=2, padding=1)
+        kaiming_normal_(conv_0.weight, nonlinearity='leaky_relu')
+        modules.append(conv_0)
+        modules.append(nn.LeakyReLU(negative_slope=0.2))
+        self.stack_0 = nn.Sequential(*modules)
+        squeeze_stack, spectral_stack = dict(), dict()
+        for i in range(self.depth):
+            squeeze = nn.Sequential(nn.Conv2d(num_filters * (2 ** i), 13, kernel_size=1, stride=1), nn.Sigmoid())
+            conv = nn.Conv2d(13 + in_channels, num_filters * 2 * (2 ** i), kernel_size=4, stride=2, padding=1)
+            conv = spectral_norm(conv, n_power_iterations=1)
+            squeeze_stack[f'squeeze_{i}'] = squeeze
+            spectral_stack[f'spectral_{i}'] = nn.Sequential(conv, nn.Tanh())
+        self.squeeze_dict = nn.ModuleDict(squeeze_stack)
+        self.spectral_dict = nn.ModuleDict(spectral_stack)
+        h, w = [int(i) // (2 ** (self.depth + 1)) for i in input_shape[2:]]
+        fc = nn.Conv2d(num_filters * (2 ** self.depth), out_channels=1, kernel_size=(h, w), stride=1)
+        xavier_uniform_(fc.weight)
+        modules = [fc, nn.Flatten()]
+        if label_noise:
+            modules.append(LabelNoise(0.1, 'sign'))
+        self.out = nn.Sequential(*modules)
+        self._has_inst, self._has_label = bool(instance_noise), bool(label_noise)
+
+    @property
+    def _inst(self):
+        return self.stack_0[0] if self._has_inst else None
+
+    @property
+    def _conv0(self):
+        return self.stack_0[1 if self._has_inst else 0]
+
+    @property
+    def _label(self):
+        return self.out[2] if self._has_label else None
+
+    # ---- spectral norm (torch.nn.utils.spectral_norm legacy semantics, n_power_iterations=1, eps=1e-12) ----
+    def _spectral_weight(self, conv: nn.Module):
+        w = conv.weight_orig.detach()
+        wm = w.reshape(w.shape[0], -1).float().contiguous()
+        u, v = conv.weight_u, conv.weight_v
+        if self.training:
+            v_new = ops.glinear_bwd_data_only(u.reshape(1, -1), wm)          # W^T u
+            v_new = v_new / v_new.norm().clamp_min(1e-12)
+            u_new = ops.glinear_fwd(v_new, wm, None, 1, 1.0)                  # W v
+            u_new = u_new / u_new.norm().clamp_min(1e-12)
+            u.copy_(u_new.reshape(-1)); v.copy_(v_new.reshape(-1))
+        wv = ops.glinear_fwd(v.reshape(1, -1).contiguous(), wm, None, 1, 1.0).reshape(-1)
+        sigma = (u * wv).sum()
+        return w.float() / sigma, sigma, u.clone(), v.clone()
+
+    # ---- explicit passes -------------------------------------------------------------------------------
+    def _fwd(self, maps: Sequence[Tensor]):
+        if len(maps) < self.depth + 1:
+            raise Exception(f'Exception raised in depth = {len(maps) - 1}')
+        y0 = maps[0]
+        if not y0.is_cuda:
+            raise RuntimeError("octave_b200: discriminator input is on CPU; the B200 kernels have no CPU fallback")
+        dt, dev = compute_dtype(), y0.device
+        B, Cin, H, W = y0.shape
+        tape = {}
+        noise_dev, clip = None, False
+        if self._inst is not None:
+            noise = self._inst.draw()
+            if self._inst.is_training:
+                noise_dev = noise.pin_memory().to(dev, non_blocking=True)
+            clip = self._inst.clipping
+        flip = self._label.draw_flip() if self._label is not None else False
+        x0 = Act.zeros(B, H, W, 8, dt, dev)
+        x0v = x0.slice(0, Cin)
+        y0c = y0.detach().contiguous().float()
+        ops.nchw_into(y0c, x0v, noise_dev, clip)                                          # blocks.py:149-154
+        c0 = self._conv0
+        spec0 = ConvSpec(c0.weight, c0.bias, Cin, c0.out_channels, 4, 2, 1, 1)
+        s = ops.conv_fwd(x0v, spec0, act=ops.ACT_LEAKY)                                   # :46-50
+        tape["in"] = (y0c, noise_dev, clip, x0v, spec0, s)
+        levels = []
+        for i in range(self.depth):
+            sq = self.squeeze_dict[f'squeeze_{i}'][0]
+            sn = self.spectral_dict[f'spectral_{i}'][0]
+            yi = maps[i + 1]
+            if yi.shape[2] != s.H or yi.shape[3] != s.W:
+                raise Exception(f'Exception raised in depth = {i}')
+            cat = Act.zeros(B, s.H, s.W, 16, dt, dev)
+            spec_sq = ConvSpec(sq.weight, sq.bias, sq.in_channels, 13, 1, 1, 0, 1)
+            ops.conv_fwd(s, spec_sq, out=cat.slice(0, 13), act=ops.ACT_SIGMOID)           # :121
+            ops.nchw_into(yi.detach(), cat.slice(13, Cin))                                # :122
+            w_sn, sigma, u, v = self._spectral_weight(sn)
+            spec_sn = ConvSpec(w_sn.contiguous(), sn.bias, 13 + Cin, sn.out_channels, 4, 2, 1, 1)
+            catv = cat.slice(0, 13 + Cin)
+            s_next = ops.conv_fwd(catv, spec_sn, act=ops.ACT_TANH)                        # :123
+            levels.append((s, spec_sq, cat, catv, spec_sn, sigma, u, v, s_next))
+            s = s_next
+        fc = self.out[0]
+        kh, kw = fc.kernel_size
+        if (s.H, s.W) != (kh, kw):
+            raise RuntimeError(f"octave_b200: final feature map {s.H}x{s.W} != output kernel {kh}x{kw}")
+        w_hwc = fc.weight.detach().float().permute(0, 2, 3, 1).reshape(1, -1).contiguous()
+        s_flat = s.buf.reshape(B, -1).float()
+        logits = ops.glinear_fwd(s_flat, w_hwc, fc.bias.detach().float(), 1, 1.0)        # :128, [B,1]
+        if flip:
+            logits = -1 * logits                                                          # :167-168
+        tape["levels"], tape["out"], tape["flip"] = levels, (s, s_flat, w_hwc), flip
+        return logits, tape
+
+    def _bwd(self, tape, g: Tensor, grads: Grads, need_params: bool, need_maps: bool):
+        g = g.contiguous().float()
+        if tape["flip"]:
+            g = -1 * g
+        s_last, s_flat, w_hwc = tape["out"]
+        fc = self.out[0]
+        ds_flat, dw, db = ops.glinear_bwd(g, s_flat, w_hwc, 1, 1.0)
+        if need_params:
+            kh, kw = fc.kernel_size
+            _acc(grads, fc.weight, dw.reshape(1, kh, kw, -1).permute(0, 3, 1, 2).contiguous())
+            _acc(grads, fc.bias, db)
+        ds = Act(ds_flat.to(s_last.dtype).reshape(s_last.B, s_last.H, s_last.W, s_last.C), s_last.B, s_last.H, s_last.W, s_last.C)
+        gmaps: List[Optional[Tensor]] = [None] * (self.depth + 1)
+        Cin = self.in_channels
+        for i in reversed(range(self.depth)):
+            s_in, spec_sq, cat, catv, spec_sn, sigma, u, v, s_out = tape["levels"][i]
+            sq = self.squeeze_dict[f'squeeze_{i}'][0]
+            sn = self.spectral_dict[f'spectral_{i}'][0]
+            dz = ops.act_bwd(s_out, ds, ops.ACT_TANH, out=ds)
+            if need_params:
+                dwsn, dbsn = ops.conv_wgrad(catv, dz, spec_sn)
+                wo = sn.weight_orig.detach().float()
+                # W = W_orig / sigma, sigma = u^T W_orig v (u, v constants): dW_orig = dW/sigma - <dW, W_orig>/sigma^2 * u v^T
+                coef = (dwsn * wo).sum() / (sigma * sigma)
+                uv = (u.reshape(-1, 1) * v.reshape(1, -1)).reshape(wo.shape)
+                _acc(grads, sn.weight_orig, dwsn / sigma - coef * uv)
+                _acc(grads, sn.bias, dbsn)
+            dcat = Act.zeros(cat.B, cat.H, cat.W, 16, cat.dtype, cat.device)
+            dcatv = dcat.slice(0, 13 + Cin)
+            ops.conv_dgrad(dz, spec_sn, cat.H, cat.W, out=dcatv)
+            if need_maps:
+                gmaps[i + 1] = ops.nhwc_to_nchw(dcat.slice(13, Cin))
+            dsq = ops.act_bwd(cat.slice(0, 13), dcat.slice(0, 13), ops.ACT_SIGMOID, out=dcat.slice(0, 13))
+            if need_params:
+                dwq, dbq = ops.conv_wgrad(s_in, dsq, spec_sq)
+                _acc(grads, sq.weight, dwq); _acc(grads, sq.bias, dbq)
+            ds = ops.conv_dgrad(dsq, spec_sq, s_in.H, s_in.W)
+        y0c, noise_dev, clip, x0v, spec0, s0 = tape["in"]
+        dz0 = ops.act_bwd(s0, ds, ops.ACT_LEAKY, out=ds)
+        if need_params:
+            dw0, db0 = ops.conv_wgrad(x0v, dz0, spec0)
+            _acc(grads, self._conv0.weight, dw0); _acc(grads, self._conv0.bias, db0)
+        if need_maps:
+            dx0 = Act.zeros(x0v.B, x0v.H, x0v.W, 8, x0v.dtype, x0v.device).slice(0, Cin)
+            ops.conv_dgrad(dz0, spec0, x0v.H, x0v.W, out=dx0)
+            gmaps[0] = ops.nhwc_to_nchw_clipmask(dx0, y0c, noise_dev, clip)
+        return gmaps
+
+    def forward(self, y: Sequence[Tensor]):
+        """y: list of multi-scale maps [B,C,H/2^k,W/2^k] -> logits [B,1] (reference blocks.py:114-130)."""
+        maps = list(y[:self.depth + 1])
+        if len(y) < self.depth + 1:
+            raise Exception(f'Exception raised in depth = {len(y) - 1}')
+        params = list(self.parameters())
+        return _DiscFn.apply(self, len(maps), *maps, *params)
+
+    def predict(self, y: List[Tensor]):
+        return self.forward(y)

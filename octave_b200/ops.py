@@ -118,6 +118,8 @@ _sigs = {
     "octave_head_wgrad": [_A, _vp, C.c_int32, _vp, _vp, _vp],
     "octave_nchw_to_nhwc": [_vp, C.c_int32, _A, _vp],
     "octave_nhwc_to_nchw": [_A, _vp, C.c_int32, _vp],
+    "octave_nchw_to_nhwc_noise": [_vp, C.c_int32, _vp, C.c_int32, _A, _vp],
+    "octave_nhwc_to_nchw_clipmask": [_A, _vp, _vp, C.c_int32, _vp, _vp],
     "octave_copy_window": [_A, _A, C.c_int32, _vp],
     "octave_space_to_depth": [_A, _A, _vp],
     "octave_depth_to_space": [_A, _A, _vp],
@@ -228,6 +230,16 @@ def glinear_bwd(dout: torch.Tensor, inp: torch.Tensor, w: torch.Tensor, groups: 
     return din, dw, db
 
 
+def glinear_bwd_data_only(dout: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """din[b][i] = sum_j dout[b][j] * w[j][i]  (W^T applied to rows of dout)"""
+    B, N = dout.shape
+    Kt = w.shape[1]
+    din = torch.empty((B, Kt), dtype=torch.float32, device=w.device)
+    d = dout.contiguous().float()
+    _chk("octave_glinear_bwd_data", lib.octave_glinear_bwd_data(d.data_ptr(), w.data_ptr(), B, Kt, N, 1, 1.0, din.data_ptr(), stream_ptr()))
+    return din
+
+
 def bn1d_relu_fwd(x: torch.Tensor, gamma, beta, rm, rv, nbt, eps: float, momentum: float, training: bool):
     B, C_ = x.shape
     y = torch.empty_like(x)
@@ -317,6 +329,18 @@ def nchw_to_nhwc(src: torch.Tensor, dtype: torch.dtype, pad_to: int = 8) -> Act:
 def nhwc_to_nchw(src: Act, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     dst = out if out is not None else torch.empty((src.B, src.C, src.H, src.W), dtype=torch.float32, device=src.device)
     _chk("octave_nhwc_to_nchw", lib.octave_nhwc_to_nchw(_ref(src), dst.data_ptr(), int(accumulate), stream_ptr()))
+    return dst
+
+
+def nchw_into(src: torch.Tensor, dst: Act, noise: Optional[torch.Tensor] = None, clip: bool = False) -> None:
+    """Write an NCHW fp32 tensor into the channel view `dst` (dst.C >= src channels), optionally + noise plane and clip."""
+    s = src.contiguous().float()
+    _chk("octave_nchw_to_nhwc_noise", lib.octave_nchw_to_nhwc_noise(s.data_ptr(), s.shape[1], _p(noise), int(clip), _ref(dst), stream_ptr()))
+
+
+def nhwc_to_nchw_clipmask(src: Act, x: Optional[torch.Tensor], noise: Optional[torch.Tensor], clip: bool) -> torch.Tensor:
+    dst = torch.empty((src.B, src.C, src.H, src.W), dtype=torch.float32, device=src.device)
+    _chk("octave_nhwc_to_nchw_clipmask", lib.octave_nhwc_to_nchw_clipmask(_ref(src), _p(x), _p(noise), int(clip), dst.data_ptr(), stream_ptr()))
     return dst
 
 
