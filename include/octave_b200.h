@@ -29,6 +29,8 @@ extern "C" {
 int octave_abi_version(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int octave_sm_count(void);
+/* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
+unsigned long long octave_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K9 — fused loss kernel (forward statistics pass + gradient pass).
@@ -110,11 +112,12 @@ typedef struct OctaveConvDesc {
   int32_t y_ld, y_coff;   /* output view */
   int32_t Hout, Wout;     /* output pixel grid (ConvT: 2H,2W or cropped, compose.py:142-147) */
   int32_t mode;           /* OCT_CONV_MODE_* */
-  int32_t relu;           /* fuse ReLU into the epilogue */
+  int32_t relu;           /* fused activation: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 sigmoid, 4 tanh */
   int32_t in_dtype;       /* direct path: storage type of x / w */
   int32_t out_dtype;      /* storage type of y */
   int32_t accumulate;     /* y += result (fwd/dgrad); dw += result (wgrad) instead of overwrite */
   int32_t real_groups;    /* wgrad: groups of the torch weight when `groups` was merged into dense groups (0 = groups) */
+  int32_t out_s2d_qs;     /* tc fwd: >0 stores the output space-to-depth: pixel (h>>1,w>>1), channel ((h&1)*2+(w&1))*qs + c */
 } OctaveConvDesc;
 
 /* tcgen05 path (bf16 in, fp32 accumulate).  `wpack` is bf16 [taps][Cout][Cin/groups] (ConvT: [4*Cout][Cin],
@@ -247,6 +250,26 @@ int octave_bn1d_relu_bwd(const float* dy, const float* x, const float* y, int32_
 /* att[b][r*C+c] = softmax_r(logits[b][r*C+c]), radix R */
 int octave_rsoftmax_fwd(const float* logits, int32_t B, int32_t R, int32_t C, float* att, void* stream);
 int octave_rsoftmax_bwd(const float* datt, const float* att, int32_t B, int32_t R, int32_t C, float* dlogits, void* stream);
+
+/* Space-to-depth formulation of the discriminator's 4x4 stride-2 pad-1 convs (discriminator/blocks.py:46-50,91-109):
+ * with X'[h'][w'][(i*2+j)*qs + c] = X[2h'+i][2w'+j][c] the conv becomes a 3x3 stride-1 pad-1 conv over 4*qs channels
+ * (tap dh' in {-1,0,1}, parity i: kh = 2dh'+i+1 if 0<=kh<4), which runs on the tcgen05 kernel. */
+int octave_nchw_to_s2d(const float* src, int32_t B, int32_t C, int32_t H, int32_t W, const float* noise, int32_t clip,
+                       const OctaveAct* dst /* [B][ceil(H/2)][ceil(W/2)][4*qs] */, int32_t qs, int32_t coff, void* stream);
+/* dst[b][c][h][w] = src quadrant channel coff+c (optionally masked by 1[0 <= x+noise <= 1], the clip backward) */
+int octave_s2d_to_nchw(const OctaveAct* src, int32_t qs, int32_t coff, int32_t C, int32_t H, int32_t W, const float* x,
+                       const float* noise, int32_t clip, float* dst, void* stream);
+/* w fp32 [cout][cin][4][4] (* scale[0] if scale != NULL) -> bf16 operand: mode 0 [9][cout][4*qs]; mode 1 (dgrad) [9][4*qs][cout] */
+int octave_pack_weight_s2d(const float* w, const float* scale, int32_t mode, int32_t cout, int32_t cin, int32_t qs,
+                           void* out_bf16, void* stream);
+/* dw3 fp32 [cout][4*qs][3][3] (gradient of the remapped weight) -> dw fp32 [cout][cin][4][4] */
+int octave_unpack_wgrad_s2d(const float* dw3, int32_t cout, int32_t cin, int32_t qs, float* dw, void* stream);
+/* Full-extent output conv of the critic (blocks.py:68-71) as one dot product per sample:
+ * out[b] = bias + sum_i x[b][i] * w[i]   (x: NHWC activation flattened per sample, w fp32 in the same order) */
+int octave_rowdot_fwd(const OctaveAct* x, const float* w, const float* bias, float* out /* [B] */, void* stream);
+/* dx[b][i] = g[b] * w[i];  dw[i] = sum_b g[b] * x[b][i];  dbias = sum_b g[b]   (dw/dbias nullable) */
+int octave_rowdot_bwd(const OctaveAct* x, const float* w, const float* g, const OctaveAct* dx, float* dw, float* dbias,
+                      void* stream);
 
 /* Weight re-packing fp32 [Cout][Cin/groups][k][k] (torch layout) -> bf16 operand of the tcgen05 kernels.
  * `dense_groups` <= groups: groups are merged into block-diagonal dense groups (zeros off the diagonal) when the

@@ -88,6 +88,7 @@ _vp = C.c_void_p
 
 lib.octave_abi_version.restype = C.c_int
 lib.octave_sm_count.restype = C.c_int
+lib.octave_launch_count.restype = C.c_ulonglong
 lib.octave_loss_stats_bytes.restype = C.c_size_t
 lib.octave_loss_stats_bytes.argtypes = [C.POINTER(LossDesc)]
 lib.octave_loss_uses_fast_path.restype = C.c_int
@@ -109,7 +110,7 @@ class ConvDesc(C.Structure):
         ("Hout", C.c_int32), ("Wout", C.c_int32),
         ("mode", C.c_int32), ("relu", C.c_int32),
         ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
-        ("accumulate", C.c_int32), ("real_groups", C.c_int32),
+        ("accumulate", C.c_int32), ("real_groups", C.c_int32), ("out_s2d_qs", C.c_int32),
     ]
 
 

@@ -12,8 +12,11 @@
 #define OCT_DTYPE_F32 0
 #define OCT_DTYPE_BF16 1
 
+// every kernel launch site is followed by exactly one OCT_CHECK_LAUNCH(): it also counts launches
+extern unsigned long long g_octave_launches;
 #define OCT_CHECK_LAUNCH()                                   \
   do {                                                       \
+    ++g_octave_launches;                                     \
     cudaError_t e__ = cudaGetLastError();                    \
     if (e__ != cudaSuccess) return OCT_ERR_LAUNCH;           \
   } while (0)

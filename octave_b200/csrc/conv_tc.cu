@@ -40,10 +40,22 @@ struct ConvTcParams {
   long long ldc;
   int c_off, Hout, Wout;
   int scatter;       // 1: ConvTranspose k2s2 — GEMM column n = tap*cout_total + co, pixel (2h+i, 2w+j)
-  int cout_total;    // channels per tap in scatter mode
+                     // 2: space-to-depth store — pixel (h>>1, w>>1), channel += ((h&1)*2 + (w&1)) * s2d_qs
+  int cout_total;    // channels per tap in scatter mode 1
+  int s2d_qs;        // quadrant stride in scatter mode 2
   const float* bias;
-  int relu, out_f32, accumulate;
+  int act, out_f32, accumulate;
 };
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+  switch (act) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return v > 0.f ? v : 0.2f * v;
+    case 3: return 1.f / (1.f + __expf(-v));
+    case 4: return tanhf(v);
+    default: return v;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // forward / dgrad kernel
@@ -135,14 +147,18 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     const int th = r / p.TW, tw = r - th * p.TW;
     const int h = h0 + th, w = w0 + tw;
     bool valid = (r < p.TW * p.TH) && (h < p.H) && (w < p.W);
-    int oh = h, ow = w, cbase = g * p.cout_g + n0;
-    if (p.scatter) {
+    int oh = h, ow = w, cbase = g * p.cout_g + n0, cshift = 0;
+    if (p.scatter == 1) {
       const int tap = cbase / p.cout_total;
       cbase -= tap * p.cout_total;
       oh = 2 * h + (tap >> 1);
       ow = 2 * w + (tap & 1);
-      valid = valid && (oh < p.Hout) && (ow < p.Wout);
+    } else if (p.scatter == 2) {
+      oh = h >> 1;
+      ow = w >> 1;
+      cshift = ((h & 1) * 2 + (w & 1)) * p.s2d_qs;
     }
+    valid = valid && (oh < p.Hout) && (ow < p.Wout);
     const long long pix = ((long long)img * p.Hout + oh) * p.Wout + ow;
     tc::mbar_wait(tc::smem_u32(&acc_bar), 0);
     tc::fence_after_sync();
@@ -159,10 +175,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         for (int i = 0; i < 16; ++i) {
           f[i] = __uint_as_float(v[i]);
           if (p.bias) f[i] += __ldg(p.bias + cbase + c0 + i);
-          if (p.relu) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.act) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
         }
         if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + pix * p.ldc + p.c_off + cbase + c0;
+          float* o = reinterpret_cast<float*>(p.out) + pix * p.ldc + p.c_off + cshift + cbase + c0;
           if (p.accumulate) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] += o[i];
@@ -170,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
         } else {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldc + p.c_off + cbase + c0;
+          bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldc + p.c_off + cshift + cbase + c0;
           if (p.accumulate) {
             float e[16];
             VecIO<bf16, 8>::ld(o, e);
@@ -500,25 +519,30 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
   p.kchunks = cin_g / BK;
   p.cin_g = cin_g;
   p.cout_g = n_cols_g;
+  // A operand dims (Ha, Wa) = the input tensor; GEMM M grid (Hm, Wm) = the output pixel grid (input grid for ConvT).
+  int Ha = d->H, Wa = d->W, B = d->B;
+  int Hm = convt ? d->H : d->Hout, Wm = convt ? d->W : d->Wout;
+  const bool s2d = d->out_s2d_qs > 0;
   // 1x1: flatten all pixels into one long row so that every tile is full
-  int H = d->H, W = d->W, B = d->B;
-  const bool flat = d->ksize == 1 && !convt;
-  if (flat) { W = d->B * d->H * d->W; H = 1; B = 1; }
-  pick_patch(H, W, &p.TW, &p.TH);
-  p.tiles_w = (W + p.TW - 1) / p.TW;
-  p.tiles_h = (H + p.TH - 1) / p.TH;
-  p.H = H; p.W = W;
+  const bool flat = d->ksize == 1 && !convt && !s2d && d->H == d->Hout && d->W == d->Wout;
+  if (flat) { Wa = Wm = d->B * d->H * d->W; Ha = Hm = 1; B = 1; }
+  pick_patch(Hm, Wm, &p.TW, &p.TH);
+  p.tiles_w = (Wm + p.TW - 1) / p.TW;
+  p.tiles_h = (Hm + p.TH - 1) / p.TH;
+  p.H = Hm; p.W = Wm;
   p.out = y; p.ldc = d->y_ld; p.c_off = d->y_coff;
-  p.Hout = flat ? 1 : d->Hout; p.Wout = flat ? W : d->Wout;
-  p.scatter = convt ? 1 : 0; p.cout_total = d->cout;
-  p.bias = bias; p.relu = d->relu; p.out_f32 = d->out_dtype == OCT_DTYPE_F32; p.accumulate = d->accumulate;
+  if (flat) { p.Hout = 1; p.Wout = Wm; }
+  else if (s2d) { p.Hout = (Hm + 1) / 2; p.Wout = (Wm + 1) / 2; }
+  else { p.Hout = d->Hout; p.Wout = d->Wout; }
+  p.scatter = convt ? 1 : (s2d ? 2 : 0); p.cout_total = d->cout; p.s2d_qs = d->out_s2d_qs;
+  p.bias = bias; p.act = d->relu; p.out_f32 = d->out_dtype == OCT_DTYPE_F32; p.accumulate = d->accumulate;
   int BN = 128;
   if (n_cols_g % 128) BN = (n_cols_g % 64 == 0) ? 64 : ((n_cols_g % 32 == 0) ? 32 : 16);
   if (convt && d->cout % BN) BN = (d->cout % 64 == 0) ? 64 : 32;  // a column tile must stay inside one tap
   if (convt && d->cout % BN) return OCT_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmB;
   const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
-  if (!make_act_map(&tmA, xb, d->cin, W, H, B, d->x_ld, BK, p.TW, p.TH, BK * 2)) return OCT_ERR_LAUNCH;
+  if (!make_act_map(&tmA, xb, d->cin, Wa, Ha, B, d->x_ld, BK, p.TW, p.TH, BK * 2)) return OCT_ERR_LAUNCH;
   if (!make_w_map(&tmB, wpack, cin_g, d->groups * n_cols_g, p.taps, BK, BN, BK * 2)) return OCT_ERR_LAUNCH;
   dim3 grid(p.tiles_w * p.tiles_h * B, (n_cols_g + BN - 1) / BN, d->groups);
   if (BK == 64) {
@@ -595,7 +619,7 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
   const bf16* dyb = reinterpret_cast<const bf16*>(dy) + d->y_coff;
   if (!make_act_map(&tmX, xb, d->cin, W, H, B, d->x_ld, CWB, p.TW, p.TH, CWB * 2)) return OCT_ERR_LAUNCH;
-  if (!make_act_map(&tmDY, dyb, cout_all, W, H, B, d->y_ld, CWA, p.TW, p.TH, CWA * 2)) return OCT_ERR_LAUNCH;
+  if (!make_act_map(&tmDY, dyb, cout_all, d->ksize == 1 ? W : d->Wout, d->ksize == 1 ? H : d->Hout, B, d->y_ld, CWA, p.TW, p.TH, CWA * 2)) return OCT_ERR_LAUNCH;
   const size_t wbytes = (size_t)cout_all * p.real_cin_g * p.taps * sizeof(float);
   if (!d->accumulate && cudaMemsetAsync(dw, 0, wbytes, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   dim3 grid(split, n_co_tiles * p.n_ci_tiles, p.taps * d->groups);

@@ -1,0 +1,221 @@
+// Discriminator-specific plumbing: space-to-depth layout changes (with InstanceNoise + clip fused), weight remapping of
+// the 4x4 stride-2 convs onto 3x3 stride-1 convs over space-to-depth inputs (so they run on the tcgen05 kernel), and the
+// full-extent output conv as a per-sample dot product.
+// Reference: /root/reference/architectures/discriminator/blocks.py:46-50,68-71,91-109,149-154.
+#include "common.cuh"
+#include "../../include/octave_b200.h"
+
+namespace {
+
+template <typename T>
+__global__ void nchw_to_s2d_kernel(const float* src, int B, int C, int H, int W, const float* noise, int clip, OctaveAct dst,
+                                   int qs, int coff) {
+  const long long hw = (long long)H * W, total = (long long)B * C * hw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long q = idx % hw;
+    const int c = (int)((idx / hw) % C);
+    const long long n = idx / (hw * C);
+    const int h = (int)(q / W), w = (int)(q - (long long)h * W);
+    float v = src[idx];
+    if (noise) v += noise[q];
+    if (clip) v = fminf(fmaxf(v, 0.f), 1.f);
+    const long long pix = (n * dst.H + (h >> 1)) * dst.W + (w >> 1);
+    reinterpret_cast<T*>(dst.data)[pix * dst.ld + dst.coff + ((h & 1) * 2 + (w & 1)) * qs + coff + c] = from_f<T>(v);
+  }
+}
+
+template <typename T>
+__global__ void s2d_to_nchw_kernel(OctaveAct src, int qs, int coff, int C, int H, int W, const float* x, const float* noise,
+                                   int clip, float* dst) {
+  const long long hw = (long long)H * W, total = (long long)src.B * C * hw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long q = idx % hw;
+    const int c = (int)((idx / hw) % C);
+    const long long n = idx / (hw * C);
+    const int h = (int)(q / W), w = (int)(q - (long long)h * W);
+    const long long pix = (n * src.H + (h >> 1)) * src.W + (w >> 1);
+    float g = to_f(reinterpret_cast<const T*>(src.data)[pix * src.ld + src.coff + ((h & 1) * 2 + (w & 1)) * qs + coff + c]);
+    if (clip) {
+      const float v = x[idx] + (noise ? noise[q] : 0.f);
+      if (!(v >= 0.f && v <= 1.f)) g = 0.f;
+    }
+    dst[idx] = g;
+  }
+}
+
+// remapped weight W3[co][q*qs + c][tap] = W[co][c][kh][kw], kh = 2*(tap/3 - 1) + (q>>1) + 1, kw likewise
+__device__ __forceinline__ float w3_at(const float* w, int cin, int qs, int co, int k, int tap) {
+  const int q = k / qs, c = k - q * qs;
+  if (c >= cin) return 0.f;
+  const int kh = 2 * (tap / 3 - 1) + (q >> 1) + 1, kw = 2 * (tap % 3 - 1) + (q & 1) + 1;
+  if (kh < 0 || kh > 3 || kw < 0 || kw > 3) return 0.f;
+  return w[(((long long)co * cin + c) * 4 + kh) * 4 + kw];
+}
+
+__global__ void pack_s2d_kernel(const float* w, const float* scale, int mode, int cout, int cin, int qs, bf16* out) {
+  const int K = 4 * qs;
+  const long long total = 9LL * cout * K;
+  const float sc = scale ? scale[0] : 1.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    float v;
+    if (mode == 0) {  // [tap][co][k]
+      const int k = (int)(idx % K);
+      const int co = (int)((idx / K) % cout);
+      const int tap = (int)(idx / ((long long)K * cout));
+      v = w3_at(w, cin, qs, co, k, tap);
+    } else {          // [tap'][k][co], tap flipped
+      const int co = (int)(idx % cout);
+      const int k = (int)((idx / cout) % K);
+      const int tap = (int)(idx / ((long long)K * cout));
+      v = w3_at(w, cin, qs, co, k, 8 - tap);
+    }
+    out[idx] = __float2bfloat16_rn(v * sc);
+  }
+}
+
+__global__ void unpack_wgrad_s2d_kernel(const float* dw3, int cout, int cin, int qs, float* dw) {
+  const long long total = (long long)cout * cin * 16;
+  const int K = 4 * qs;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(idx % 4), kh = (int)((idx / 4) % 4);
+    const int c = (int)((idx / 16) % cin);
+    const int co = (int)(idx / (16LL * cin));
+    const int i = (kh + 1) & 1, j = (kw + 1) & 1;
+    const int th = ((kh + 1) >> 1), tw = ((kw + 1) >> 1);  // dh'+1, dw'+1
+    const int k = (i * 2 + j) * qs + c;
+    dw[idx] = dw3[((long long)co * K + k) * 9 + th * 3 + tw];
+  }
+}
+
+template <typename T>
+__global__ void rowdot_fwd_kernel(OctaveAct x, const float* w, float* out) {
+  // grid (chunks, B); x is dense per sample: n = H*W*C elements
+  __shared__ float red[8];
+  const long long n = (long long)x.H * x.W * x.C;
+  const T* xp = reinterpret_cast<const T*>(x.data) + (long long)blockIdx.y * n;
+  float acc = 0.f;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * blockDim.x * 8) {
+    float f[8];
+    VecIO<T, 8>::ld(xp + i, f);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i)), w1 = __ldg(reinterpret_cast<const float4*>(w + i) + 1);
+    acc += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
+  }
+  float v[1] = {acc};
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, v[0]);
+}
+
+__global__ void rowdot_init_kernel(float* out, const float* bias, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = bias ? bias[0] : 0.f;
+}
+
+template <typename T>
+__global__ void rowdot_bwd_kernel(OctaveAct x, const float* w, const float* g, OctaveAct dx, float* dw, float* dbias) {
+  const long long n = (long long)x.H * x.W * x.C;
+  const int B = x.B;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += (long long)gridDim.x * blockDim.x * 8) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i)), w1 = __ldg(reinterpret_cast<const float4*>(w + i) + 1);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < B; ++b) {
+      const float gb = g[b];
+      float f[8], o[8];
+      if (dw) VecIO<T, 8>::ld(reinterpret_cast<const T*>(x.data) + (long long)b * n + i, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        o[k] = gb * wv[k];
+        if (dw) acc[k] += gb * f[k];
+      }
+      VecIO<T, 8>::st(reinterpret_cast<T*>(dx.data) + (long long)b * n + i, o);
+    }
+    if (dw) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dw[i + k] = acc[k];
+    }
+  }
+  if (dbias && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += g[b];
+    dbias[0] = s;
+  }
+}
+
+int grid_for(long long total, int bs) {
+  long long g = (total + bs - 1) / bs;
+  const long long cap = 148LL * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+bool dense(const OctaveAct* a) { return a && a->data && a->coff == 0 && a->ld == a->C && (a->C % 8) == 0; }
+
+}  // namespace
+
+extern "C" int octave_nchw_to_s2d(const float* src, int32_t B, int32_t C, int32_t H, int32_t W, const float* noise, int32_t clip,
+                                  const OctaveAct* dst, int32_t qs, int32_t coff, void* stream) {
+  if (!src || !dst || !dst->data || B <= 0 || C <= 0 || qs <= 0 || coff + C > qs) return OCT_ERR_INVALID;
+  if (dst->H != (H + 1) / 2 || dst->W != (W + 1) / 2 || dst->C < 4 * qs || dst->B != B) return OCT_ERR_INVALID;
+  const long long total = (long long)B * C * H * W;
+  if (dst->dtype == OCT_DTYPE_F32)
+    nchw_to_s2d_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, B, C, H, W, noise, clip, *dst, qs, coff);
+  else
+    nchw_to_s2d_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, B, C, H, W, noise, clip, *dst, qs, coff);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_s2d_to_nchw(const OctaveAct* src, int32_t qs, int32_t coff, int32_t C, int32_t H, int32_t W, const float* x,
+                                  const float* noise, int32_t clip, float* dst, void* stream) {
+  if (!src || !src->data || !dst || qs <= 0 || coff + C > qs || (clip && !x)) return OCT_ERR_INVALID;
+  if (src->H != (H + 1) / 2 || src->W != (W + 1) / 2 || src->C < 4 * qs) return OCT_ERR_INVALID;
+  const long long total = (long long)src->B * C * H * W;
+  if (src->dtype == OCT_DTYPE_F32)
+    s2d_to_nchw_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src, qs, coff, C, H, W, x, noise, clip, dst);
+  else
+    s2d_to_nchw_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src, qs, coff, C, H, W, x, noise, clip, dst);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_pack_weight_s2d(const float* w, const float* scale, int32_t mode, int32_t cout, int32_t cin, int32_t qs,
+                                      void* out, void* stream) {
+  if (!w || !out || cout <= 0 || cin <= 0 || cin > qs || (mode != 0 && mode != 1)) return OCT_ERR_INVALID;
+  const long long total = 9LL * cout * 4 * qs;
+  pack_s2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, mode, cout, cin, qs, (bf16*)out);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_unpack_wgrad_s2d(const float* dw3, int32_t cout, int32_t cin, int32_t qs, float* dw, void* stream) {
+  if (!dw3 || !dw || cin > qs) return OCT_ERR_INVALID;
+  const long long total = (long long)cout * cin * 16;
+  unpack_wgrad_s2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw3, cout, cin, qs, dw);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_rowdot_fwd(const OctaveAct* x, const float* w, const float* bias, float* out, void* stream) {
+  if (!dense(x) || !w || !out) return OCT_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  rowdot_init_kernel<<<(x->B + 127) / 128, 128, 0, s>>>(out, bias, x->B);
+  OCT_CHECK_LAUNCH();
+  const long long n = (long long)x->H * x->W * x->C;
+  int gx = (int)((n / 8 + 255) / 256);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  if (x->dtype == OCT_DTYPE_F32) rowdot_fwd_kernel<float><<<dim3(gx, x->B), 256, 0, s>>>(*x, w, out);
+  else rowdot_fwd_kernel<bf16><<<dim3(gx, x->B), 256, 0, s>>>(*x, w, out);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_rowdot_bwd(const OctaveAct* x, const float* w, const float* g, const OctaveAct* dx, float* dw, float* dbias,
+                                 void* stream) {
+  if (!dense(x) || !dense(dx) || !w || !g || dx->C != x->C || dx->dtype != x->dtype) return OCT_ERR_INVALID;
+  const long long n = (long long)x->H * x->W * x->C;
+  const int gx = grid_for(n / 8, 256);
+  if (x->dtype == OCT_DTYPE_F32) rowdot_bwd_kernel<float><<<gx, 256, 0, (cudaStream_t)stream>>>(*x, w, g, *dx, dw, dbias);
+  else rowdot_bwd_kernel<bf16><<<gx, 256, 0, (cudaStream_t)stream>>>(*x, w, g, *dx, dw, dbias);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}

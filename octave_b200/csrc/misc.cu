@@ -10,3 +10,6 @@ extern "C" int octave_sm_count(void) {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return OCT_ERR_LAUNCH;
   return n;
 }
+
+unsigned long long g_octave_launches = 0;
+extern "C" unsigned long long octave_launch_count(void) { return g_octave_launches; }

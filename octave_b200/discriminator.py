@@ -130,7 +130,135 @@ class DiscriminatorBlock(nn.Module):
         return w.float() / sigma, sigma, u.clone(), v.clone()
 
     # ---- explicit passes -------------------------------------------------------------------------------
+    def _use_tc(self) -> bool:
+        return compute_dtype() == torch.bfloat16 and self.in_channels <= 3 and self.num_filters % 32 == 0
+
     def _fwd(self, maps: Sequence[Tensor]):
+        if self._use_tc():
+            return self._fwd_tc(maps)
+        return self._fwd_plain(maps)
+
+    def _bwd(self, tape, g, grads, need_params, need_maps):
+        if tape.get("tc"):
+            return self._bwd_tc(tape, g, grads, need_params, need_maps)
+        return self._bwd_plain(tape, g, grads, need_params, need_maps)
+
+    # ---- tensor-core path: every 4x4 s2 conv becomes a 3x3 conv over a space-to-depth input -----------------
+    def _noise_and_flip(self, dev):
+        noise_dev, clip = None, False
+        if self._inst is not None:
+            noise = self._inst.draw()
+            if self._inst.is_training:
+                noise_dev = noise.pin_memory().to(dev, non_blocking=True)
+            clip = self._inst.clipping
+        flip = self._label.draw_flip() if self._label is not None else False
+        return noise_dev, clip, flip
+
+    def _fwd_tc(self, maps: Sequence[Tensor]):
+        if len(maps) < self.depth + 1:
+            raise Exception(f'Exception raised in depth = {len(maps) - 1}')
+        y0 = maps[0]
+        if not y0.is_cuda:
+            raise RuntimeError("octave_b200: discriminator input is on CPU; the B200 kernels have no CPU fallback")
+        dt, dev = torch.bfloat16, y0.device
+        B, Cin, H, W = y0.shape
+        noise_dev, clip, flip = self._noise_and_flip(dev)
+        tape = {"tc": True}
+        y0c = y0.detach().contiguous().float()
+        X0 = Act.zeros(B, (H + 1) // 2, (W + 1) // 2, 32, dt, dev)                         # quadrant stride 8
+        ops.nchw_to_s2d(y0c, X0, 8, 0, noise_dev, clip)                                   # blocks.py:149-154
+        c0 = self._conv0
+        nf = c0.out_channels
+        ho, wo = (H + 2 - 4) // 2 + 1, (W + 2 - 4) // 2 + 1
+        s = ops.conv4x4s2_tc_fwd(X0, ops.pack_weight_s2d(c0.weight.detach(), None, 0, 8), c0.bias.detach().float(), nf, ho, wo,
+                                 ops.ACT_LEAKY)                                           # :46-50
+        tape["in"] = (y0c, noise_dev, clip, X0, s, (H, W))
+        levels = []
+        for i in range(self.depth):
+            sq = self.squeeze_dict[f'squeeze_{i}'][0]
+            sn = self.spectral_dict[f'spectral_{i}'][0]
+            yi = maps[i + 1]
+            if yi.shape[2] != s.H or yi.shape[3] != s.W:
+                raise Exception(f'Exception raised in depth = {i}')
+            h, w = s.H, s.W
+            catS = Act.zeros(B, (h + 1) // 2, (w + 1) // 2, 64, dt, dev)                   # quadrant stride 16: 13 + Cin (+pad)
+            w16 = torch.zeros((16, sq.in_channels, 1, 1), dtype=torch.float32, device=dev)
+            w16[:13] = sq.weight.detach()
+            b16 = torch.zeros(16, dtype=torch.float32, device=dev)
+            b16[:13] = sq.bias.detach()
+            spec_sq = ConvSpec(w16, None, sq.in_channels, 16, 1, 1, 0, 1)
+            ops.conv1x1_tc_s2d_store(s, spec_sq.pack(0), b16, 16, catS, 16, ops.ACT_SIGMOID)   # :121
+            ops.nchw_to_s2d(yi.detach(), catS, 16, 13)                                    # :122 (overwrites pad channels 13,14)
+            w_sn, sigma, u, v = self._spectral_weight(sn)
+            inv_sigma = (1.0 / sigma).reshape(1).float()
+            wo_ = sn.weight_orig.detach()
+            ho, wo = (h + 2 - 4) // 2 + 1, (w + 2 - 4) // 2 + 1
+            s_next = ops.conv4x4s2_tc_fwd(catS, ops.pack_weight_s2d(wo_, inv_sigma, 0, 16), sn.bias.detach().float(),
+                                          sn.out_channels, ho, wo, ops.ACT_TANH)          # :123
+            levels.append((s, catS, sigma, inv_sigma, u, v, s_next, (h, w)))
+            s = s_next
+        fc = self.out[0]
+        kh, kw = fc.kernel_size
+        if (s.H, s.W) != (kh, kw):
+            raise RuntimeError(f"octave_b200: final feature map {s.H}x{s.W} != output kernel {kh}x{kw}")
+        w_hwc = fc.weight.detach().float().permute(0, 2, 3, 1).reshape(-1).contiguous()
+        logits = ops.rowdot_fwd(s, w_hwc, fc.bias.detach().float())
+        if flip:
+            logits = -1 * logits
+        tape["levels"], tape["out"], tape["flip"] = levels, (s, w_hwc), flip
+        return logits, tape
+
+    def _bwd_tc(self, tape, g: Tensor, grads: Grads, need_params: bool, need_maps: bool):
+        g = g.contiguous().float()
+        if tape["flip"]:
+            g = -1 * g
+        s_last, w_hwc = tape["out"]
+        fc = self.out[0]
+        ds, dw, db = ops.rowdot_bwd(s_last, w_hwc, g.reshape(-1), need_params)
+        if need_params:
+            kh, kw = fc.kernel_size
+            _acc(grads, fc.weight, dw.reshape(1, kh, kw, -1).permute(0, 3, 1, 2).contiguous())
+            _acc(grads, fc.bias, db)
+        gmaps: List[Optional[Tensor]] = [None] * (self.depth + 1)
+        Cin = self.in_channels
+        for i in reversed(range(self.depth)):
+            s_in, catS, sigma, inv_sigma, u, v, s_out, (h, w) = tape["levels"][i]
+            sq = self.squeeze_dict[f'squeeze_{i}'][0]
+            sn = self.spectral_dict[f'spectral_{i}'][0]
+            dz = ops.act_bwd(s_out, ds, ops.ACT_TANH, out=ds)
+            if need_params:
+                dwsn = ops.conv4x4s2_tc_wgrad(catS, dz, 13 + Cin, 16)
+                wo = sn.weight_orig.detach().float()
+                coef = (dwsn * wo).sum() / (sigma * sigma)
+                uv = (u.reshape(-1, 1) * v.reshape(1, -1)).reshape(wo.shape)
+                _acc(grads, sn.weight_orig, dwsn / sigma - coef * uv)
+                _acc(grads, sn.bias, ops.chan_stats(dz)[:dz.C].float())
+            dcatS = ops.conv4x4s2_tc_dgrad(dz, ops.pack_weight_s2d(sn.weight_orig.detach(), inv_sigma, 1, 16), catS.H, catS.W, 64)
+            if need_maps:
+                gmaps[i + 1] = ops.s2d_to_nchw(dcatS, 16, 13, Cin, h, w)
+            ops.act_bwd(catS, dcatS, ops.ACT_SIGMOID, out=dcatS)
+            dsq16 = Act.empty(catS.B, h, w, 16, catS.dtype, catS.device)
+            ops._chk("octave_depth_to_space", ops.lib.octave_depth_to_space(ops._ref(dcatS), ops._ref(dsq16), ops.stream_ptr()))
+            dsq = dsq16.slice(0, 13)
+            spec_sq = ConvSpec(sq.weight, sq.bias, sq.in_channels, 13, 1, 1, 0, 1)
+            if need_params:
+                # narrow (13-channel) weight gradient: CUDA-core kernel
+                dwq, dbq = ops.conv_wgrad_direct(s_in, dsq, spec_sq)
+                _acc(grads, sq.weight, dwq); _acc(grads, sq.bias, dbq)
+            ds = ops.conv_dgrad_direct(dsq, spec_sq, s_in.H, s_in.W)
+        y0c, noise_dev, clip, X0, s0, (H, W) = tape["in"]
+        dz0 = ops.act_bwd(s0, ds, ops.ACT_LEAKY, out=ds)
+        c0 = self._conv0
+        if need_params:
+            _acc(grads, c0.weight, ops.conv4x4s2_tc_wgrad(X0, dz0, Cin, 8))
+            _acc(grads, c0.bias, ops.chan_stats(dz0)[:dz0.C].float())
+        if need_maps:
+            dX0 = ops.conv4x4s2_tc_dgrad(dz0, ops.pack_weight_s2d(c0.weight.detach(), None, 1, 8), X0.H, X0.W, 32)
+            gmaps[0] = ops.s2d_to_nchw(dX0, 8, 0, Cin, H, W, y0c, noise_dev, clip)
+        return gmaps
+
+    # ---- CUDA-core path (fp32 mode): plain NHWC, direct 4x4 s2 convs ----------------------------------------
+    def _fwd_plain(self, maps: Sequence[Tensor]):
         if len(maps) < self.depth + 1:
             raise Exception(f'Exception raised in depth = {len(maps) - 1}')
         y0 = maps[0]
@@ -175,26 +303,24 @@ class DiscriminatorBlock(nn.Module):
         kh, kw = fc.kernel_size
         if (s.H, s.W) != (kh, kw):
             raise RuntimeError(f"octave_b200: final feature map {s.H}x{s.W} != output kernel {kh}x{kw}")
-        w_hwc = fc.weight.detach().float().permute(0, 2, 3, 1).reshape(1, -1).contiguous()
-        s_flat = s.buf.reshape(B, -1).float()
-        logits = ops.glinear_fwd(s_flat, w_hwc, fc.bias.detach().float(), 1, 1.0)        # :128, [B,1]
+        w_hwc = fc.weight.detach().float().permute(0, 2, 3, 1).reshape(-1).contiguous()
+        logits = ops.rowdot_fwd(s, w_hwc, fc.bias.detach().float())                       # :128, [B,1]
         if flip:
             logits = -1 * logits                                                          # :167-168
-        tape["levels"], tape["out"], tape["flip"] = levels, (s, s_flat, w_hwc), flip
+        tape["levels"], tape["out"], tape["flip"] = levels, (s, w_hwc), flip
         return logits, tape
 
-    def _bwd(self, tape, g: Tensor, grads: Grads, need_params: bool, need_maps: bool):
+    def _bwd_plain(self, tape, g: Tensor, grads: Grads, need_params: bool, need_maps: bool):
         g = g.contiguous().float()
         if tape["flip"]:
             g = -1 * g
-        s_last, s_flat, w_hwc = tape["out"]
+        s_last, w_hwc = tape["out"]
         fc = self.out[0]
-        ds_flat, dw, db = ops.glinear_bwd(g, s_flat, w_hwc, 1, 1.0)
+        ds, dw, db = ops.rowdot_bwd(s_last, w_hwc, g.reshape(-1), need_params)
         if need_params:
             kh, kw = fc.kernel_size
             _acc(grads, fc.weight, dw.reshape(1, kh, kw, -1).permute(0, 3, 1, 2).contiguous())
             _acc(grads, fc.bias, db)
-        ds = Act(ds_flat.to(s_last.dtype).reshape(s_last.B, s_last.H, s_last.W, s_last.C), s_last.B, s_last.H, s_last.W, s_last.C)
         gmaps: List[Optional[Tensor]] = [None] * (self.depth + 1)
         Cin = self.in_channels
         for i in reversed(range(self.depth)):

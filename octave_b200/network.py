@@ -393,13 +393,7 @@ class _SegmentorFn(torch.autograd.Function):
         grads: Grads = {}
         net._bwd(ctx.tape, gouts, grads)
         ctx.tape = None
-        hook = net._grad_ready_hook
-        out = []
-        for p in ctx.params:
-            out.append(grads.get(p))
-        if hook is not None:
-            hook(ctx.params, out)
-        return (None, None, *out)
+        return (None, None, *[grads.get(p) for p in ctx.params])
 
 
 class ResnestUNet(nn.Module):
@@ -552,6 +546,18 @@ class ResnestUNet(nn.Module):
         def cont(t):
             return None if t is None else t.contiguous().float()
 
+        emitted = set()
+
+        def emit():
+            # announce the gradients completed since the last call (data-parallel buckets start their all-reduce now)
+            hook = self._grad_ready_hook
+            if hook is None:
+                return
+            new = [g for p, g in grads.items() if p not in emitted]
+            emitted.update(grads.keys())
+            if new:
+                hook(None, new)
+
         d_f, wfc, bfc = tape["fc"]
         dd, dw, db = ops.head_bwd(d_f, wfc, bfc, 0, cont(g_agg), None)
         _acc(grads, self.fc.weight, dw); _acc(grads, self.fc.bias, db)
@@ -559,22 +565,27 @@ class ResnestUNet(nn.Module):
             dd = self.aag_0.bwd(tape["aag0"], dd, cont(gy.get(0)), grads)
         dd = self.decoder_0.bwd(tape["dec0"], dd, grads)
         dd = self.upsampling_0.bwd(tape["up0"], dd, grads)
+        emit()
         if tape["aag1"] is not None:
             dd = self.aag_1.bwd(tape["aag1"], dd, cont(gy.get(1)), grads)
         dcat1 = self.decoder_1.bwd(tape["dec1"], dd, grads)
         dd = self.upsampling_1.bwd(tape["up1"], dcat1.slice(64, 64), grads)
+        emit()
         if tape["aag2"] is not None:
             dd = self.aag_2.bwd(tape["aag2"], dd, cont(gy.get(2)), grads)
         dcat2 = self.decoder_2.bwd(tape["dec2"], dd, grads)
         dd = self.upsampling_2.bwd(tape["up2"], dcat2.slice(256, 256), grads)
+        emit()
         if tape["aag3"] is not None:
             dd = self.aag_3.bwd(tape["aag3"], dd, cont(gy.get(3)), grads)
         dcat3 = self.decoder_3.bwd(tape["dec3"], dd, grads)
         dd = self.upsampling_3.bwd(tape["up3"], dcat3.slice(512, 512), grads)
+        emit()
         if tape["aag4"] is not None:
             dd = self.aag_4.bwd(tape["aag4"], dd, cont(gy.get(4)), grads)
         dcat4 = self.decoder_4.bwd(tape["dec4"], dd, grads)
         dx4 = self.upsampling_4.bwd(tape["up4"], dcat4.slice(1024, 1024), grads)
+        emit()
         if g_x4 is not None:
             x4 = tape["x4"]
             gx = ops.nchw_to_nhwc(cont(g_x4), x4.dtype)
@@ -584,15 +595,19 @@ class ResnestUNet(nn.Module):
         dx3p = layer_bwd(self.encoder_4, tape["enc4"], dx4, grads)
         dx3 = dcat4.slice(0, 1024)
         ops.copy_window(dx3p, dx3, True)     # crop the padding away and merge with the skip gradient
+        emit()
         dx2 = layer_bwd(self.encoder_3, tape["enc3"], dx3, grads)
         ops.add_inplace(dx2, dcat3.slice(0, 512))
+        emit()
         dx1 = layer_bwd(self.encoder_2, tape["enc2"], dx2, grads)
         ops.add_inplace(dx1, dcat2.slice(0, 256))
+        emit()
         dx01 = layer_bwd(self.encoder_1, tape["enc1"], dx1, grads)
         B, H, W = tape["dims"]
         dx00 = ops.pool_bwd(self._maxpool_pd, dx01, tape["maxpool"], H // 2, W // 2)
         ops.add_inplace(dx00, dcat1.slice(0, 64))
         self._stem_bwd(tape["stem"], dx00, grads)
+        emit()
 
     # ---- public interface ----------------------------------------------------------------------------
     def forward(self, x):

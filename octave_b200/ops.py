@@ -123,6 +123,12 @@ _sigs = {
     "octave_copy_window": [_A, _A, C.c_int32, _vp],
     "octave_space_to_depth": [_A, _A, _vp],
     "octave_depth_to_space": [_A, _A, _vp],
+    "octave_nchw_to_s2d": [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32, _A, C.c_int32, C.c_int32, _vp],
+    "octave_s2d_to_nchw": [_A, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp],
+    "octave_pack_weight_s2d": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+    "octave_unpack_wgrad_s2d": [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+    "octave_rowdot_fwd": [_A, _vp, _vp, _vp, _vp],
+    "octave_rowdot_bwd": [_A, _vp, _vp, _A, _vp, _vp, _vp],
     "octave_glinear_fwd": [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp, _vp],
     "octave_glinear_bwd_data": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp, _vp],
     "octave_glinear_bwd_weight": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp, _vp, _vp],
@@ -389,10 +395,11 @@ class ConvSpec:
         if hit is not None and hit[0] == key:
             return hit[1]
         taps = self.k * self.k
+        dg = max(self.dense_groups, 1)
         if mode == _lib_pack.FWD:
-            n = taps * self.cout * (self.cin // self.dense_groups)
+            n = taps * self.cout * (self.cin // dg)
         elif mode == _lib_pack.DGRAD:
-            n = taps * self.cin * (self.cout // self.dense_groups)
+            n = taps * self.cin * (self.cout // dg)
         else:
             n = 4 * self.cout * self.cin
         out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
@@ -498,6 +505,21 @@ def conv_wgrad(x: Act, dy: Act, spec: ConvSpec):
     return dw, db
 
 
+def conv_wgrad_direct(x: Act, dy: Act, spec: ConvSpec):
+    dw = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
+    db = torch.empty(spec.cout, dtype=torch.float32, device=x.device) if spec.bias is not None else None
+    d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, x, dy, dy.H, dy.W)
+    _chk("octave_conv_direct_wgrad", lib.octave_conv_direct_wgrad(C.byref(d), x.buf.data_ptr(), dy.buf.data_ptr(), dw.data_ptr(), _p(db), stream_ptr()))
+    return dw, db
+
+
+def conv_dgrad_direct(dy: Act, spec: ConvSpec, H: int, W: int) -> Act:
+    out = Act.empty(dy.B, H, W, spec.cin, dy.dtype, dy.device)
+    d = _conv_desc(dy.B, H, W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, out, dy, dy.H, dy.W)
+    _chk("octave_conv_direct_dgrad", lib.octave_conv_direct_dgrad(C.byref(d), dy.buf.data_ptr(), _f32(spec.weight).data_ptr(), out.buf.data_ptr(), stream_ptr()))
+    return out
+
+
 def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
     """Backward of ConvTranspose2d(k=2,s=2): dy (possibly cropped view [B,Ho,Wo,cout]) -> (dx, dW [Cin,Cout,2,2], dbias)."""
     dys = space_to_depth(dy, x.H, x.W)  # [B,H,W,4*cout], zeros where dy was cropped
@@ -525,4 +547,73 @@ def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
         dd = _conv_desc(x.B, x.H, x.W, 4 * spec.cout, spec.cin, 1, 1, 1, 0, dys, dx, x.H, x.W)
         wp = spec.pack(_lib_pack.CONVT_DGRAD)
         _chk("octave_conv_tc_fwd(convT dgrad)", lib.octave_conv_tc_fwd(C.byref(dd), dys.buf.data_ptr(), wp.data_ptr(), None, dx.buf.data_ptr(), stream_ptr()))
+    return dx, dw, db
+
+
+# --- discriminator: space-to-depth formulation on the tensor cores ------------------------------------------
+def nchw_to_s2d(src: torch.Tensor, dst: Act, qs: int, coff: int, noise: Optional[torch.Tensor] = None, clip: bool = False) -> None:
+    s = src.contiguous().float()
+    B, C_, H, W = s.shape
+    _chk("octave_nchw_to_s2d", lib.octave_nchw_to_s2d(s.data_ptr(), B, C_, H, W, _p(noise), int(clip), _ref(dst), qs, coff, stream_ptr()))
+
+
+def s2d_to_nchw(src: Act, qs: int, coff: int, C_: int, H: int, W: int, x: Optional[torch.Tensor] = None,
+                noise: Optional[torch.Tensor] = None, clip: bool = False) -> torch.Tensor:
+    dst = torch.empty((src.B, C_, H, W), dtype=torch.float32, device=src.device)
+    _chk("octave_s2d_to_nchw", lib.octave_s2d_to_nchw(_ref(src), qs, coff, C_, H, W, _p(x), _p(noise), int(clip), dst.data_ptr(), stream_ptr()))
+    return dst
+
+
+def pack_weight_s2d(w: torch.Tensor, scale: Optional[torch.Tensor], mode: int, qs: int) -> torch.Tensor:
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.empty(9 * cout * 4 * qs, dtype=torch.bfloat16, device=w.device)
+    _chk("octave_pack_weight_s2d", lib.octave_pack_weight_s2d(_f32(w).data_ptr(), _p(scale), mode, cout, cin, qs, out.data_ptr(), stream_ptr()))
+    return out
+
+
+def conv4x4s2_tc_fwd(xs: Act, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, Ho: int, Wo: int, act: int) -> Act:
+    """4x4 stride-2 pad-1 conv as a 3x3 conv over the space-to-depth input `xs` ([B,hs,ws,4*qs]); output [B,Ho,Wo,cout]."""
+    y = Act.empty(xs.B, Ho, Wo, cout, xs.dtype, xs.device)
+    d = _conv_desc(xs.B, xs.H, xs.W, xs.C, cout, 1, 3, 1, 1, xs, y, Ho, Wo, act=act)
+    _chk("octave_conv_tc_fwd(s2d)", lib.octave_conv_tc_fwd(C.byref(d), xs.buf.data_ptr(), wpack.data_ptr(), _p(bias), y.buf.data_ptr(), stream_ptr()))
+    return y
+
+
+def conv4x4s2_tc_dgrad(dz: Act, wpack_d: torch.Tensor, hs: int, ws: int, K: int) -> Act:
+    """Gradient w.r.t. the space-to-depth input: 3x3 conv over dz ([B,Ho,Wo,cout]) with the flipped pack -> [B,hs,ws,K]."""
+    dx = Act.empty(dz.B, hs, ws, K, dz.dtype, dz.device)
+    d = _conv_desc(dz.B, dz.H, dz.W, dz.C, K, 1, 3, 1, 1, dz, dx, hs, ws)
+    _chk("octave_conv_tc_fwd(s2d dgrad)", lib.octave_conv_tc_fwd(C.byref(d), dz.buf.data_ptr(), wpack_d.data_ptr(), None, dx.buf.data_ptr(), stream_ptr()))
+    return dx
+
+
+def conv4x4s2_tc_wgrad(xs: Act, dz: Act, cin: int, qs: int) -> torch.Tensor:
+    """-> dW fp32 [cout][cin][4][4]"""
+    cout = dz.C
+    dw3 = torch.empty((cout, xs.C, 3, 3), dtype=torch.float32, device=xs.device)
+    d = _conv_desc(xs.B, xs.H, xs.W, xs.C, cout, 1, 3, 1, 1, xs, dz, dz.H, dz.W)
+    _chk("octave_conv_tc_wgrad(s2d)", lib.octave_conv_tc_wgrad(C.byref(d), xs.buf.data_ptr(), dz.buf.data_ptr(), dw3.data_ptr(), stream_ptr()))
+    dw = torch.empty((cout, cin, 4, 4), dtype=torch.float32, device=xs.device)
+    _chk("octave_unpack_wgrad_s2d", lib.octave_unpack_wgrad_s2d(dw3.data_ptr(), cout, cin, qs, dw.data_ptr(), stream_ptr()))
+    return dw
+
+
+def conv1x1_tc_s2d_store(x: Act, wpack: torch.Tensor, bias: torch.Tensor, cout: int, dst: Act, qs: int, act: int) -> None:
+    """1x1 conv (+bias, +act) whose output pixel (h,w) is stored space-to-depth into `dst` ([B,ceil(h/2),ceil(w/2),4*qs])."""
+    d = _conv_desc(x.B, x.H, x.W, x.C, cout, 1, 1, 1, 0, x, dst, x.H, x.W, act=act)
+    d.out_s2d_qs = qs
+    _chk("octave_conv_tc_fwd(s2d store)", lib.octave_conv_tc_fwd(C.byref(d), x.buf.data_ptr(), wpack.data_ptr(), bias.data_ptr(), dst.buf.data_ptr(), stream_ptr()))
+
+
+def rowdot_fwd(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    out = torch.empty((x.B, 1), dtype=torch.float32, device=x.device)
+    _chk("octave_rowdot_fwd", lib.octave_rowdot_fwd(_ref(x), w.data_ptr(), _p(bias), out.data_ptr(), stream_ptr()))
+    return out
+
+
+def rowdot_bwd(x: Act, w: torch.Tensor, g: torch.Tensor, need_dw: bool):
+    dx = x.like()
+    dw = torch.empty_like(w) if need_dw else None
+    db = torch.empty(1, dtype=torch.float32, device=x.device) if need_dw else None
+    _chk("octave_rowdot_bwd", lib.octave_rowdot_bwd(_ref(x), w.data_ptr(), g.data_ptr(), _ref(dx), _p(dw), _p(db), stream_ptr()))
     return dx, dw, db

