@@ -259,11 +259,12 @@ int octave_nchw_to_s2d(const float* src, int32_t B, int32_t C, int32_t H, int32_
 /* dst[b][c][h][w] = src quadrant channel coff+c (optionally masked by 1[0 <= x+noise <= 1], the clip backward) */
 int octave_s2d_to_nchw(const OctaveAct* src, int32_t qs, int32_t coff, int32_t C, int32_t H, int32_t W, const float* x,
                        const float* noise, int32_t clip, float* dst, void* stream);
-/* w fp32 [cout][cin][4][4] (* scale[0] if scale != NULL) -> bf16 operand: mode 0 [9][cout][4*qs]; mode 1 (dgrad) [9][4*qs][cout] */
+/* The same remap serves the stem's 3x3 stride-2 pad-1 conv (resnest.py:327): ksize 3 (valid kh in 0..2) or 4.
+ * w fp32 [cout][cin][k][k] (* scale[0] if scale != NULL) -> bf16 operand: mode 0 [9][cout][4*qs]; mode 1 (dgrad) [9][4*qs][cout] */
 int octave_pack_weight_s2d(const float* w, const float* scale, int32_t mode, int32_t cout, int32_t cin, int32_t qs,
-                           void* out_bf16, void* stream);
-/* dw3 fp32 [cout][4*qs][3][3] (gradient of the remapped weight) -> dw fp32 [cout][cin][4][4] */
-int octave_unpack_wgrad_s2d(const float* dw3, int32_t cout, int32_t cin, int32_t qs, float* dw, void* stream);
+                           int32_t ksize, void* out_bf16, void* stream);
+/* dw3 fp32 [cout][4*qs][3][3] (gradient of the remapped weight) -> dw fp32 [cout][cin][k][k] */
+int octave_unpack_wgrad_s2d(const float* dw3, int32_t cout, int32_t cin, int32_t qs, int32_t ksize, float* dw, void* stream);
 /* Full-extent output conv of the critic (blocks.py:68-71) as one dot product per sample:
  * out[b] = bias + sum_i x[b][i] * w[i]   (x: NHWC activation flattened per sample, w fp32 in the same order) */
 int octave_rowdot_fwd(const OctaveAct* x, const float* w, const float* bias, float* out /* [B] */, void* stream);

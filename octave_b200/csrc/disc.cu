@@ -44,15 +44,15 @@ __global__ void s2d_to_nchw_kernel(OctaveAct src, int qs, int coff, int C, int H
 }
 
 // remapped weight W3[co][q*qs + c][tap] = W[co][c][kh][kw], kh = 2*(tap/3 - 1) + (q>>1) + 1, kw likewise
-__device__ __forceinline__ float w3_at(const float* w, int cin, int qs, int co, int k, int tap) {
+__device__ __forceinline__ float w3_at(const float* w, int cin, int qs, int ksz, int co, int k, int tap) {
   const int q = k / qs, c = k - q * qs;
   if (c >= cin) return 0.f;
   const int kh = 2 * (tap / 3 - 1) + (q >> 1) + 1, kw = 2 * (tap % 3 - 1) + (q & 1) + 1;
-  if (kh < 0 || kh > 3 || kw < 0 || kw > 3) return 0.f;
-  return w[(((long long)co * cin + c) * 4 + kh) * 4 + kw];
+  if (kh < 0 || kh >= ksz || kw < 0 || kw >= ksz) return 0.f;
+  return w[(((long long)co * cin + c) * ksz + kh) * ksz + kw];
 }
 
-__global__ void pack_s2d_kernel(const float* w, const float* scale, int mode, int cout, int cin, int qs, bf16* out) {
+__global__ void pack_s2d_kernel(const float* w, const float* scale, int mode, int cout, int cin, int qs, int ksz, bf16* out) {
   const int K = 4 * qs;
   const long long total = 9LL * cout * K;
   const float sc = scale ? scale[0] : 1.f;
@@ -62,24 +62,25 @@ __global__ void pack_s2d_kernel(const float* w, const float* scale, int mode, in
       const int k = (int)(idx % K);
       const int co = (int)((idx / K) % cout);
       const int tap = (int)(idx / ((long long)K * cout));
-      v = w3_at(w, cin, qs, co, k, tap);
+      v = w3_at(w, cin, qs, ksz, co, k, tap);
     } else {          // [tap'][k][co], tap flipped
       const int co = (int)(idx % cout);
       const int k = (int)((idx / cout) % K);
       const int tap = (int)(idx / ((long long)K * cout));
-      v = w3_at(w, cin, qs, co, k, 8 - tap);
+      v = w3_at(w, cin, qs, ksz, co, k, 8 - tap);
     }
     out[idx] = __float2bfloat16_rn(v * sc);
   }
 }
 
-__global__ void unpack_wgrad_s2d_kernel(const float* dw3, int cout, int cin, int qs, float* dw) {
-  const long long total = (long long)cout * cin * 16;
+__global__ void unpack_wgrad_s2d_kernel(const float* dw3, int cout, int cin, int qs, int ksz, float* dw) {
+  const int kk = ksz * ksz;
+  const long long total = (long long)cout * cin * kk;
   const int K = 4 * qs;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int kw = (int)(idx % 4), kh = (int)((idx / 4) % 4);
-    const int c = (int)((idx / 16) % cin);
-    const int co = (int)(idx / (16LL * cin));
+    const int kw = (int)(idx % ksz), kh = (int)((idx / ksz) % ksz);
+    const int c = (int)((idx / kk) % cin);
+    const int co = (int)(idx / ((long long)kk * cin));
     const int i = (kh + 1) & 1, j = (kw + 1) & 1;
     const int th = ((kh + 1) >> 1), tw = ((kw + 1) >> 1);  // dh'+1, dw'+1
     const int k = (i * 2 + j) * qs + c;
@@ -178,18 +179,18 @@ extern "C" int octave_s2d_to_nchw(const OctaveAct* src, int32_t qs, int32_t coff
 }
 
 extern "C" int octave_pack_weight_s2d(const float* w, const float* scale, int32_t mode, int32_t cout, int32_t cin, int32_t qs,
-                                      void* out, void* stream) {
-  if (!w || !out || cout <= 0 || cin <= 0 || cin > qs || (mode != 0 && mode != 1)) return OCT_ERR_INVALID;
+                                      int32_t ksize, void* out, void* stream) {
+  if (!w || !out || cout <= 0 || cin <= 0 || cin > qs || (mode != 0 && mode != 1) || (ksize != 3 && ksize != 4)) return OCT_ERR_INVALID;
   const long long total = 9LL * cout * 4 * qs;
-  pack_s2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, mode, cout, cin, qs, (bf16*)out);
+  pack_s2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, scale, mode, cout, cin, qs, ksize, (bf16*)out);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
 
-extern "C" int octave_unpack_wgrad_s2d(const float* dw3, int32_t cout, int32_t cin, int32_t qs, float* dw, void* stream) {
-  if (!dw3 || !dw || cin > qs) return OCT_ERR_INVALID;
-  const long long total = (long long)cout * cin * 16;
-  unpack_wgrad_s2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw3, cout, cin, qs, dw);
+extern "C" int octave_unpack_wgrad_s2d(const float* dw3, int32_t cout, int32_t cin, int32_t qs, int32_t ksize, float* dw, void* stream) {
+  if (!dw3 || !dw || cin > qs || (ksize != 3 && ksize != 4)) return OCT_ERR_INVALID;
+  const long long total = (long long)cout * cin * ksize * ksize;
+  unpack_wgrad_s2d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dw3, cout, cin, qs, ksize, dw);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

@@ -18,7 +18,10 @@ struct Geo {
   dim3 grid;
 };
 
-bool make_geo(const OctaveAct* a, Geo* g, int max_blocks_x = 0) {
+constexpr int kReduceBlocks = 148 * 4;   // total blocks of a reduction kernel: bounds the atomics per channel
+constexpr int kStreamBlocks = 148 * 16;
+
+bool make_geo(const OctaveAct* a, Geo* g, int total_blocks = kStreamBlocks) {
   if (a->C % 8) return false;
   g->G = a->C / 8;
   if (g->G > 1024) return false;
@@ -26,7 +29,7 @@ bool make_geo(const OctaveAct* a, Geo* g, int max_blocks_x = 0) {
   g->ppb = g->bs / g->G;
   const long long hw = (long long)a->H * a->W;
   long long bx = (hw + g->ppb - 1) / g->ppb;
-  long long cap = max_blocks_x > 0 ? max_blocks_x : (long long)(148 * 16 + a->B - 1) / a->B;
+  long long cap = (long long)(total_blocks + a->B - 1) / a->B;
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
   g->grid = dim3((unsigned)bx, (unsigned)a->B);
@@ -75,11 +78,22 @@ __global__ void chan_stats_kernel(const OctaveAct x, double* sums) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float f[8];
-    VecIO<T, 8>::ld(at<T>(x, base + p, cg * 8), f);
+  const long long step = (long long)gridDim.x * ppb;
+  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += 4 * step) {
+    float f[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] += f[i]; v[8 + i] += f[i] * f[i]; }
+    for (int u = 0; u < 4; ++u) {
+      if (p + u * step < hw) VecIO<T, 8>::ld(at<T>(x, base + p + u * step, cg * 8), f[u]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] += f[u][i]; v[8 + i] += f[u][i] * f[u][i]; }
+    }
   }
   fold_lanes<16>(v, sm, G);
   if (threadIdx.x < G) {
@@ -179,20 +193,29 @@ __global__ void bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, i
     inv[i] = mi[x.C + cg * 8 + i];
     v[i] = v[8 + i] = 0.f;
   }
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float d[8], f[8];
-    VecIO<T, 8>::ld(at<T>(dy, base + p, cg * 8), d);
-    VecIO<T, 8>::ld(at<T>(x, base + p, cg * 8), f);
-    if (has_mask) {
-      float m[8];
-      VecIO<T, 8>::ld(at<T>(mask, base + p, cg * 8), m);
+  const long long step = (long long)gridDim.x * ppb;
+  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += 2 * step) {
+    float d[2][8], f[2][8], m[2][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+    for (int u = 0; u < 2; ++u) {
+      const bool ok = p + u * step < hw;
+      const long long q = ok ? p + u * step : p;
+      VecIO<T, 8>::ld(at<T>(dy, base + q, cg * 8), d[u]);
+      VecIO<T, 8>::ld(at<T>(x, base + q, cg * 8), f[u]);
+      if (has_mask) VecIO<T, 8>::ld(at<T>(mask, base + q, cg * 8), m[u]);
+      if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[u][i] = 0.f;
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[i] += d[i];
-      v[8 + i] += d[i] * (f[i] - mean[i]) * inv[i];
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dd = (has_mask && !(m[u][i] > 0.f)) ? 0.f : d[u][i];
+        v[i] += dd;
+        v[8 + i] += dd * (f[u][i] - mean[i]) * inv[i];
+      }
     }
   }
   fold_lanes<16>(v, sm, G);
@@ -367,7 +390,7 @@ __global__ void splat_bwd_du_kernel(const OctaveAct dout, const OctaveAct mask, 
 extern "C" int octave_chan_stats(const OctaveAct* x, double* sums, void* stream) {
   if (!view_ok(x) || !sums) return OCT_ERR_INVALID;
   Geo g;
-  if (!make_geo(x, &g)) return OCT_ERR_UNSUPPORTED;
+  if (!make_geo(x, &g, kReduceBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   DISPATCH_T(x->dtype, (chan_stats_kernel<T><<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*x, sums)));
@@ -394,7 +417,7 @@ extern "C" int octave_affine_act(const OctaveAct* x, const float* ab, const Octa
   if (res && (!view_ok(res) || !same_shape(x, res))) return OCT_ERR_INVALID;
   if (gap && (x->C % 16)) return OCT_ERR_INVALID;
   Geo g;
-  if (!make_geo(x, &g)) return OCT_ERR_UNSUPPORTED;
+  if (!make_geo(x, &g, gap ? kReduceBlocks * 2 : kStreamBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (gap && cudaMemsetAsync(gap, 0, sizeof(float) * x->B * (x->C / 2), s) != cudaSuccess) return OCT_ERR_LAUNCH;
   OctaveAct r = res ? *res : *x;
@@ -409,7 +432,7 @@ extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, 
   if (!view_ok(dy) || !view_ok(x) || !same_shape(dy, x) || !mean_invstd || !sums2) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, x))) return OCT_ERR_INVALID;
   Geo g;
-  if (!make_geo(x, &g)) return OCT_ERR_UNSUPPORTED;
+  if (!make_geo(x, &g, kReduceBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   OctaveAct m = mask ? *mask : *x;
@@ -469,7 +492,7 @@ extern "C" int octave_splat_bwd_reduce(const OctaveAct* dout, const OctaveAct* m
   if (U->C != 2 * dout->C || U->B != dout->B || U->H != dout->H || U->W != dout->W || U->dtype != dout->dtype) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, dout))) return OCT_ERR_INVALID;
   Geo g;
-  if (!make_geo(dout, &g)) return OCT_ERR_UNSUPPORTED;
+  if (!make_geo(dout, &g, kReduceBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(datt, 0, sizeof(float) * dout->B * 2 * dout->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   OctaveAct m = mask ? *mask : *dout;

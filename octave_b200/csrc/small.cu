@@ -32,16 +32,29 @@ __global__ void glinear_fwd_kernel(const float* in, const float* w, const float*
   }
 }
 
-// one thread per (b, i)
+// thread per input feature i (weight reads coalesced over i), blockIdx.y splits the outputs j of i's group,
+// BCHUNK batch rows share every weight load; partial sums are merged with atomics into the zeroed din
 __global__ void glinear_bwd_data_kernel(const float* dout, const float* w, int B, int Kt, int N, int groups, float scale,
                                         float* din) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * Kt) return;
-  const int b = (int)(idx / Kt), i = (int)(idx % Kt);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Kt) return;
   const int Kg = Kt / groups, Ng = N / groups, g = i / Kg, il = i - g * Kg;
-  float acc = 0.f;
-  for (int j = 0; j < Ng; ++j) acc += dout[(long long)b * N + g * Ng + j] * w[(long long)(g * Ng + j) * Kg + il];
-  din[idx] = acc * scale;
+  const int chunk = (Ng + gridDim.y - 1) / gridDim.y;
+  const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, Ng);
+  for (int b0 = 0; b0 < B; b0 += BCHUNK) {
+    float acc[BCHUNK];
+#pragma unroll
+    for (int r = 0; r < BCHUNK; ++r) acc[r] = 0.f;
+    for (int j = j0; j < j1; ++j) {
+      const float wv = w[(long long)(g * Ng + j) * Kg + il];
+#pragma unroll
+      for (int r = 0; r < BCHUNK; ++r)
+        if (b0 + r < B) acc[r] += dout[(long long)(b0 + r) * N + g * Ng + j] * wv;
+    }
+#pragma unroll
+    for (int r = 0; r < BCHUNK; ++r)
+      if (b0 + r < B) atomicAdd(din + (long long)(b0 + r) * Kt + i, acc[r] * scale);
+  }
 }
 
 // one thread per (j, i)
@@ -188,8 +201,13 @@ extern "C" int octave_glinear_fwd(const float* in, const float* w, const float* 
 extern "C" int octave_glinear_bwd_data(const float* dout, const float* w, int32_t B, int32_t Kt, int32_t N, int32_t groups,
                                        float in_scale, float* din, void* stream) {
   if (!dout || !w || !din || B <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
-  const long long total = (long long)B * Kt;
-  glinear_bwd_data_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dout, w, B, Kt, N, groups, in_scale, din);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(din, 0, sizeof(float) * (size_t)B * Kt, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  const int Ng = N / groups;
+  int split = Ng / 16;
+  if (split < 1) split = 1;
+  if (split > 64) split = 64;
+  glinear_bwd_data_kernel<<<dim3((Kt + 127) / 128, split), 128, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

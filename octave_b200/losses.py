@@ -20,7 +20,7 @@ _OUT_WPCE, _OUT_DICE, _OUT_KLD, _OUT_LSG, _OUT_LSD, _OUT_NAN = 0, 1, 2, 3, 4, 5
 
 
 def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _require_cuda(t: Tensor, name: str) -> None:

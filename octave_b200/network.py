@@ -445,10 +445,20 @@ class ResnestUNet(nn.Module):
     def _hot_params(self) -> List[nn.Parameter]:
         return [p for n, p in self.named_parameters() if not n.startswith("linear_head_")]
 
-    def _stem_fwd(self, x: Act, out: Act):
+    def _stem_fwd(self, x, out: Act):
+        """x: Act (fp32 mode, NHWC with 3 of 8 channels) or, in bf16 mode, the raw NCHW fp32 tensor: the 3x3 stride-2
+        conv then runs on the tensor cores as a 3x3 stride-1 conv over the space-to-depth input (see disc.cu)."""
         seq, bn1 = self.encoder_0_1_2[0], self.encoder_0_1_2[1]
         tr = self.training
-        z0 = ops.conv_fwd(x, _spec(seq[0]))
+        if isinstance(x, Act):
+            z0 = ops.conv_fwd(x, _spec(seq[0]))
+        else:
+            B, _, H, W = x.shape
+            xs = Act.zeros(B, H // 2, W // 2, 32, torch.bfloat16, x.device)
+            ops.nchw_to_s2d(x, xs, 8, 0)
+            z0 = ops.conv4x4s2_tc_fwd(xs, ops.pack_weight_s2d(seq[0].weight.detach(), None, 0, 8), None, seq[0].out_channels,
+                                      H // 2, W // 2, 0)
+            x = xs
         y0, c0, _ = bn_fwd(seq[1], z0, tr, True)
         z1 = ops.conv_fwd(y0, _spec(seq[3]))
         y1, c1, _ = bn_fwd(seq[4], z1, tr, True)
@@ -464,7 +474,10 @@ class ResnestUNet(nn.Module):
         dz1 = bn_bwd(c1, dy1, y1, grads, out=dy1)
         dy0 = conv_bwd(seq[3], y0, dz1, grads)
         dz0 = bn_bwd(c0, dy0, y0, grads, out=dy0)
-        conv_bwd(seq[0], x, dz0, grads, need_dx=False)
+        if x.C == 32:   # space-to-depth tensor-core path
+            _acc(grads, seq[0].weight, ops.conv4x4s2_tc_wgrad(x, dz0, 3, 8, 3))
+        else:
+            conv_bwd(seq[0], x, dz0, grads, need_dx=False)
 
     def _fwd(self, x: Tensor):
         """x: [B,3,H,W] (any float dtype) -> ((att..., agg_map, x_4) as fp32 NCHW tensors, tape)"""
@@ -478,7 +491,7 @@ class ResnestUNet(nn.Module):
                              f"fail otherwise, compose.py:141-169)")
         dt, dev = compute_dtype(), x.device
         tape = {}
-        xa = ops.nchw_to_nhwc(x, dt)
+        xa = ops.nchw_to_nhwc(x, dt) if dt != torch.bfloat16 else x.detach()
         cat1 = Act.empty(B, H // 2, W // 2, 128, dt, dev)
         cat2 = Act.empty(B, H // 4, W // 4, 512, dt, dev)
         cat3 = Act.empty(B, H // 8, W // 8, 1024, dt, dev)

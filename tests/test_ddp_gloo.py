@@ -1,0 +1,55 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the bucketed gradient all-reducer used by TrainStep (the data path
+has no other collective: batch shards are independent, BatchNorm statistics stay per replica — SURVEY.md §8e)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from octave_b200.train import GradAllReducer
+    torch.manual_seed(0)
+    shapes = [(64, 32, 3, 3), (64,), (128, 64, 1, 1), (2, 32), (1024, 512, 3, 3), (7,)]
+    base = [torch.randn(s) for s in shapes]
+    grads = [b * (rank + 1) for b in base]          # rank r holds (r+1) * base
+    red = GradAllReducer(bucket_bytes=1 << 16)      # small buckets: several flushes, one oversized tensor
+    red.reduce(grads[:2]); red.reduce([None] + grads[2:4]); red.reduce(grads[4:])
+    red.finish()
+    mean = sum(range(1, world + 1)) / world
+    ok = all(torch.allclose(g, b * mean, rtol=1e-6, atol=1e-6) for g, b in zip(grads, base))
+    # second use of the same reducer (next step) must start clean
+    g2 = [torch.full((10,), float(rank))]
+    red.reduce(g2); red.finish()
+    ok = ok and torch.allclose(g2[0], torch.full((10,), (world - 1) / 2))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_single_process_is_a_no_op():
+    from octave_b200.train import GradAllReducer
+    red = GradAllReducer()
+    g = [torch.ones(3)]
+    red.reduce(g); red.finish()
+    assert torch.equal(g[0], torch.ones(3))
