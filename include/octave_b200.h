@@ -123,8 +123,10 @@ typedef struct OctaveConvDesc {
 /* tcgen05 path (bf16 in, fp32 accumulate).  `wpack` is bf16 [taps][Cout][Cin/groups] (ConvT: [4*Cout][Cin],
  * row = (i*2+j)*Cout + co).  Data gradient = the same entry point with the dgrad pack and cin/cout swapped. */
 int octave_conv_tc_supported(const OctaveConvDesc* d);
+/* stats (nullable, fp64 [2*cout], overwritten): per-channel sum and sum of squares of the stored outputs — the batch
+ * statistics of the BatchNorm that follows (resnest.py:25,86,182,224,338), fused into the conv epilogue. */
 int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
-                       void* stream);
+                       double* stats, void* stream);
 /* dw: fp32 gradient in the torch parameter layout ([Cout][Cin/real_groups][k][k]; ConvT: [Cin][Cout][2][2]),
  * overwritten unless `accumulate`.  x = forward input view, dy = output-gradient view (x_* / y_* of the descriptor;
  * for ConvT dy is the space-to-depth view with 4*cout channels). */

@@ -120,7 +120,7 @@ CONV_MODE_CONVT = 1
 lib.octave_conv_tc_supported.restype = C.c_int
 lib.octave_conv_tc_supported.argtypes = [C.POINTER(ConvDesc)]
 lib.octave_conv_tc_fwd.restype = C.c_int
-lib.octave_conv_tc_fwd.argtypes = [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]
+lib.octave_conv_tc_fwd.argtypes = [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp]
 lib.octave_conv_tc_wgrad_supported.restype = C.c_int
 lib.octave_conv_tc_wgrad_supported.argtypes = [C.POINTER(ConvDesc)]
 lib.octave_conv_tc_wgrad.restype = C.c_int

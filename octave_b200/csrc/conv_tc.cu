@@ -34,6 +34,7 @@ struct ConvTcParams {
   int kchunks;   // Cin_g / BK
   int cin_g, cout_g;
   int tiles_w, tiles_h, TW, TH;
+  int n_tiles, groups;
   int H, W;      // extent of the pixel grid the GEMM M dimension runs over
   // output addressing: pixel (n, oh, ow) -> out + ((n*Hout + oh)*Wout + ow)*ldc + c_off + channel
   void* out;
@@ -45,6 +46,9 @@ struct ConvTcParams {
   int s2d_qs;        // quadrant stride in scatter mode 2
   const float* bias;
   int act, out_f32, accumulate;
+  long long total_tiles;
+  double* stats;        // nullable: [2][stats_stride] per-channel sum, sum of squares of the stored outputs
+  int stats_stride;
 };
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -58,42 +62,52 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// forward / dgrad kernel
+// forward / dgrad kernel — persistent: one CTA per SM loops over output tiles (N tile fastest, so the CTAs that
+// share an A tile run side by side and hit L2).  Two TMEM accumulators: the epilogue of tile i (TMEM -> registers ->
+// bias/activation -> bf16 -> warp-private padded smem -> 16-byte coalesced global stores) overlaps the TMA/MMA main
+// loop of tile i+1.  Optional fused BatchNorm statistics: per-channel sum / sum of squares of the stored (bf16-rounded)
+// outputs are reduced across the 32 rows of a warp with a shuffle butterfly, kept in registers across the CTA's tiles
+// (the grid is a multiple of n_tiles*groups, so a CTA always owns the same channels) and flushed with one fp64 atomic
+// per channel per warp at the end.
 // ---------------------------------------------------------------------------------------------------
+constexpr int kProducers = 4;                         // TMA producer warps (one issuing lane each)
+constexpr int kFwdThreads = (10 + kProducers - 1) * 32;  // warp 0 + warps 10.. producers, warp 1 MMA, warps 2..9 epilogue
+
 template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                          const __grid_constant__ CUtensorMap tmB,
-                                                          const ConvTcParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const ConvTcParams p) {
   constexpr int A_BYTES = 128 * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int SWZ = BK * 2;  // bytes per smem row = swizzle span
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  constexpr int COLS_W = BN >= 32 ? BN / 2 : BN;   // columns handled by one epilogue warp
+  constexpr int NCHUNK_W = COLS_W / 16;
+  constexpr int NSTAT = (COLS_W + 31) / 32;
+  constexpr int PITCH = COLS_W * 2 + 16;           // bytes per staged row (+16 spreads the banks)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-
-  // tile coordinates
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const int img = blockIdx.x / tiles_per_img;
-  const int trem = blockIdx.x - img * tiles_per_img;
-  const int th_i = trem / p.tiles_w;
-  const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
-  const int n0 = blockIdx.y * BN;
-  const int g = blockIdx.z;
+  uint8_t* const smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
       tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
     }
-    tc::mbar_init(tc::smem_u32(&acc_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&acc_full[b]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty[b]), 8);  // one arrival per epilogue warp
+    }
     tc::fence_barrier_init();
     tc::fence_proxy_async();
     tc::tma_prefetch_desc(&tmA);
@@ -105,109 +119,201 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
   const int total_k = p.taps * p.kchunks;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int ng = p.n_tiles * p.groups;
 
-  if (warp == 0) {
+  if (warp == 0 || warp >= 10) {
+    // kProducers TMA producer warps (one lane each): measured, one thread sustains only ~1 UTMALDG per ~350 cycles, so a
+    // single producer starves narrow layers (ncu: MMA thread spinning on the full barrier, profiles/).  Even roles load
+    // the A tile of their k-iterations and arm the barrier with the stage's byte count, odd roles load the B tile.
     if (lane == 0) {
+      const int role = warp == 0 ? 0 : warp - 9;       // 0 .. kProducers-1
+      const bool is_a = (role & 1) == 0;                // even roles load A (and arm the barrier), odd roles load B
+      const uint32_t it_sel = (uint32_t)(role >> 1);    // this producer serves k-iterations it % (kProducers/2) == it_sel
       const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * SWZ + B_BYTES);
-      for (int it = 0; it < total_k; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
-        const uint32_t fb = tc::smem_u32(&full_bar[s]);
-        tc::mbar_arrive_expect_tx(fb, tx_bytes);
-        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        tc::tma_load_4d(sa, &tmA, fb, g * p.cin_g + kc * BK, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
-        tc::tma_load_3d(sa + A_BYTES, &tmB, fb, kc * BK, g * p.cout_g + n0, tap);
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int n_tile = (int)(t % p.n_tiles);
+        const int g = (int)((t / p.n_tiles) % p.groups);
+        const int m_tile = (int)(t / ng);
+        const int img = m_tile / tiles_per_img;
+        const int trem = m_tile - img * tiles_per_img;
+        const int th_i = trem / p.tiles_w;
+        const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+        const int n0 = n_tile * BN;
+        for (int kk = 0; kk < total_k; ++kk, ++it) {
+          if ((it % (kProducers / 2)) != it_sel) continue;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = tc::smem_u32(&full_bar[s]);
+          const int tap = kk / p.kchunks, kc = kk - tap * p.kchunks;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          if (is_a) {
+            tc::mbar_arrive_expect_tx(fb, tx_bytes);
+            tc::tma_load_4d(sa, &tmA, fb, g * p.cin_g + kc * BK, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
+          } else {
+            tc::tma_load_3d(sa + A_BYTES, &tmB, fb, kc * BK, g * p.cout_g + n0, tap);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 0, 0);
-      for (int it = 0; it < total_k; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
+      uint32_t it = 0, li = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
+        const uint32_t buf = li & 1u;
+        tc::mbar_wait(tc::smem_u32(&acc_empty[buf]), ((li >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         tc::fence_after_sync();
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint64_t da = tc::umma_smem_desc(sa, SWZ, 16);
-        const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, SWZ, 16);
+        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+        for (int kk = 0; kk < total_k; ++kk, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
+          tc::fence_after_sync();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint64_t da = tc::umma_smem_desc(sa, SWZ, 16);
+          const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, SWZ, 16);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          tc::umma_bf16(tmem_base, tc::umma_desc_advance(da, k * 32), tc::umma_desc_advance(db, k * 32), idesc,
-                        (it | k) != 0);
-        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_bf16(d_tmem, tc::umma_desc_advance(da, k * 32), tc::umma_desc_advance(db, k * 32), idesc, (kk | k) != 0);
+          tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+        }
+        tc::umma_commit(tc::smem_u32(&acc_full[buf]));
       }
-      tc::umma_commit(tc::smem_u32(&acc_bar));
     }
   } else {
-    // ---- epilogue: TMEM lane quarter q <-> GEMM rows [32q, 32q+32)
+    // ---- 8 epilogue warps: TMEM lane quarter q <-> GEMM rows [32q, 32q+32); column half hsel
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const bool works = (hsel == 0) || (BN >= 32);
     const int r = q * 32 + lane;
     const int th = r / p.TW, tw = r - th * p.TW;
-    const int h = h0 + th, w = w0 + tw;
-    bool valid = (r < p.TW * p.TH) && (h < p.H) && (w < p.W);
-    int oh = h, ow = w, cbase = g * p.cout_g + n0, cshift = 0;
-    if (p.scatter == 1) {
-      const int tap = cbase / p.cout_total;
-      cbase -= tap * p.cout_total;
-      oh = 2 * h + (tap >> 1);
-      ow = 2 * w + (tap & 1);
-    } else if (p.scatter == 2) {
-      oh = h >> 1;
-      ow = w >> 1;
-      cshift = ((h & 1) * 2 + (w & 1)) * p.s2d_qs;
-    }
-    valid = valid && (oh < p.Hout) && (ow < p.Wout);
-    const long long pix = ((long long)img * p.Hout + oh) * p.Wout + ow;
-    tc::mbar_wait(tc::smem_u32(&acc_bar), 0);
-    tc::fence_after_sync();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int nvalid = min(BN, p.cout_g - n0);  // columns of this tile that exist
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tc::tmem_ld16(taddr + c0, v);
-      tc::tmem_ld_wait();
-      if (valid && c0 < nvalid) {
-        float f[16];
+    uint8_t* const stage = smem_gen + STAGES * STAGE_BYTES + (warp - 2) * (32 * PITCH);
+    float ssum[NSTAT], ssq[NSTAT];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          f[i] = __uint_as_float(v[i]);
-          if (p.bias) f[i] += __ldg(p.bias + cbase + c0 + i);
-        }
-        if (p.act) {
+    for (int c = 0; c < NSTAT; ++c) ssum[c] = ssq[c] = 0.f;
+    int stat_col0 = -1;  // global channel of this warp's column 0 (fixed across the CTA's tiles when stats are on)
+    uint32_t li = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
+      const uint32_t buf = li & 1u;
+      const int n_tile = (int)(t % p.n_tiles);
+      const int g = (int)((t / p.n_tiles) % p.groups);
+      const int m_tile = (int)(t / ng);
+      const int img = m_tile / tiles_per_img;
+      const int trem = m_tile - img * tiles_per_img;
+      const int th_i = trem / p.tiles_w;
+      const int h = th_i * p.TH + th, w = (trem - th_i * p.tiles_w) * p.TW + tw;
+      const int n0 = n_tile * BN + hsel * COLS_W;   // first column of this warp inside the group
+      bool valid = (r < p.TW * p.TH) && (h < p.H) && (w < p.W);
+      int oh = h, ow = w, cbase = g * p.cout_g + n0, cshift = 0;
+      if (p.scatter == 1) {
+        const int tap = cbase / p.cout_total;
+        cbase -= tap * p.cout_total;
+        oh = 2 * h + (tap >> 1);
+        ow = 2 * w + (tap & 1);
+      } else if (p.scatter == 2) {
+        oh = h >> 1;
+        ow = w >> 1;
+        cshift = ((h & 1) * 2 + (w & 1)) * p.s2d_qs;
+      }
+      valid = valid && (oh < p.Hout) && (ow < p.Wout);
+      // element offset of this row's first output channel; -1 marks rows that are not stored
+      const long long row_off = valid ? (((long long)img * p.Hout + oh) * p.Wout + ow) * p.ldc + p.c_off + cshift + cbase : -1;
+      stat_col0 = cbase;
+      const int nvalid = min(COLS_W, p.cout_g - n0);
+      tc::mbar_wait(tc::smem_u32(&acc_full[buf]), (li >> 1) & 1u);
+      tc::fence_after_sync();
+      if (works) {
+        const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
-        }
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + pix * p.ldc + p.c_off + cshift + cbase + c0;
-          if (p.accumulate) {
+        for (int c = 0; c < NCHUNK_W; ++c) {
+          uint32_t v[16];
+          tc::tmem_ld16(taddr + c * 16, v);
+          tc::tmem_ld_wait();
+          float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += o[i];
+          for (int i = 0; i < 16; ++i) {
+            f[i] = __uint_as_float(v[i]);
+            if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
           }
+          if (p.act) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-        } else {
-          bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldc + p.c_off + cshift + cbase + c0;
-          if (p.accumulate) {
-            float e[16];
-            VecIO<bf16, 8>::ld(o, e);
-            VecIO<bf16, 8>::ld(o + 8, e + 8);
+            for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
+          }
+          if (!valid) {   // rows outside the image stage zeros: they are not stored and must not enter the statistics
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += e[i];
+            for (int i = 0; i < 16; ++i) f[i] = 0.f;
           }
           uint4 u0, u1;
           u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
           u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
           u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
           u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
-          *reinterpret_cast<uint4*>(o) = u0;
-          *reinterpret_cast<uint4*>(o + 8) = u1;
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
+        }
+      }
+      // this accumulator may be overwritten by the MMA of the tile after next
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+      if (works) {
+        if (p.stats) {
+          // per-channel sum / sum of squares of the staged (bf16-rounded) values: lane <-> column(s)
+#pragma unroll
+          for (int k = 0; k < NSTAT; ++k) {
+            const int col = lane + 32 * k;
+            if (col < COLS_W) {
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                const float val = __bfloat162float(*reinterpret_cast<const bf16*>(stage + rr * PITCH + col * 2));
+                s1 += val;
+                s2 += val * val;
+              }
+              ssum[k] += s1;
+              ssq[k] += s2;
+            }
+          }
+        }
+        // coalesced write-out of the warp's 32 staged rows: LPR lanes cover one row (16 B each)
+        constexpr int LPR = (COLS_W * 2) / 16;   // lanes per row: 8 (64 cols), 4, 2
+        constexpr int RPI = 32 / LPR;            // rows per instruction
+        const int sub = lane % LPR, rsel = lane / LPR;
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+          const int row = r0 + rsel;
+          const long long off = __shfl_sync(0xffffffffu, row_off, row);
+          if (off >= 0 && sub * 8 < nvalid) {
+            uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
+            bf16* o = reinterpret_cast<bf16*>(p.out) + off + sub * 8;
+            if (p.accumulate) {
+              const uint4 e = *reinterpret_cast<const uint4*>(o);
+              float x0, x1, y0, y1;
+              bf16x2_unpack(val.x, x0, x1); bf16x2_unpack(e.x, y0, y1); val.x = bf16x2_pack(x0 + y0, x1 + y1);
+              bf16x2_unpack(val.y, x0, x1); bf16x2_unpack(e.y, y0, y1); val.y = bf16x2_pack(x0 + y0, x1 + y1);
+              bf16x2_unpack(val.z, x0, x1); bf16x2_unpack(e.z, y0, y1); val.z = bf16x2_pack(x0 + y0, x1 + y1);
+              bf16x2_unpack(val.w, x0, x1); bf16x2_unpack(e.w, y0, y1); val.w = bf16x2_pack(x0 + y0, x1 + y1);
+            }
+            *reinterpret_cast<uint4*>(o) = val;
+          }
+        }
+        __syncwarp();  // staging rows are rewritten by the next tile
+      }
+    }
+    if (p.stats && works && stat_col0 >= 0) {
+      const int nvalid_cols = p.cout_g - (stat_col0 % p.cout_g);
+#pragma unroll
+      for (int k = 0; k < NSTAT; ++k) {
+        const int col = lane + 32 * k;
+        if (col < COLS_W && col < nvalid_cols) {
+          atomicAdd(p.stats + stat_col0 + col, (double)ssum[k]);
+          atomicAdd(p.stats + p.stats_stride + stat_col0 + col, (double)ssq[k]);
         }
       }
     }
-    tc::fence_before_sync();
   }
   __syncthreads();
   if (warp == 1) {
@@ -235,13 +341,18 @@ struct WgradParams {
   int convt_cout;
 };
 
-template <int BN, int CWA, int CWB, int STAGES>
-__global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
+constexpr int kWgProducers = 4;
+constexpr int kWgThreads = (6 + kWgProducers - 1) * 32;  // warp 0 + warps 6.. producers, warp 1 MMA, warps 2..5 epilogue
+
+template <int BN, int CWA, int CWB, int NA, int STAGES>
+__global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
                                                                 const __grid_constant__ CUtensorMap tmX,
                                                                 const WgradParams p) {
   constexpr int PITCH_A = CWA * 2, PITCH_B = CWB * 2;   // bytes per pixel row of one box
   constexpr int CHUNK_A = 128 * PITCH_A, CHUNK_B = 128 * PITCH_B;
-  constexpr int NCH_A = 128 / CWA, NCH_B = (BN + CWB - 1) / CWB;
+  // NA = A chunks that really exist (cout_g <= NA*CWA): only they get shared memory; the 128-row UMMA still strides
+  // over 128/CWA chunks, the missing ones alias whatever follows (their accumulator rows are never stored)
+  constexpr int NCH_A = NA, NCH_B = (BN + CWB - 1) / CWB;
   constexpr int A_BYTES = NCH_A * CHUNK_A;
   constexpr int B_BYTES = NCH_B * CHUNK_B;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -256,10 +367,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const int co_tile = blockIdx.y / p.n_ci_tiles, ci_tile = blockIdx.y - co_tile * p.n_ci_tiles;
+  // blockIdx.x = tap + taps * (output tile): the CTAs that read the same pixel slice (all taps, all channel tiles)
+  // are adjacent in launch order, so x / dy are fetched from HBM once and then served by L2.
+  const int tap = blockIdx.x % p.taps;
+  const int otile = blockIdx.x / p.taps;
+  const int co_tile = otile / p.n_ci_tiles, ci_tile = otile - co_tile * p.n_ci_tiles;
   const int co0 = co_tile * 128, ci0 = ci_tile * BN;
-  const int tap = blockIdx.z % p.taps, g = blockIdx.z / p.taps;
-  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int g = blockIdx.y;
+  const int t_begin = blockIdx.z * p.tiles_per_cta;
   const int t_end = min(t_begin + p.tiles_per_cta, p.total_tiles);
   const int n_iter = t_end - t_begin;
   const int rows = p.TW * p.TH;            // pixel rows written by one box
@@ -272,11 +387,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
     for (int st = 0; st < STAGES; ++st) {
       for (int rgn = 0; rgn < NCH_A; ++rgn) {
         uint8_t* q = base + st * STAGE_BYTES + rgn * CHUNK_A + rows * PITCH_A;
-        for (int i = threadIdx.x * 16; i < tail_rows * PITCH_A; i += kThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x * 16; i < tail_rows * PITCH_A; i += kWgThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
       }
       for (int rgn = 0; rgn < NCH_B; ++rgn) {
         uint8_t* q = base + st * STAGE_BYTES + A_BYTES + rgn * CHUNK_B + rows * PITCH_B;
-        for (int i = threadIdx.x * 16; i < tail_rows * PITCH_B; i += kThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x * 16; i < tail_rows * PITCH_B; i += kWgThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
       }
     }
   }
@@ -306,26 +421,35 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const __grid_co
   const int a_boxes = min(NCH_A, (p.cout_g - co0 + CWA - 1) / CWA);
   const int b_boxes = min(NCH_B, (p.cin_g - ci0 + CWB - 1) / CWB);
 
-  if (warp == 0) {
+  if (warp == 0 || warp >= 6) {
+    // kWgProducers TMA producer warps (one lane each); the boxes of a pixel tile are dealt round-robin, producer 0 also
+    // arms the barrier with the byte count (a single issuing thread sustains only ~1 UTMALDG per ~350 cycles)
     if (lane == 0) {
+      const int role = warp == 0 ? 0 : warp - 5;
       const uint32_t tx_bytes = (uint32_t)(rows * (PITCH_A * a_boxes + PITCH_B * b_boxes));
       const int dh = p.tap_dhs[tap], dw = p.tap_dws[tap];
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
-        const uint32_t fb = tc::smem_u32(&full_bar[s]);
-        tc::mbar_arrive_expect_tx(fb, tx_bytes);
-        const int t = t_begin + it;
-        const int img = t / tiles_per_img;
-        const int trem = t - img * tiles_per_img;
-        const int th_i = trem / p.tiles_w;
-        const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        for (int j = 0; j < a_boxes; ++j)
-          tc::tma_load_4d(sa + j * CHUNK_A, &tmDY, fb, g * p.cout_g + co0 + CWA * j, w0, h0, img);
-        for (int j = 0; j < b_boxes; ++j)
-          tc::tma_load_4d(sa + A_BYTES + j * CHUNK_B, &tmX, fb, g * p.cin_g + ci0 + CWB * j, w0 + dw, h0 + dh, img);
+      const int nbox = a_boxes + b_boxes;
+      if (role < nbox || role == 0) {
+        for (int it = 0; it < n_iter; ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = tc::smem_u32(&full_bar[s]);
+          if (role == 0) tc::mbar_arrive_expect_tx(fb, tx_bytes);
+          const int t = t_begin + it;
+          const int img = t / tiles_per_img;
+          const int trem = t - img * tiles_per_img;
+          const int th_i = trem / p.tiles_w;
+          const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          for (int j = role; j < nbox; j += kWgProducers) {
+            if (j < a_boxes)
+              tc::tma_load_4d(sa + j * CHUNK_A, &tmDY, fb, g * p.cout_g + co0 + CWA * j, w0, h0, img);
+            else
+              tc::tma_load_4d(sa + A_BYTES + (j - a_boxes) * CHUNK_B, &tmX, fb, g * p.cin_g + ci0 + CWB * (j - a_boxes), w0 + dw,
+                              h0 + dh, img);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -451,29 +575,35 @@ void pick_patch(int H, int W, int* TW, int* TH) {
 }
 
 template <int BN, int BK, int STAGES>
-int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, dim3 grid, cudaStream_t s) {
-  constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + 1024;
+int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int grid, cudaStream_t s) {
+  constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + 8 * 32 * ((BN >= 32 ? BN / 2 : BN) * 2 + 16) + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return OCT_ERR_LAUNCH;
     attr_done = true;
   }
-  conv_tc_kernel<BN, BK, STAGES><<<grid, kThreads, smem, s>>>(tmA, tmB, p);
+  conv_tc_kernel<BN, BK, STAGES><<<grid, kFwdThreads, smem, s>>>(tmA, tmB, p);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
 
-template <int BN, int CWA, int CWB, int STAGES>
+template <int BN, int CWA, int CWB, int NA>
+constexpr int wgrad_stage_bytes() { return NA * 128 * CWA * 2 + ((BN + CWB - 1) / CWB) * 128 * CWB * 2; }
+
+template <int BN, int CWA, int CWB, int NA, int STAGES>
 int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& p, dim3 grid, cudaStream_t s) {
-  constexpr int smem = STAGES * (128 * 128 * 2 + ((BN + CWB - 1) / CWB) * 128 * CWB * 2) + 1024;
+  // +32 KB slack: the chunks a 128-row UMMA strides over beyond NA must stay inside the allocation
+  constexpr int smem = STAGES * wgrad_stage_bytes<BN, CWA, CWB, NA>() + (128 / CWA - NA) * 128 * CWA * 2 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, CWA, CWB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return OCT_ERR_LAUNCH;
     attr_done = true;
   }
-  conv_tc_wgrad_kernel<BN, CWA, CWB, STAGES><<<grid, kThreads, smem, s>>>(tmDY, tmX, p);
+  conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES><<<grid, kWgThreads, smem, s>>>(tmDY, tmX, p);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -500,7 +630,7 @@ extern "C" int octave_conv_tc_supported(const OctaveConvDesc* d) {
 }
 
 extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
-                                  void* stream) {
+                                  double* stats, void* stream) {
   int rc = validate_conv(d);
   if (rc != OCT_OK) return rc;
   if (!octave_conv_tc_supported(d)) return OCT_ERR_UNSUPPORTED;
@@ -544,20 +674,39 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
   const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
   if (!make_act_map(&tmA, xb, d->cin, Wa, Ha, B, d->x_ld, BK, p.TW, p.TH, BK * 2)) return OCT_ERR_LAUNCH;
   if (!make_w_map(&tmB, wpack, cin_g, d->groups * n_cols_g, p.taps, BK, BN, BK * 2)) return OCT_ERR_LAUNCH;
-  dim3 grid(p.tiles_w * p.tiles_h * B, (n_cols_g + BN - 1) / BN, d->groups);
+  p.n_tiles = (n_cols_g + BN - 1) / BN;
+  p.groups = d->groups;
+  p.total_tiles = (long long)p.tiles_w * p.tiles_h * B * p.n_tiles * d->groups;
+  p.stats = stats; p.stats_stride = d->cout;
+  if (p.out_f32) return OCT_ERR_UNSUPPORTED;
+  if (stats && (convt || s2d)) return OCT_ERR_UNSUPPORTED;
+  int sms = octave_sm_count();
+  if (sms <= 0) sms = 148;
+  long long grid = sms;
+  const int ng = p.n_tiles * d->groups;
+  if (stats) {
+    // a CTA must always own the same output channels: grid is a multiple of n_tiles * groups
+    if (ng > sms) return OCT_ERR_UNSUPPORTED;
+    grid = (sms / ng) * ng;
+    if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  }
+  if (grid > p.total_tiles) grid = stats ? ((p.total_tiles + ng - 1) / ng) * ng : p.total_tiles;
+  if (stats && grid > p.total_tiles) grid = p.total_tiles;  // total_tiles is itself a multiple of ng
   if (BK == 64) {
     switch (BN) {
-      case 128: return launch_fwd<128, 64, 4>(tmA, tmB, p, grid, s);
-      case 64: return launch_fwd<64, 64, 4>(tmA, tmB, p, grid, s);
-      case 32: return launch_fwd<32, 64, 4>(tmA, tmB, p, grid, s);
-      default: return launch_fwd<16, 64, 4>(tmA, tmB, p, grid, s);
+      // pipeline depth sized to ~160-190 KB in flight per SM: the persistent CTA is alone on its SM, so the ring must
+      // cover the HBM bandwidth-delay product by itself, also for the small stages of narrow layers
+      case 128: return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
+      case 64: return launch_fwd<64, 64, 7>(tmA, tmB, p, (int)grid, s);
+      case 32: return launch_fwd<32, 64, 9>(tmA, tmB, p, (int)grid, s);
+      default: return launch_fwd<16, 64, 10>(tmA, tmB, p, (int)grid, s);
     }
   } else {
     switch (BN) {
-      case 128: return launch_fwd<128, 32, 4>(tmA, tmB, p, grid, s);
-      case 64: return launch_fwd<64, 32, 4>(tmA, tmB, p, grid, s);
-      case 32: return launch_fwd<32, 32, 4>(tmA, tmB, p, grid, s);
-      default: return launch_fwd<16, 32, 4>(tmA, tmB, p, grid, s);
+      case 128: return launch_fwd<128, 32, 10>(tmA, tmB, p, (int)grid, s);
+      case 64: return launch_fwd<64, 32, 14>(tmA, tmB, p, (int)grid, s);
+      case 32: return launch_fwd<32, 32, 16>(tmA, tmB, p, (int)grid, s);
+      default: return launch_fwd<16, 32, 18>(tmA, tmB, p, (int)grid, s);
     }
   }
 }
@@ -609,7 +758,8 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   const int out_tiles = n_co_tiles * p.n_ci_tiles * p.taps * d->groups;
   int sms = octave_sm_count();
   if (sms <= 0) sms = 148;
-  int split = (2 * sms + out_tiles - 1) / out_tiles;
+  // one wave of CTAs (1 CTA per SM: the TMA ring takes most of the shared memory): no tail wave
+  int split = sms / out_tiles;
   if (split < 1) split = 1;
   if (split > p.total_tiles) split = p.total_tiles;
   p.tiles_per_cta = (p.total_tiles + split - 1) / split;
@@ -622,15 +772,19 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   if (!make_act_map(&tmDY, dyb, cout_all, d->ksize == 1 ? W : d->Wout, d->ksize == 1 ? H : d->Hout, B, d->y_ld, CWA, p.TW, p.TH, CWA * 2)) return OCT_ERR_LAUNCH;
   const size_t wbytes = (size_t)cout_all * p.real_cin_g * p.taps * sizeof(float);
   if (!d->accumulate && cudaMemsetAsync(dw, 0, wbytes, s) != cudaSuccess) return OCT_ERR_LAUNCH;
-  dim3 grid(split, n_co_tiles * p.n_ci_tiles, p.taps * d->groups);
+  if (split > 65535) return OCT_ERR_UNSUPPORTED;
+  dim3 grid(p.taps * n_co_tiles * p.n_ci_tiles, d->groups, split);
+  const bool one_a = cout_g <= CWA;   // a single A box per pixel tile
   if (CWA == 64 && CWB == 64) {
     switch (BN) {
-      case 256: return launch_wgrad<256, 64, 64, 2>(tmDY, tmX, p, grid, s);
-      case 128: return launch_wgrad<128, 64, 64, 3>(tmDY, tmX, p, grid, s);
-      default: return launch_wgrad<64, 64, 64, 4>(tmDY, tmX, p, grid, s);
+      case 256: return one_a ? launch_wgrad<256, 64, 64, 1, 2>(tmDY, tmX, p, grid, s) : launch_wgrad<256, 64, 64, 2, 2>(tmDY, tmX, p, grid, s);
+      case 128: return one_a ? launch_wgrad<128, 64, 64, 1, 4>(tmDY, tmX, p, grid, s) : launch_wgrad<128, 64, 64, 2, 3>(tmDY, tmX, p, grid, s);
+      default: return one_a ? launch_wgrad<64, 64, 64, 1, 6>(tmDY, tmX, p, grid, s) : launch_wgrad<64, 64, 64, 2, 4>(tmDY, tmX, p, grid, s);
     }
   }
-  if (CWA == 32 && CWB == 64) return launch_wgrad<64, 32, 64, 4>(tmDY, tmX, p, grid, s);
-  if (CWA == 64 && CWB == 32) return launch_wgrad<32, 64, 32, 4>(tmDY, tmX, p, grid, s);
-  return launch_wgrad<32, 32, 32, 4>(tmDY, tmX, p, grid, s);
+  if (CWA == 32 && CWB == 64)
+    return one_a ? launch_wgrad<64, 32, 64, 1, 8>(tmDY, tmX, p, grid, s) : launch_wgrad<64, 32, 64, 4, 4>(tmDY, tmX, p, grid, s);
+  if (CWA == 64 && CWB == 32)
+    return one_a ? launch_wgrad<32, 64, 32, 1, 8>(tmDY, tmX, p, grid, s) : launch_wgrad<32, 64, 32, 2, 5>(tmDY, tmX, p, grid, s);
+  return one_a ? launch_wgrad<32, 32, 32, 1, 12>(tmDY, tmX, p, grid, s) : launch_wgrad<32, 32, 32, 4, 5>(tmDY, tmX, p, grid, s);
 }

