@@ -168,14 +168,15 @@ int octave_bn_prepare(int32_t C, double count, const double* sums, const float* 
  * gap[b][c % (C/2)] += sum_pixels y  — the radix-sum + global-average-pool of resnest.py:106-116. */
 int octave_affine_act(const OctaveAct* x, const float* ab, const OctaveAct* res, int32_t relu, const OctaveAct* y,
                       float* gap, void* stream);
-/* dz = dy * (mask > 0) (mask nullable).  sums2[c] = sum dz, sums2[C+c] = sum dz * xhat. */
-int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* x, const float* mean_invstd,
-                         double* sums2, void* stream);
+/* dz = dy * (mask > 0) (mask nullable); or, with mask NULL and relu_ab != NULL (the [2C] scale/shift of this very BN),
+ * the ReLU mask is recomputed from x as (x*a+b > 0) instead of being read.  sums2[c] = sum dz, sums2[C+c] = sum dz * xhat. */
+int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
+                         const float* mean_invstd, double* sums2, void* stream);
 /* dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or gamma*invstd*dz (eval, mean_invstd then
  * holds the running statistics).  dgamma = sum dz*xhat, dbeta = sum dz (nullable) are overwritten. */
-int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* x, const float* mean_invstd,
-                        const float* gamma, const double* sums2, int32_t training, const OctaveAct* dx, float* dgamma,
-                        float* dbeta, void* stream);
+int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
+                        const float* mean_invstd, const float* gamma, const double* sums2, int32_t training,
+                        const OctaveAct* dx, float* dgamma, float* dbeta, void* stream);
 /* dst += src (same shape); used where gradients of two branches merge. */
 int octave_add_inplace(const OctaveAct* dst, const OctaveAct* src, void* stream);
 /* dst = src * (mask > 0) */

@@ -8,6 +8,8 @@
 //
 // Reference arithmetic: nn.BatchNorm2d / ReLU / SplAtConv2d.forward (/root/reference/architectures/extra/resnest.py:97-138),
 // residual adds at resnest.py:42,264-265.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/octave_b200.h"
 
@@ -18,7 +20,16 @@ struct Geo {
   dim3 grid;
 };
 
-constexpr int kReduceBlocks = 148 * 4;   // total blocks of a reduction kernel: bounds the atomics per channel
+static int reduce_blocks() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("OCTAVE_REDUCE_BLOCKS");
+    v = e ? atoi(e) : 148 * 4;
+    if (v < 1) v = 148 * 4;
+  }
+  return v;
+}
+#define kReduceBlocks reduce_blocks()   // total blocks of a reduction kernel: bounds the atomics per channel
 constexpr int kStreamBlocks = 148 * 16;
 
 bool make_geo(const OctaveAct* a, Geo* g, int total_blocks = kStreamBlocks) {
@@ -180,17 +191,20 @@ __global__ void affine_act_kernel(const OctaveAct x, const float* ab, const Octa
   }
 }
 
+// has_mask: 0 none, 1 mask tensor (dz = dy * (mask > 0)), 2 recompute the ReLU mask of this very BN from x: (x*a+b > 0)
 template <typename T>
-__global__ void bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, int has_mask, const OctaveAct x,
+__global__ void bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, int has_mask, const float* ab, const OctaveAct x,
                                      const float* mi, double* sums2) {
   extern __shared__ float sm[];
   const int G = x.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
   const long long hw = (long long)x.H * x.W, base = (long long)blockIdx.y * hw;
-  float mean[8], inv[8], v[16];
+  float mean[8], inv[8], v[16], aa[8], bb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     mean[i] = mi[cg * 8 + i];
     inv[i] = mi[x.C + cg * 8 + i];
+    aa[i] = has_mask == 2 ? ab[cg * 8 + i] : 0.f;
+    bb[i] = has_mask == 2 ? ab[x.C + cg * 8 + i] : 0.f;
     v[i] = v[8 + i] = 0.f;
   }
   const long long step = (long long)gridDim.x * ppb;
@@ -202,7 +216,11 @@ __global__ void bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, i
       const long long q = ok ? p + u * step : p;
       VecIO<T, 8>::ld(at<T>(dy, base + q, cg * 8), d[u]);
       VecIO<T, 8>::ld(at<T>(x, base + q, cg * 8), f[u]);
-      if (has_mask) VecIO<T, 8>::ld(at<T>(mask, base + q, cg * 8), m[u]);
+      if (has_mask == 1) VecIO<T, 8>::ld(at<T>(mask, base + q, cg * 8), m[u]);
+      if (has_mask == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[u][i] = to_f(from_f<T>(f[u][i] * aa[i] + bb[i]));
+      }
       if (!ok) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[u][i] = 0.f;
@@ -229,18 +247,20 @@ __global__ void bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, i
 }
 
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const OctaveAct dy, const OctaveAct mask, int has_mask, const OctaveAct x,
+__global__ void bn_bwd_apply_kernel(const OctaveAct dy, const OctaveAct mask, int has_mask, const float* ab, const OctaveAct x,
                                     const float* mi, const float* gamma, const double* sums2, int training,
                                     const OctaveAct dx, float* dgamma, float* dbeta) {
   const int G = x.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
   const long long hw = (long long)x.H * x.W, base = (long long)blockIdx.y * hw;
   const float inv_n = 1.f / ((float)x.B * (float)hw);
-  float mean[8], inv[8], k1[8], k2[8], ag[8];
+  float mean[8], inv[8], k1[8], k2[8], ag[8], aa[8], bb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = cg * 8 + i;
     mean[i] = mi[c];
     inv[i] = mi[x.C + c];
+    aa[i] = has_mask == 2 ? ab[c] : 0.f;
+    bb[i] = has_mask == 2 ? ab[x.C + c] : 0.f;
     const float sd = (float)sums2[c], sdx = (float)sums2[x.C + c];
     k1[i] = training ? sd * inv_n : 0.f;
     k2[i] = training ? sdx * inv_n : 0.f;
@@ -254,11 +274,14 @@ __global__ void bn_bwd_apply_kernel(const OctaveAct dy, const OctaveAct mask, in
     float d[8], f[8];
     VecIO<T, 8>::ld(at<T>(dy, base + p, cg * 8), d);
     VecIO<T, 8>::ld(at<T>(x, base + p, cg * 8), f);
-    if (has_mask) {
+    if (has_mask == 1) {
       float m[8];
       VecIO<T, 8>::ld(at<T>(mask, base + p, cg * 8), m);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+    } else if (has_mask == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? d[i] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = ag[i] * (d[i] - k1[i] - (f[i] - mean[i]) * inv[i] * k2[i]);
@@ -427,7 +450,7 @@ extern "C" int octave_affine_act(const OctaveAct* x, const float* ab, const Octa
   return OCT_OK;
 }
 
-extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* x,
+extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
                                     const float* mean_invstd, double* sums2, void* stream) {
   if (!view_ok(dy) || !view_ok(x) || !same_shape(dy, x) || !mean_invstd || !sums2) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, x))) return OCT_ERR_INVALID;
@@ -436,13 +459,14 @@ extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, 
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   OctaveAct m = mask ? *mask : *x;
+  const int mmode = mask ? 1 : (relu_ab ? 2 : 0);
   DISPATCH_T(x->dtype, (bn_bwd_reduce_kernel<T><<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(
-                           *dy, m, mask != nullptr, *x, mean_invstd, sums2)));
+                           *dy, m, mmode, relu_ab, *x, mean_invstd, sums2)));
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
 
-extern "C" int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* x,
+extern "C" int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
                                    const float* mean_invstd, const float* gamma, const double* sums2, int32_t training,
                                    const OctaveAct* dx, float* dgamma, float* dbeta, void* stream) {
   if (!view_ok(dy) || !view_ok(x) || !view_ok(dx) || !same_shape(dy, x) || !same_shape(dx, x)) return OCT_ERR_INVALID;
@@ -451,8 +475,9 @@ extern "C" int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, c
   Geo g;
   if (!make_geo(x, &g)) return OCT_ERR_UNSUPPORTED;
   OctaveAct m = mask ? *mask : *x;
+  const int mmode = mask ? 1 : (relu_ab ? 2 : 0);
   DISPATCH_T(x->dtype, (bn_bwd_apply_kernel<T><<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(
-                           *dy, m, mask != nullptr, *x, mean_invstd, gamma, sums2, training, *dx, dgamma, dbeta)));
+                           *dy, m, mmode, relu_ab, *x, mean_invstd, gamma, sums2, training, *dx, dgamma, dbeta)));
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

@@ -65,12 +65,17 @@ def bn_fwd(bn: BatchNorm2d, z: Act, training: bool, relu: bool, res: Optional[Ac
         ab, mi = ops.bn_prepare(z.C, z.npix, None, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                 None, bn.eps, bn.momentum, False, z.device)
     y, gap = ops.affine_act(z, ab, res, relu, out, want_gap)
-    return y, (bn, z, mi, ab, training), gap
+    return y, (bn, z, mi, ab, training, relu and res is None, y), gap
 
 
 def bn_bwd(ctx, dy: Act, mask: Optional[Act], grads: Grads, out: Optional[Act] = None) -> Act:
-    bn, z, mi, _ab, training = ctx
-    dz, dg, db = ops.bn_bwd(dy, mask, z, mi, bn.weight.detach(), training, out)
+    """mask: the activation whose ReLU gates dy.  When it is this BN's own output (y = relu(BN(z)), no residual) the
+    mask is recomputed from z inside the kernels instead of being read (one tensor pass less in each kernel)."""
+    bn, z, mi, ab, training, relu_self, y = ctx
+    relu_ab = None
+    if mask is not None and relu_self and mask is y:
+        mask, relu_ab = None, ab
+    dz, dg, db = ops.bn_bwd(dy, mask, z, mi, bn.weight.detach(), training, out, relu_ab)
     _acc(grads, bn.weight, dg)
     _acc(grads, bn.bias, db)
     return dz

@@ -104,8 +104,8 @@ _sigs = {
     "octave_chan_stats": [_A, _vp, _vp],
     "octave_bn_prepare": [C.c_int32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_int32, _vp, _vp, _vp],
     "octave_affine_act": [_A, _vp, _A, C.c_int32, _A, _vp, _vp],
-    "octave_bn_bwd_reduce": [_A, _A, _A, _vp, _vp, _vp],
-    "octave_bn_bwd_apply": [_A, _A, _A, _vp, _vp, _vp, C.c_int32, _A, _vp, _vp, _vp],
+    "octave_bn_bwd_reduce": [_A, _A, _vp, _A, _vp, _vp, _vp],
+    "octave_bn_bwd_apply": [_A, _A, _vp, _A, _vp, _vp, _vp, C.c_int32, _A, _vp, _vp, _vp],
     "octave_add_inplace": [_A, _A, _vp],
     "octave_relu_bwd": [_A, _A, _A, _vp],
     "octave_splat_combine": [_A, _vp, C.c_int32, _A, _vp],
@@ -170,14 +170,14 @@ def affine_act(x: Act, ab: Optional[torch.Tensor], res: Optional[Act], relu: boo
 
 
 def bn_bwd(dy: Act, mask: Optional[Act], x: Act, mi: torch.Tensor, gamma: Optional[torch.Tensor], training: bool,
-           out: Optional[Act] = None):
-    """-> dx, dgamma, dbeta"""
+           out: Optional[Act] = None, relu_ab: Optional[torch.Tensor] = None):
+    """-> dx, dgamma, dbeta.  relu_ab (with mask None): recompute this BN's own ReLU mask from x instead of reading it."""
     sums2 = torch.empty(2 * x.C, dtype=torch.float64, device=x.device)
-    _chk("octave_bn_bwd_reduce", lib.octave_bn_bwd_reduce(_ref(dy), _ref(mask), _ref(x), mi.data_ptr(), sums2.data_ptr(), stream_ptr()))
+    _chk("octave_bn_bwd_reduce", lib.octave_bn_bwd_reduce(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), sums2.data_ptr(), stream_ptr()))
     dx = out if out is not None else x.like()
     dgamma = torch.empty(x.C, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(x.C, dtype=torch.float32, device=x.device)
-    _chk("octave_bn_bwd_apply", lib.octave_bn_bwd_apply(_ref(dy), _ref(mask), _ref(x), mi.data_ptr(), _p(gamma), sums2.data_ptr(),
+    _chk("octave_bn_bwd_apply", lib.octave_bn_bwd_apply(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), _p(gamma), sums2.data_ptr(),
                                                         int(training), _ref(dx), dgamma.data_ptr(), dbeta.data_ptr(), stream_ptr()))
     return dx, dgamma, dbeta
 

@@ -29,6 +29,7 @@ for (H, C) in [(400, 32), (400, 64), (200, 64), (200, 128), (100, 256), (100, 64
     t_aff = timeit(lambda: ops.affine_act(x, ab, None, True, y))
     t_gap = timeit(lambda: ops.affine_act(x, ab, None, True, y, True))
     t_bwd = timeit(lambda: ops.bn_bwd(dy, y, x, mi, gamma, True, out=dy))
+    t_bwd2 = timeit(lambda: ops.bn_bwd(dy, None, x, mi, gamma, True, out=dy, relu_ab=ab))
     t_relu = timeit(lambda: ops.relu_bwd(dy, y, y))
     print(f"{H:4d}x{H:<4d} C={C:5d} {nbytes/2**20:7.1f} MiB | stats {t_stats*1e3:7.1f} us {nbytes/t_stats/1e6:6.0f} GB/s | affine {t_aff*1e3:7.1f} us {2*nbytes/t_aff/1e6:6.0f} GB/s | "
-          f"affine+gap {t_gap*1e3:7.1f} us {2*nbytes/t_gap/1e6:6.0f} | bn_bwd(reduce+apply) {t_bwd*1e3:7.1f} us {7*nbytes/t_bwd/1e6:6.0f} GB/s | relu_bwd {t_relu*1e3:6.1f} us {3*nbytes/t_relu/1e6:6.0f}")
+          f"affine+gap {t_gap*1e3:7.1f} us {2*nbytes/t_gap/1e6:6.0f} | bn_bwd(reduce+apply) {t_bwd*1e3:7.1f} us {7*nbytes/t_bwd/1e6:6.0f} GB/s | selfmask {t_bwd2*1e3:7.1f} us {5*nbytes/t_bwd2/1e6:6.0f} | relu_bwd {t_relu*1e3:6.1f} us {3*nbytes/t_relu/1e6:6.0f}")
