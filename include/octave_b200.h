@@ -209,9 +209,11 @@ int octave_pool_bwd(const OctavePoolDesc* p, const OctaveAct* dy, const uint8_t*
  *                                                       — AdversarialAttentionGate.forward, segmentor/blocks.py:38-46 */
 int octave_head_fwd(const OctaveAct* x, const float* w /* [K][C] */, const float* b /* [K] */, int32_t K, int32_t mode,
                     float* out /* [B][K][H][W] */, const OctaveAct* gated /* mode 1 */, void* stream);
-/* dout nullable (no gradient reached the map).  dlogits: fp32 [B][K][H][W] scratch, overwritten (input of head_wgrad). */
+/* dout nullable (no gradient reached the map).  dw [K][C] / db [K] (both or neither, nullable): parameter gradients,
+ * overwritten.  K == 2 with dlogits == NULL takes the fused kernel (dx, dw, db in one pass over x).  Otherwise dlogits
+ * (fp32 [B][K][H][W] scratch, overwritten) is required and dw/db are produced through octave_head_wgrad. */
 int octave_head_bwd(const OctaveAct* x, const float* w, const float* b, int32_t K, int32_t mode, const float* dout,
-                    const OctaveAct* dgated, const OctaveAct* dx, float* dlogits, void* stream);
+                    const OctaveAct* dgated, const OctaveAct* dx, float* dlogits, float* dw, float* db, void* stream);
 int octave_head_wgrad(const OctaveAct* x, const float* dlogits, int32_t K, float* dw /* [K][C] */, float* db /* [K] */,
                       void* stream);
 

@@ -145,3 +145,68 @@ template <> struct VecIO<bf16, 1> {
   static __device__ __forceinline__ void ld(const bf16* p, float* v) { v[0] = __bfloat162float(*p); }
   static __device__ __forceinline__ void st(bf16* p, const float* v) { p[0] = __float2bfloat16_rn(v[0]); }
 };
+
+// 8 consecutive elements held in their storage form (4 registers for bf16) until they are consumed.
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void ld(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void zero() { r = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void get(float* v) const {
+    bf16x2_unpack(r.x, v[0], v[1]); bf16x2_unpack(r.y, v[2], v[3]);
+    bf16x2_unpack(r.z, v[4], v[5]); bf16x2_unpack(r.w, v[6], v[7]);
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void get(float* v) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+
+// Fold NV per-thread values over the pixel lanes of a block (threads with equal tid % Gb).
+// Result valid for threads tid < Gb.  sm must hold NV * blockDim.x floats.
+template <int NV>
+__device__ __forceinline__ void fold_lanes(float (&v)[NV], float* sm, int Gb) {
+  const int tid = threadIdx.x, bs = blockDim.x;
+  if (Gb < 32 && (32 % Gb) == 0 && (bs & 31) == 0) {
+    // lanes of a warp that share a channel group are Gb apart: butterfly over them, then one row per warp
+    for (int off = 16; off >= Gb; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    }
+    const int lane = tid & 31, warp = tid >> 5, nw = bs >> 5;
+    if (lane < Gb) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) sm[(i * nw + warp) * Gb + lane] = v[i];
+    }
+    __syncthreads();
+    if (tid < Gb) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += sm[(i * nw + w) * Gb + tid];
+        v[i] = s;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sm[i * bs + tid] = v[i];
+    __syncthreads();
+    if (tid < Gb) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float s = 0.f;
+        for (int l = tid; l < bs; l += Gb) s += sm[i * bs + l];
+        v[i] = s;
+      }
+    }
+  }
+}
+

@@ -15,35 +15,64 @@
 
 namespace {
 
+// Geometry shared by every kernel here.  G = C/8 channel groups; a block covers Gb = min(G, 256) of them (blockIdx.z
+// selects the 256-group slab when G > 256) with ppb = bs/Gb pixel lanes.  Every loop iteration of a block handles U*ppb
+// consecutive pixels: all U 16-byte loads of a thread are issued before the first use (memory-level parallelism), and a
+// block reads U*ppb*C*2 contiguous bytes per tensor.
 struct Geo {
-  int G, bs, ppb;  // channel groups, block size, pixels per block pass
+  int G, Gb, bs, ppb;
   dim3 grid;
 };
 
-static int reduce_blocks() {
-  static int v = 0;
-  if (!v) {
-    const char* e = getenv("OCTAVE_REDUCE_BLOCKS");
-    v = e ? atoi(e) : 148 * 4;
-    if (v < 1) v = 148 * 4;
-  }
-  return v;
+// Resident blocks per SM of a kernel (cached): grids are sized to ONE wave so that reductions flush their atomics once
+// per resident block and no tail wave runs at partial occupancy.
+int resident_blocks(const void* fn, int bs, size_t smem) {
+  struct Entry { const void* fn; int bs; size_t smem; int n; };
+  static Entry cache[64];
+  static int used = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].fn == fn && cache[i].bs == bs && cache[i].smem == smem) return cache[i].n;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, bs, smem) != cudaSuccess || n < 1) n = 1;
+  if (used < 64) cache[used++] = Entry{fn, bs, smem, n};
+  return n;
 }
-#define kReduceBlocks reduce_blocks()   // total blocks of a reduction kernel: bounds the atomics per channel
-constexpr int kStreamBlocks = 148 * 16;
 
-bool make_geo(const OctaveAct* a, Geo* g, int total_blocks = kStreamBlocks) {
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    sms = octave_sm_count();
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// per_image: blockIdx.y = image and the pixel domain of a block is one image; otherwise the whole batch is one domain.
+// total_blocks: upper bound of the grid (all of x, y, z together).
+bool make_geo(const OctaveAct* a, Geo* g, int U, bool per_image, int total_blocks, int min_iters = 1) {
   if (a->C % 8) return false;
   g->G = a->C / 8;
-  if (g->G > 1024) return false;
-  if (g->G <= 256) g->bs = (256 / g->G) * g->G; else g->bs = g->G;
-  g->ppb = g->bs / g->G;
+  int gz = 1;
+  if (g->G <= 256) {
+    g->Gb = g->G;
+    g->bs = (256 / g->G) * g->G;
+  } else {
+    if (g->G % 256) return false;
+    g->Gb = 256;
+    g->bs = 256;
+    gz = g->G / 256;
+  }
+  g->ppb = g->bs / g->Gb;
   const long long hw = (long long)a->H * a->W;
-  long long bx = (hw + g->ppb - 1) / g->ppb;
-  long long cap = (long long)(total_blocks + a->B - 1) / a->B;
+  const long long n = per_image ? hw : hw * a->B;
+  const int gy = per_image ? a->B : 1;
+  long long bx = (n + (long long)g->ppb * U - 1) / ((long long)g->ppb * U);
+  if (min_iters > 1) bx = (bx + min_iters - 1) / min_iters;  // reductions: amortise the per-block fold + atomics
+  long long cap = total_blocks / ((long long)gy * gz);
   if (cap < 1) cap = 1;
   if (bx > cap) bx = cap;
-  g->grid = dim3((unsigned)bx, (unsigned)a->B);
+  if (bx < 1) bx = 1;
+  g->grid = dim3((unsigned)bx, (unsigned)gy, (unsigned)gz);
   return true;
 }
 
@@ -62,56 +91,57 @@ __device__ __forceinline__ T* at(const OctaveAct& a, long long pix, int c) {
   return reinterpret_cast<T*>(a.data) + pix * a.ld + a.coff + c;
 }
 
-// Fold NV per-thread values over the pixel lanes of a block (threads with equal tid % G).
-// Result valid for threads tid < G.  sm must hold NV * blockDim.x floats.
-template <int NV>
-__device__ __forceinline__ void fold_lanes(float (&v)[NV], float* sm, int G) {
-  const int tid = threadIdx.x, bs = blockDim.x;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) sm[i * bs + tid] = v[i];
-  __syncthreads();
-  if (tid < G) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float s = 0.f;
-      for (int l = tid; l < bs; l += G) s += sm[i * bs + l];
-      v[i] = s;
-    }
-  }
+struct Tix {
+  int cg, lane, ppb;
+  long long base, n, first, stride;
+};
+template <int U>
+__device__ __forceinline__ Tix make_tix(const OctaveAct& x, int Gb) {
+  Tix t;
+  t.cg = blockIdx.z * Gb + threadIdx.x % Gb;
+  t.lane = threadIdx.x / Gb;
+  t.ppb = blockDim.x / Gb;
+  const long long hw = (long long)x.H * x.W;
+  if (gridDim.y > 1 || x.B == 1) { t.base = (long long)blockIdx.y * hw; t.n = hw; }
+  else { t.base = 0; t.n = hw * x.B; }
+  t.first = (long long)blockIdx.x * t.ppb * U + t.lane;
+  t.stride = (long long)gridDim.x * t.ppb * U;
+  return t;
 }
 
 // ---------------------------------------------------------------------------------------------------
+constexpr int U_STATS = 8;
 template <typename T>
-__global__ void chan_stats_kernel(const OctaveAct x, double* sums) {
+__global__ void __launch_bounds__(256, 4) chan_stats_kernel(const OctaveAct x, int Gb, double* sums) {
   extern __shared__ float sm[];
-  const int G = x.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)x.H * x.W, base = (long long)blockIdx.y * hw;
+  const Tix t = make_tix<U_STATS>(x, Gb);
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  const long long step = (long long)gridDim.x * ppb;
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += 4 * step) {
-    float f[4][8];
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> r[U_STATS];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (p + u * step < hw) VecIO<T, 8>::ld(at<T>(x, base + p + u * step, cg * 8), f[u]);
-      else {
+    for (int u = 0; u < U_STATS; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) r[u].ld(at<T>(x, t.base + q, t.cg * 8));
+    }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+    for (int u = 0; u < U_STATS; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float f[8];
+        r[u].get(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] += f[i]; v[8 + i] += f[i] * f[i]; }
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { v[i] += f[u][i]; v[8 + i] += f[u][i] * f[u][i]; }
-    }
   }
-  fold_lanes<16>(v, sm, G);
-  if (threadIdx.x < G) {
+  fold_lanes<16>(v, sm, Gb);
+  if (threadIdx.x < Gb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(sums + cg * 8 + i, (double)v[i]);
-      atomicAdd(sums + x.C + cg * 8 + i, (double)v[8 + i]);
+      atomicAdd(sums + t.cg * 8 + i, (double)v[i]);
+      atomicAdd(sums + x.C + t.cg * 8 + i, (double)v[8 + i]);
     }
   }
 }
@@ -145,260 +175,353 @@ __global__ void bn_prepare_kernel(int C, double count, const double* sums, const
   mi[C + c] = invstd;
 }
 
-template <typename T>
-__global__ void affine_act_kernel(const OctaveAct x, const float* ab, const OctaveAct res, int has_res, int relu,
-                                  const OctaveAct y, float* gap) {
+constexpr int U_AFF = 4;
+template <typename T, bool HAS_RES, bool HAS_GAP>
+__global__ void __launch_bounds__(256) affine_act_kernel(const OctaveAct x, int Gb, const float* ab, const OctaveAct res,
+                                                         int relu, const OctaveAct y, float* gap) {
   extern __shared__ float sm[];
-  const int G = x.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)x.H * x.W, base = (long long)blockIdx.y * hw;
+  const Tix t = make_tix<U_AFF>(x, Gb);
   float a[8], b[8], acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    a[i] = ab ? ab[cg * 8 + i] : 1.f;
-    b[i] = ab ? ab[x.C + cg * 8 + i] : 0.f;
+    a[i] = ab ? ab[t.cg * 8 + i] : 1.f;
+    b[i] = ab ? ab[x.C + t.cg * 8 + i] : 0.f;
     acc[i] = 0.f;
   }
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float f[8];
-    VecIO<T, 8>::ld(at<T>(x, base + p, cg * 8), f);
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> rx[U_AFF], rr[HAS_RES ? U_AFF : 1];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = f[i] * a[i] + b[i];
-    if (has_res) {
-      float r[8];
-      VecIO<T, 8>::ld(at<T>(res, base + p, cg * 8), r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    for (int u = 0; u < U_AFF; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        rx[u].ld(at<T>(x, t.base + q, t.cg * 8));
+        if (HAS_RES) rr[u].ld(at<T>(res, t.base + q, t.cg * 8));
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-    }
-    if (gap) {
-      // accumulate what the consumer will read back (storage-rounded values)
+    for (int u = 0; u < U_AFF; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float f[8];
+        rx[u].get(f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += to_f(from_f<T>(f[i]));
+        for (int i = 0; i < 8; ++i) f[i] = f[i] * a[i] + b[i];
+        if (HAS_RES) {
+          float r[8];
+          rr[u].get(r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += r[i];
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (HAS_GAP) {
+          // accumulate what the consumer will read back (storage-rounded values)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += to_f(from_f<T>(f[i]));
+        }
+        VecIO<T, 8>::st(at<T>(y, t.base + q, t.cg * 8), f);
+      }
     }
-    VecIO<T, 8>::st(at<T>(y, base + p, cg * 8), f);
   }
-  if (gap) {
-    fold_lanes<8>(acc, sm, G);
-    if (threadIdx.x < G) {
+  if (HAS_GAP) {
+    fold_lanes<8>(acc, sm, Gb);
+    if (threadIdx.x < Gb) {
       const int half = x.C >> 1;
-      const int c = (cg * 8) % half;
+      const int c = (t.cg * 8) % half;
 #pragma unroll
       for (int i = 0; i < 8; ++i) atomicAdd(gap + (long long)blockIdx.y * half + c + i, acc[i]);
     }
   }
 }
 
-// has_mask: 0 none, 1 mask tensor (dz = dy * (mask > 0)), 2 recompute the ReLU mask of this very BN from x: (x*a+b > 0)
-template <typename T>
-__global__ void bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, int has_mask, const float* ab, const OctaveAct x,
-                                     const float* mi, double* sums2) {
+// MASK: 0 none, 1 mask tensor (dz = dy * (mask > 0)), 2 recompute the ReLU mask of this very BN from x: (x*a+b > 0)
+constexpr int U_BNR = 4;
+template <typename T, int MASK>
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, int Gb,
+                                                               const float* ab, const OctaveAct x, const float* mi,
+                                                               double* sums2) {
   extern __shared__ float sm[];
-  const int G = x.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)x.H * x.W, base = (long long)blockIdx.y * hw;
-  float mean[8], inv[8], v[16], aa[8], bb[8];
+  const Tix t = make_tix<U_BNR>(x, Gb);
+  float mean[8], v[16], aa[8], bb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    mean[i] = mi[cg * 8 + i];
-    inv[i] = mi[x.C + cg * 8 + i];
-    aa[i] = has_mask == 2 ? ab[cg * 8 + i] : 0.f;
-    bb[i] = has_mask == 2 ? ab[x.C + cg * 8 + i] : 0.f;
+    mean[i] = mi[t.cg * 8 + i];
+    aa[i] = MASK == 2 ? ab[t.cg * 8 + i] : 0.f;
+    bb[i] = MASK == 2 ? ab[x.C + t.cg * 8 + i] : 0.f;
     v[i] = v[8 + i] = 0.f;
   }
-  const long long step = (long long)gridDim.x * ppb;
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += 2 * step) {
-    float d[2][8], f[2][8], m[2][8];
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> rd[U_BNR], rx[U_BNR], rm[MASK == 1 ? U_BNR : 1];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const bool ok = p + u * step < hw;
-      const long long q = ok ? p + u * step : p;
-      VecIO<T, 8>::ld(at<T>(dy, base + q, cg * 8), d[u]);
-      VecIO<T, 8>::ld(at<T>(x, base + q, cg * 8), f[u]);
-      if (has_mask == 1) VecIO<T, 8>::ld(at<T>(mask, base + q, cg * 8), m[u]);
-      if (has_mask == 2) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m[u][i] = to_f(from_f<T>(f[u][i] * aa[i] + bb[i]));
-      }
-      if (!ok) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[u][i] = 0.f;
+    for (int u = 0; u < U_BNR; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        rd[u].ld(at<T>(dy, t.base + q, t.cg * 8));
+        rx[u].ld(at<T>(x, t.base + q, t.cg * 8));
+        if (MASK == 1) rm[u].ld(at<T>(mask, t.base + q, t.cg * 8));
+      } else {
+        rd[u].zero();
+        rx[u].zero();
+        if (MASK == 1) rm[u].zero();
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U_BNR; ++u) {
+      float d[8], f[8];
+      rd[u].get(d);
+      rx[u].get(f);
+      if (MASK == 1) {
+        float m[8];
+        rm[u].get(m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+      } else if (MASK == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? d[i] : 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float dd = (has_mask && !(m[u][i] > 0.f)) ? 0.f : d[u][i];
-        v[i] += dd;
-        v[8 + i] += dd * (f[u][i] - mean[i]) * inv[i];
+        v[i] += d[i];
+        v[8 + i] += d[i] * (f[i] - mean[i]);
       }
     }
   }
-  fold_lanes<16>(v, sm, G);
-  if (threadIdx.x < G) {
+  fold_lanes<16>(v, sm, Gb);
+  if (threadIdx.x < Gb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(sums2 + cg * 8 + i, (double)v[i]);
-      atomicAdd(sums2 + x.C + cg * 8 + i, (double)v[8 + i]);
+      atomicAdd(sums2 + t.cg * 8 + i, (double)v[i]);
+      atomicAdd(sums2 + x.C + t.cg * 8 + i, (double)v[8 + i] * (double)mi[x.C + t.cg * 8 + i]);
     }
   }
 }
 
-template <typename T>
-__global__ void bn_bwd_apply_kernel(const OctaveAct dy, const OctaveAct mask, int has_mask, const float* ab, const OctaveAct x,
-                                    const float* mi, const float* gamma, const double* sums2, int training,
-                                    const OctaveAct dx, float* dgamma, float* dbeta) {
-  const int G = x.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)x.H * x.W, base = (long long)blockIdx.y * hw;
-  const float inv_n = 1.f / ((float)x.B * (float)hw);
-  float mean[8], inv[8], k1[8], k2[8], ag[8], aa[8], bb[8];
+// dx = P*dz + Q*x + R with P = gamma*invstd, Q = -P*invstd*mean(dz*xhat), R = -P*mean(dz) - Q*mean
+constexpr int U_BNA = 2;
+template <typename T, int MASK>
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bn_bwd_apply_kernel(const OctaveAct dy, const OctaveAct mask, int Gb,
+                                                              const float* ab, const OctaveAct x, const float* mi,
+                                                              const float* gamma, const double* sums2, int training,
+                                                              const OctaveAct dx, float* dgamma, float* dbeta) {
+  const Tix t = make_tix<U_BNA>(x, Gb);
+  const float inv_n = 1.f / ((float)x.B * (float)x.H * (float)x.W);
+  float P[8], Q[8], R[8], aa[8], bb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = cg * 8 + i;
-    mean[i] = mi[c];
-    inv[i] = mi[x.C + c];
-    aa[i] = has_mask == 2 ? ab[c] : 0.f;
-    bb[i] = has_mask == 2 ? ab[x.C + c] : 0.f;
+    const int c = t.cg * 8 + i;
+    const float mean = mi[c], inv = mi[x.C + c];
+    aa[i] = MASK == 2 ? ab[c] : 0.f;
+    bb[i] = MASK == 2 ? ab[x.C + c] : 0.f;
     const float sd = (float)sums2[c], sdx = (float)sums2[x.C + c];
-    k1[i] = training ? sd * inv_n : 0.f;
-    k2[i] = training ? sdx * inv_n : 0.f;
-    ag[i] = (gamma ? gamma[c] : 1.f) * inv[i];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+    const float k1 = training ? sd * inv_n : 0.f;
+    const float k2 = training ? sdx * inv_n : 0.f;
+    P[i] = (gamma ? gamma[c] : 1.f) * inv;
+    Q[i] = -P[i] * inv * k2;
+    R[i] = -P[i] * k1 - Q[i] * mean;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && t.lane == 0) {
       if (dgamma) dgamma[c] = sdx;
       if (dbeta) dbeta[c] = sd;
     }
   }
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float d[8], f[8];
-    VecIO<T, 8>::ld(at<T>(dy, base + p, cg * 8), d);
-    VecIO<T, 8>::ld(at<T>(x, base + p, cg * 8), f);
-    if (has_mask == 1) {
-      float m[8];
-      VecIO<T, 8>::ld(at<T>(mask, base + p, cg * 8), m);
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> rd[U_BNA], rx[U_BNA], rm[MASK == 1 ? U_BNA : 1];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
-    } else if (has_mask == 2) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? d[i] : 0.f;
+    for (int u = 0; u < U_BNA; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        rd[u].ld(at<T>(dy, t.base + q, t.cg * 8));
+        rx[u].ld(at<T>(x, t.base + q, t.cg * 8));
+        if (MASK == 1) rm[u].ld(at<T>(mask, t.base + q, t.cg * 8));
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = ag[i] * (d[i] - k1[i] - (f[i] - mean[i]) * inv[i] * k2[i]);
-    VecIO<T, 8>::st(at<T>(dx, base + p, cg * 8), d);
-  }
-}
-
-template <typename T>
-__global__ void add_inplace_kernel(const OctaveAct dst, const OctaveAct src) {
-  const int G = dst.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)dst.H * dst.W, base = (long long)blockIdx.y * hw;
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float a[8], b[8];
-    VecIO<T, 8>::ld(at<T>(dst, base + p, cg * 8), a);
-    VecIO<T, 8>::ld(at<T>(src, base + p, cg * 8), b);
+    for (int u = 0; u < U_BNA; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float d[8], f[8];
+        rd[u].get(d);
+        rx[u].get(f);
+        if (MASK == 1) {
+          float m[8];
+          rm[u].get(m);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] += b[i];
-    VecIO<T, 8>::st(at<T>(dst, base + p, cg * 8), a);
-  }
-}
-
-template <typename T>
-__global__ void relu_bwd_kernel(const OctaveAct dy, const OctaveAct mask, const OctaveAct dx) {
-  const int G = dy.C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)dy.H * dy.W, base = (long long)blockIdx.y * hw;
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float a[8], m[8];
-    VecIO<T, 8>::ld(at<T>(dy, base + p, cg * 8), a);
-    VecIO<T, 8>::ld(at<T>(mask, base + p, cg * 8), m);
+          for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+        } else if (MASK == 2) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = m[i] > 0.f ? a[i] : 0.f;
-    VecIO<T, 8>::st(at<T>(dx, base + p, cg * 8), a);
+          for (int i = 0; i < 8; ++i) d[i] = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? d[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = P[i] * d[i] + (Q[i] * f[i] + R[i]);
+        VecIO<T, 8>::st(at<T>(dx, t.base + q, t.cg * 8), d);
+      }
+    }
   }
 }
 
-// ---- split attention ------------------------------------------------------------------------------
+// OP 0: dst += src; OP 1: dst = src * (mask > 0)  (a = dst/dy, b = src/mask)
+constexpr int U_BIN = 4;
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) binary_kernel(const OctaveAct a, const OctaveAct b, int Gb, const OctaveAct out) {
+  const Tix t = make_tix<U_BIN>(a, Gb);
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> ra[U_BIN], rb[U_BIN];
+#pragma unroll
+    for (int u = 0; u < U_BIN; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        ra[u].ld(at<T>(a, t.base + q, t.cg * 8));
+        rb[u].ld(at<T>(b, t.base + q, t.cg * 8));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U_BIN; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float f[8], g[8];
+        ra[u].get(f);
+        rb[u].get(g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = OP == 0 ? f[i] + g[i] : (g[i] > 0.f ? f[i] : 0.f);
+        VecIO<T, 8>::st(at<T>(out, t.base + q, t.cg * 8), f);
+      }
+    }
+  }
+}
+
+// ---- split attention (per image: blockIdx.y = image) -------------------------------------------------
+constexpr int U_SPL = 2;
 template <typename T>
-__global__ void splat_combine_kernel(const OctaveAct U, const float* att, int relu, const OctaveAct out) {
-  const int C = out.C, G = C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)out.H * out.W, base = (long long)blockIdx.y * hw;
+__global__ void __launch_bounds__(256) splat_combine_kernel(const OctaveAct U, const float* att, int Gb, int relu,
+                                                            const OctaveAct out) {
+  const int C = out.C;
+  const Tix t = make_tix<U_SPL>(out, Gb);
   float a0[8], a1[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    a0[i] = att[(long long)blockIdx.y * 2 * C + cg * 8 + i];
-    a1[i] = att[(long long)blockIdx.y * 2 * C + C + cg * 8 + i];
+    a0[i] = att[(long long)blockIdx.y * 2 * C + t.cg * 8 + i];
+    a1[i] = att[(long long)blockIdx.y * 2 * C + C + t.cg * 8 + i];
   }
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float u0[8], u1[8];
-    VecIO<T, 8>::ld(at<T>(U, base + p, cg * 8), u0);
-    VecIO<T, 8>::ld(at<T>(U, base + p, C + cg * 8), u1);
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> r0[U_SPL], r1[U_SPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      u0[i] = a0[i] * u0[i] + a1[i] * u1[i];
-      if (relu) u0[i] = fmaxf(u0[i], 0.f);
+    for (int u = 0; u < U_SPL; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        r0[u].ld(at<T>(U, t.base + q, t.cg * 8));
+        r1[u].ld(at<T>(U, t.base + q, C + t.cg * 8));
+      }
     }
-    VecIO<T, 8>::st(at<T>(out, base + p, cg * 8), u0);
+#pragma unroll
+    for (int u = 0; u < U_SPL; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float u0[8], u1[8];
+        r0[u].get(u0);
+        r1[u].get(u1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          u0[i] = a0[i] * u0[i] + a1[i] * u1[i];
+          if (relu) u0[i] = fmaxf(u0[i], 0.f);
+        }
+        VecIO<T, 8>::st(at<T>(out, t.base + q, t.cg * 8), u0);
+      }
+    }
   }
 }
 
-template <typename T>
-__global__ void splat_bwd_reduce_kernel(const OctaveAct dout, const OctaveAct mask, int has_mask, const OctaveAct U,
-                                        float* datt) {
+template <typename T, bool HAS_MASK>
+__global__ void __launch_bounds__(256, 2) splat_bwd_reduce_kernel(const OctaveAct dout, const OctaveAct mask, int Gb,
+                                                                  const OctaveAct U, float* datt) {
   extern __shared__ float sm[];
-  const int C = dout.C, G = C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)dout.H * dout.W, base = (long long)blockIdx.y * hw;
+  const int C = dout.C;
+  const Tix t = make_tix<U_SPL>(dout, Gb);
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float d[8], u0[8], u1[8];
-    VecIO<T, 8>::ld(at<T>(dout, base + p, cg * 8), d);
-    VecIO<T, 8>::ld(at<T>(U, base + p, cg * 8), u0);
-    VecIO<T, 8>::ld(at<T>(U, base + p, C + cg * 8), u1);
-    if (has_mask) {
-      float m[8];
-      VecIO<T, 8>::ld(at<T>(mask, base + p, cg * 8), m);
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> rd[U_SPL], r0[U_SPL], r1[U_SPL], rm[HAS_MASK ? U_SPL : 1];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+    for (int u = 0; u < U_SPL; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        rd[u].ld(at<T>(dout, t.base + q, t.cg * 8));
+        r0[u].ld(at<T>(U, t.base + q, t.cg * 8));
+        r1[u].ld(at<T>(U, t.base + q, C + t.cg * 8));
+        if (HAS_MASK) rm[u].ld(at<T>(mask, t.base + q, t.cg * 8));
+      } else {
+        rd[u].zero(); r0[u].zero(); r1[u].zero();
+        if (HAS_MASK) rm[u].zero();
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] += d[i] * u0[i]; v[8 + i] += d[i] * u1[i]; }
+    for (int u = 0; u < U_SPL; ++u) {
+      float d[8], u0[8], u1[8];
+      rd[u].get(d);
+      r0[u].get(u0);
+      r1[u].get(u1);
+      if (HAS_MASK) {
+        float m[8];
+        rm[u].get(m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] += d[i] * u0[i]; v[8 + i] += d[i] * u1[i]; }
+    }
   }
-  fold_lanes<16>(v, sm, G);
-  if (threadIdx.x < G) {
+  fold_lanes<16>(v, sm, Gb);
+  if (threadIdx.x < Gb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(datt + (long long)blockIdx.y * 2 * C + cg * 8 + i, v[i]);
-      atomicAdd(datt + (long long)blockIdx.y * 2 * C + C + cg * 8 + i, v[8 + i]);
+      atomicAdd(datt + (long long)blockIdx.y * 2 * C + t.cg * 8 + i, v[i]);
+      atomicAdd(datt + (long long)blockIdx.y * 2 * C + C + t.cg * 8 + i, v[8 + i]);
     }
   }
 }
 
-template <typename T>
-__global__ void splat_bwd_du_kernel(const OctaveAct dout, const OctaveAct mask, int has_mask, const float* att,
-                                    const float* dgap, float gap_scale, const OctaveAct dU) {
-  const int C = dout.C, G = C >> 3, cg = threadIdx.x % G, lane = threadIdx.x / G, ppb = blockDim.x / G;
-  const long long hw = (long long)dout.H * dout.W, base = (long long)blockIdx.y * hw;
+template <typename T, bool HAS_MASK>
+__global__ void __launch_bounds__(256) splat_bwd_du_kernel(const OctaveAct dout, const OctaveAct mask, int Gb,
+                                                           const float* att, const float* dgap, float gap_scale,
+                                                           const OctaveAct dU) {
+  const int C = dout.C;
+  const Tix t = make_tix<U_SPL>(dout, Gb);
   float a0[8], a1[8], gg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    a0[i] = att[(long long)blockIdx.y * 2 * C + cg * 8 + i];
-    a1[i] = att[(long long)blockIdx.y * 2 * C + C + cg * 8 + i];
-    gg[i] = dgap ? dgap[(long long)blockIdx.y * C + cg * 8 + i] * gap_scale : 0.f;
+    a0[i] = att[(long long)blockIdx.y * 2 * C + t.cg * 8 + i];
+    a1[i] = att[(long long)blockIdx.y * 2 * C + C + t.cg * 8 + i];
+    gg[i] = dgap ? dgap[(long long)blockIdx.y * C + t.cg * 8 + i] * gap_scale : 0.f;
   }
-  for (long long p = (long long)blockIdx.x * ppb + lane; p < hw; p += (long long)gridDim.x * ppb) {
-    float d[8], o0[8], o1[8];
-    VecIO<T, 8>::ld(at<T>(dout, base + p, cg * 8), d);
-    if (has_mask) {
-      float m[8];
-      VecIO<T, 8>::ld(at<T>(mask, base + p, cg * 8), m);
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> rd[U_SPL], rm[HAS_MASK ? U_SPL : 1];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+    for (int u = 0; u < U_SPL; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        rd[u].ld(at<T>(dout, t.base + q, t.cg * 8));
+        if (HAS_MASK) rm[u].ld(at<T>(mask, t.base + q, t.cg * 8));
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { o0[i] = a0[i] * d[i] + gg[i]; o1[i] = a1[i] * d[i] + gg[i]; }
-    VecIO<T, 8>::st(at<T>(dU, base + p, cg * 8), o0);
-    VecIO<T, 8>::st(at<T>(dU, base + p, C + cg * 8), o1);
+    for (int u = 0; u < U_SPL; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float d[8], o0[8], o1[8];
+        rd[u].get(d);
+        if (HAS_MASK) {
+          float m[8];
+          rm[u].get(m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o0[i] = a0[i] * d[i] + gg[i]; o1[i] = a1[i] * d[i] + gg[i]; }
+        VecIO<T, 8>::st(at<T>(dU, t.base + q, t.cg * 8), o0);
+        VecIO<T, 8>::st(at<T>(dU, t.base + q, C + t.cg * 8), o1);
+      }
+    }
   }
 }
 
@@ -408,15 +531,21 @@ __global__ void splat_bwd_du_kernel(const OctaveAct dout, const OctaveAct mask, 
     else { using T = bf16; __VA_ARGS__; }              \
   } while (0)
 
+// one wave of `fn`: resident blocks per SM x SMs
+#define ONE_WAVE(fn, bs, smem) (resident_blocks(reinterpret_cast<const void*>(fn), (bs), (smem)) * sm_count())
+
 }  // namespace
 
 extern "C" int octave_chan_stats(const OctaveAct* x, double* sums, void* stream) {
   if (!view_ok(x) || !sums) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(x, &g, kReduceBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
-  DISPATCH_T(x->dtype, (chan_stats_kernel<T><<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*x, sums)));
+  Geo g;
+  DISPATCH_T(x->dtype, {
+    auto fn = chan_stats_kernel<T>;
+    if (!make_geo(x, &g, U_STATS, false, ONE_WAVE(fn, 256, 16 * 256 * sizeof(float)), 4)) return OCT_ERR_UNSUPPORTED;
+    fn<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*x, g.Gb, sums);
+  });
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -434,19 +563,42 @@ extern "C" int octave_bn_prepare(int32_t C, double count, const double* sums, co
   return OCT_OK;
 }
 
+template <typename T, bool HAS_RES, bool HAS_GAP>
+static int launch_affine(const OctaveAct* x, const float* ab, const OctaveAct* res, int relu, const OctaveAct* y,
+                         float* gap, cudaStream_t s) {
+  auto fn = affine_act_kernel<T, HAS_RES, HAS_GAP>;
+  const size_t smem = HAS_GAP ? 8 * 256 * sizeof(float) : 0;
+  Geo g;
+  if (!make_geo(x, &g, U_AFF, HAS_GAP, ONE_WAVE(fn, 256, smem), HAS_GAP ? 4 : 1)) return OCT_ERR_UNSUPPORTED;
+  OctaveAct r = res ? *res : *x;
+  fn<<<g.grid, g.bs, HAS_GAP ? 8 * g.bs * sizeof(float) : 0, s>>>(*x, g.Gb, ab, r, relu, *y, gap);
+  return OCT_OK;
+}
+
 extern "C" int octave_affine_act(const OctaveAct* x, const float* ab, const OctaveAct* res, int32_t relu,
                                  const OctaveAct* y, float* gap, void* stream) {
   if (!view_ok(x) || !view_ok(y) || !same_shape(x, y)) return OCT_ERR_INVALID;
   if (res && (!view_ok(res) || !same_shape(x, res))) return OCT_ERR_INVALID;
   if (gap && (x->C % 16)) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(x, &g, gap ? kReduceBlocks * 2 : kStreamBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (gap && cudaMemsetAsync(gap, 0, sizeof(float) * x->B * (x->C / 2), s) != cudaSuccess) return OCT_ERR_LAUNCH;
-  OctaveAct r = res ? *res : *x;
-  DISPATCH_T(x->dtype, (affine_act_kernel<T><<<g.grid, g.bs, gap ? 8 * g.bs * sizeof(float) : 0, s>>>(
-                           *x, ab, r, res != nullptr, relu, *y, gap)));
+  int rc = OCT_OK;
+  DISPATCH_T(x->dtype, {
+    if (gap) rc = res ? launch_affine<T, true, true>(x, ab, res, relu, y, gap, s) : launch_affine<T, false, true>(x, ab, res, relu, y, gap, s);
+    else rc = res ? launch_affine<T, true, false>(x, ab, res, relu, y, gap, s) : launch_affine<T, false, false>(x, ab, res, relu, y, gap, s);
+  });
+  if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+template <typename T, int MASK>
+static int launch_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* m, const float* relu_ab, const OctaveAct* x,
+                                const float* mi, double* sums2, cudaStream_t s) {
+  auto fn = bn_bwd_reduce_kernel<T, MASK>;
+  Geo g;
+  if (!make_geo(x, &g, U_BNR, false, ONE_WAVE(fn, 256, 16 * 256 * sizeof(float)), 4)) return OCT_ERR_UNSUPPORTED;
+  fn<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*dy, *m, g.Gb, relu_ab, *x, mi, sums2);
   return OCT_OK;
 }
 
@@ -454,15 +606,29 @@ extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, 
                                     const float* mean_invstd, double* sums2, void* stream) {
   if (!view_ok(dy) || !view_ok(x) || !same_shape(dy, x) || !mean_invstd || !sums2) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, x))) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(x, &g, kReduceBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
-  OctaveAct m = mask ? *mask : *x;
+  const OctaveAct* m = mask ? mask : x;
   const int mmode = mask ? 1 : (relu_ab ? 2 : 0);
-  DISPATCH_T(x->dtype, (bn_bwd_reduce_kernel<T><<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(
-                           *dy, m, mmode, relu_ab, *x, mean_invstd, sums2)));
+  int rc = OCT_OK;
+  DISPATCH_T(x->dtype, {
+    if (mmode == 0) rc = launch_bn_bwd_reduce<T, 0>(dy, m, relu_ab, x, mean_invstd, sums2, s);
+    else if (mmode == 1) rc = launch_bn_bwd_reduce<T, 1>(dy, m, relu_ab, x, mean_invstd, sums2, s);
+    else rc = launch_bn_bwd_reduce<T, 2>(dy, m, relu_ab, x, mean_invstd, sums2, s);
+  });
+  if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+template <typename T, int MASK>
+static int launch_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* m, const float* relu_ab, const OctaveAct* x,
+                               const float* mi, const float* gamma, const double* sums2, int training,
+                               const OctaveAct* dx, float* dgamma, float* dbeta, cudaStream_t s) {
+  auto fn = bn_bwd_apply_kernel<T, MASK>;
+  Geo g;
+  if (!make_geo(x, &g, U_BNA, false, ONE_WAVE(fn, 256, 0))) return OCT_ERR_UNSUPPORTED;
+  fn<<<g.grid, g.bs, 0, s>>>(*dy, *m, g.Gb, relu_ab, *x, mi, gamma, sums2, training, *dx, dgamma, dbeta);
   return OCT_OK;
 }
 
@@ -472,30 +638,43 @@ extern "C" int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, c
   if (!view_ok(dy) || !view_ok(x) || !view_ok(dx) || !same_shape(dy, x) || !same_shape(dx, x)) return OCT_ERR_INVALID;
   if (!mean_invstd || !sums2) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, x))) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(x, &g)) return OCT_ERR_UNSUPPORTED;
-  OctaveAct m = mask ? *mask : *x;
+  cudaStream_t s = (cudaStream_t)stream;
+  const OctaveAct* m = mask ? mask : x;
   const int mmode = mask ? 1 : (relu_ab ? 2 : 0);
-  DISPATCH_T(x->dtype, (bn_bwd_apply_kernel<T><<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(
-                           *dy, m, mmode, relu_ab, *x, mean_invstd, gamma, sums2, training, *dx, dgamma, dbeta)));
+  int rc = OCT_OK;
+  DISPATCH_T(x->dtype, {
+    if (mmode == 0) rc = launch_bn_bwd_apply<T, 0>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, s);
+    else if (mmode == 1) rc = launch_bn_bwd_apply<T, 1>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, s);
+    else rc = launch_bn_bwd_apply<T, 2>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, s);
+  });
+  if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+template <typename T, int OP>
+static int launch_binary(const OctaveAct* a, const OctaveAct* b, const OctaveAct* out, cudaStream_t s) {
+  auto fn = binary_kernel<T, OP>;
+  Geo g;
+  if (!make_geo(a, &g, U_BIN, false, ONE_WAVE(fn, 256, 0))) return OCT_ERR_UNSUPPORTED;
+  fn<<<g.grid, g.bs, 0, s>>>(*a, *b, g.Gb, *out);
   return OCT_OK;
 }
 
 extern "C" int octave_add_inplace(const OctaveAct* dst, const OctaveAct* src, void* stream) {
   if (!view_ok(dst) || !view_ok(src) || !same_shape(dst, src)) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(dst, &g)) return OCT_ERR_UNSUPPORTED;
-  DISPATCH_T(dst->dtype, (add_inplace_kernel<T><<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(*dst, *src)));
+  int rc = OCT_OK;
+  DISPATCH_T(dst->dtype, rc = (launch_binary<T, 0>(dst, src, dst, (cudaStream_t)stream)));
+  if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
 
 extern "C" int octave_relu_bwd(const OctaveAct* dy, const OctaveAct* mask, const OctaveAct* dx, void* stream) {
   if (!view_ok(dy) || !view_ok(mask) || !view_ok(dx) || !same_shape(dy, mask) || !same_shape(dy, dx)) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(dy, &g)) return OCT_ERR_UNSUPPORTED;
-  DISPATCH_T(dy->dtype, (relu_bwd_kernel<T><<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(*dy, *mask, *dx)));
+  int rc = OCT_OK;
+  DISPATCH_T(dy->dtype, rc = (launch_binary<T, 1>(dy, mask, dx, (cudaStream_t)stream)));
+  if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -505,8 +684,11 @@ extern "C" int octave_splat_combine(const OctaveAct* U, const float* att, int32_
   if (!view_ok(U) || !view_ok(out) || !att) return OCT_ERR_INVALID;
   if (U->C != 2 * out->C || U->B != out->B || U->H != out->H || U->W != out->W || U->dtype != out->dtype) return OCT_ERR_INVALID;
   Geo g;
-  if (!make_geo(out, &g)) return OCT_ERR_UNSUPPORTED;
-  DISPATCH_T(out->dtype, (splat_combine_kernel<T><<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(*U, att, relu, *out)));
+  DISPATCH_T(out->dtype, {
+    auto fn = splat_combine_kernel<T>;
+    if (!make_geo(out, &g, U_SPL, true, 2 * ONE_WAVE(fn, 256, 0))) return OCT_ERR_UNSUPPORTED;
+    fn<<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(*U, att, g.Gb, relu, *out);
+  });
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -516,13 +698,21 @@ extern "C" int octave_splat_bwd_reduce(const OctaveAct* dout, const OctaveAct* m
   if (!view_ok(dout) || !view_ok(U) || !datt) return OCT_ERR_INVALID;
   if (U->C != 2 * dout->C || U->B != dout->B || U->H != dout->H || U->W != dout->W || U->dtype != dout->dtype) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, dout))) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(dout, &g, kReduceBlocks)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(datt, 0, sizeof(float) * dout->B * 2 * dout->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   OctaveAct m = mask ? *mask : *dout;
-  DISPATCH_T(dout->dtype, (splat_bwd_reduce_kernel<T><<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(
-                              *dout, m, mask != nullptr, *U, datt)));
+  Geo g;
+  DISPATCH_T(dout->dtype, {
+    if (mask) {
+      auto fn = splat_bwd_reduce_kernel<T, true>;
+      if (!make_geo(dout, &g, U_SPL, true, ONE_WAVE(fn, 256, 16 * 256 * sizeof(float)), 4)) return OCT_ERR_UNSUPPORTED;
+      fn<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*dout, m, g.Gb, *U, datt);
+    } else {
+      auto fn = splat_bwd_reduce_kernel<T, false>;
+      if (!make_geo(dout, &g, U_SPL, true, ONE_WAVE(fn, 256, 16 * 256 * sizeof(float)), 4)) return OCT_ERR_UNSUPPORTED;
+      fn<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*dout, m, g.Gb, *U, datt);
+    }
+  });
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -532,11 +722,19 @@ extern "C" int octave_splat_bwd_du(const OctaveAct* dout, const OctaveAct* mask,
   if (!view_ok(dout) || !view_ok(dU) || !att) return OCT_ERR_INVALID;
   if (dU->C != 2 * dout->C || dU->B != dout->B || dU->H != dout->H || dU->W != dout->W || dU->dtype != dout->dtype) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, dout))) return OCT_ERR_INVALID;
-  Geo g;
-  if (!make_geo(dout, &g)) return OCT_ERR_UNSUPPORTED;
   OctaveAct m = mask ? *mask : *dout;
-  DISPATCH_T(dout->dtype, (splat_bwd_du_kernel<T><<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(
-                              *dout, m, mask != nullptr, att, dgap, gap_scale, *dU)));
+  Geo g;
+  DISPATCH_T(dout->dtype, {
+    if (mask) {
+      auto fn = splat_bwd_du_kernel<T, true>;
+      if (!make_geo(dout, &g, U_SPL, true, 2 * ONE_WAVE(fn, 256, 0))) return OCT_ERR_UNSUPPORTED;
+      fn<<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(*dout, m, g.Gb, att, dgap, gap_scale, *dU);
+    } else {
+      auto fn = splat_bwd_du_kernel<T, false>;
+      if (!make_geo(dout, &g, U_SPL, true, 2 * ONE_WAVE(fn, 256, 0))) return OCT_ERR_UNSUPPORTED;
+      fn<<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(*dout, m, g.Gb, att, dgap, gap_scale, *dU);
+    }
+  });
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

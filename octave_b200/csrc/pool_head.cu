@@ -2,6 +2,7 @@
 // Reference arithmetic: nn.MaxPool2d / nn.AvgPool2d as configured at /root/reference/architectures/extra/resnest.py:189,340,383;
 // AdversarialAttentionGate.forward /root/reference/architectures/segmentor/blocks.py:38-46; ResnestUNet.fc compose.py:181.
 #include "common.cuh"
+#include "head_k2.cuh"
 #include "../../include/octave_b200.h"
 
 namespace {
@@ -525,6 +526,60 @@ static int head_check(const OctaveAct* x, int K) {
   return OCT_OK;
 }
 
+// one wave of resident blocks for the persistent K=2 head kernels
+template <typename F>
+static int head_wave(F fn, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, smem) != cudaSuccess || n < 1) n = 1;
+  int sms = octave_sm_count();
+  if (sms <= 0) sms = 148;
+  return n * sms;
+}
+
+template <typename T, int LP, int NCH, int MODE>
+static void launch_head_k2_fwd(const OctaveAct* x, const float* w, const float* b, float* out, const OctaveAct& g,
+                               cudaStream_t s) {
+  constexpr int U = 4 / NCH;
+  auto fn = head_k2::fwd_kernel<T, LP, NCH, U, MODE>;
+  static int wave = 0;
+  if (!wave) wave = head_wave(fn, 0);
+  const long long npix = (long long)x->B * x->H * x->W;
+  long long need = (npix + (256 / LP) * U - 1) / ((256 / LP) * U);
+  const int grid = (int)(need < wave ? (need < 1 ? 1 : need) : wave);
+  fn<<<grid, 256, 0, s>>>(*x, w, b, out, g);
+}
+
+template <typename T, int LP, int NCH, int MODE>
+static void launch_head_k2_bwd(const OctaveAct* x, const float* w, const float* b, const float* dout, const OctaveAct& g,
+                               const OctaveAct* dx, float* dw, float* db, cudaStream_t s) {
+  constexpr int U = 4 / NCH;
+  auto fn = head_k2::bwd_kernel<T, LP, NCH, U, MODE>;
+  constexpr size_t smem = 18 * 256 * sizeof(float);
+  static int wave = 0;
+  if (!wave) wave = head_wave(fn, smem);
+  const long long npix = (long long)x->B * x->H * x->W;
+  long long need = (npix + (256 / LP) * U * 4 - 1) / ((256 / LP) * U * 4);   // >= 4 iterations per block: amortise the fold
+  const int grid = (int)(need < wave ? (need < 1 ? 1 : need) : wave);
+  fn<<<grid, 256, smem, s>>>(*x, w, b, dout, g, *dx, dw, db);
+}
+
+#define DISPATCH_K2(lp, nch, ...)                                                        \
+  switch (lp) {                                                                          \
+    case 4: { constexpr int LP = 4; constexpr int NCH = 1; __VA_ARGS__; break; }         \
+    case 8: { constexpr int LP = 8; constexpr int NCH = 1; __VA_ARGS__; break; }         \
+    case 16: { constexpr int LP = 16; constexpr int NCH = 1; __VA_ARGS__; break; }       \
+    default:                                                                             \
+      if (nch == 1) { constexpr int LP = 32; constexpr int NCH = 1; __VA_ARGS__; }       \
+      else if (nch == 2) { constexpr int LP = 32; constexpr int NCH = 2; __VA_ARGS__; }  \
+      else { constexpr int LP = 32; constexpr int NCH = 4; __VA_ARGS__; }                \
+      break;                                                                             \
+  }
+
+static bool head_k2_ok(const OctaveAct* x, int K) {
+  const int lp = pick_lp(x->C), nch = x->C / (8 * lp);
+  return K == 2 && lp >= 4 && (nch == 1 || nch == 2 || nch == 4);
+}
+
 extern "C" int octave_head_fwd(const OctaveAct* x, const float* w, const float* b, int32_t K, int32_t mode, float* out,
                                const OctaveAct* gated, void* stream) {
   int rc = head_check(x, K);
@@ -533,25 +588,54 @@ extern "C" int octave_head_fwd(const OctaveAct* x, const float* w, const float* 
   if (mode == 1 && (!view_ok(gated) || gated->C != x->C)) return OCT_ERR_INVALID;
   const int lp = pick_lp(x->C);
   const long long npix = (long long)x->B * x->H * x->W;
-  const int grid = grid_for(npix * lp, 256);
   OctaveAct g = gated ? *gated : *x;
+  if (head_k2_ok(x, K)) {
+    const int nch = x->C / (8 * lp);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH_T(x->dtype, DISPATCH_K2(lp, nch, {
+      if (mode == 1) launch_head_k2_fwd<T, LP, NCH, 1>(x, w, b, out, g, s);
+      else launch_head_k2_fwd<T, LP, NCH, 0>(x, w, b, out, g, s);
+    }));
+    OCT_CHECK_LAUNCH();
+    return OCT_OK;
+  }
+  const int grid = grid_for(npix * lp, 256);
   DISPATCH_T(x->dtype, DISPATCH_LP(lp, (head_fwd_kernel<T, LP><<<grid, 256, 0, (cudaStream_t)stream>>>(*x, w, b, K, mode, out, g))));
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
 
 extern "C" int octave_head_bwd(const OctaveAct* x, const float* w, const float* b, int32_t K, int32_t mode, const float* dout,
-                               const OctaveAct* dgated, const OctaveAct* dx, float* dlogits, void* stream) {
+                               const OctaveAct* dgated, const OctaveAct* dx, float* dlogits, float* dw, float* db,
+                               void* stream) {
   int rc = head_check(x, K);
   if (rc != OCT_OK) return rc;
   if (!w || !b || !view_ok(dx) || dx->C != x->C) return OCT_ERR_INVALID;
   if (mode == 1 && (!view_ok(dgated) || dgated->C != x->C)) return OCT_ERR_INVALID;
+  if ((dw != nullptr) != (db != nullptr)) return OCT_ERR_INVALID;
   const int lp = pick_lp(x->C);
   const long long npix = (long long)x->B * x->H * x->W;
-  const int grid = grid_for(npix * lp, 256);
   OctaveAct g = dgated ? *dgated : *x;
-  DISPATCH_T(x->dtype, DISPATCH_LP(lp, (head_bwd_kernel<T, LP><<<grid, 256, 0, (cudaStream_t)stream>>>(*x, w, b, K, mode, dout, g, *dx, dlogits))));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (head_k2_ok(x, K) && !dlogits) {
+    if (dw) {
+      if (cudaMemsetAsync(dw, 0, sizeof(float) * K * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+      if (cudaMemsetAsync(db, 0, sizeof(float) * K, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+    }
+    const int nch = x->C / (8 * lp);
+    DISPATCH_T(x->dtype, DISPATCH_K2(lp, nch, {
+      if (mode == 1) launch_head_k2_bwd<T, LP, NCH, 1>(x, w, b, dout, g, dx, dw, db, s);
+      else launch_head_k2_bwd<T, LP, NCH, 0>(x, w, b, dout, g, dx, dw, db, s);
+    }));
+    OCT_CHECK_LAUNCH();
+    return OCT_OK;
+  }
+  // generic path: dlogits scratch is required; parameter gradients come from octave_head_wgrad
+  if (!dlogits) return OCT_ERR_INVALID;
+  const int grid = grid_for(npix * lp, 256);
+  DISPATCH_T(x->dtype, DISPATCH_LP(lp, (head_bwd_kernel<T, LP><<<grid, 256, 0, s>>>(*x, w, b, K, mode, dout, g, *dx, dlogits))));
   OCT_CHECK_LAUNCH();
+  if (dw) return octave_head_wgrad(x, dlogits, K, dw, db, stream);
   return OCT_OK;
 }
 

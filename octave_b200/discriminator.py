@@ -237,15 +237,18 @@ class DiscriminatorBlock(nn.Module):
             if need_maps:
                 gmaps[i + 1] = ops.s2d_to_nchw(dcatS, 16, 13, Cin, h, w)
             ops.act_bwd(catS, dcatS, ops.ACT_SIGMOID, out=dcatS)
-            dsq16 = Act.empty(catS.B, h, w, 16, catS.dtype, catS.device)
-            ops._chk("octave_depth_to_space", ops.lib.octave_depth_to_space(ops._ref(dcatS), ops._ref(dsq16), ops.stream_ptr()))
-            dsq = dsq16.slice(0, 13)
-            spec_sq = ConvSpec(sq.weight, sq.bias, sq.in_channels, 13, 1, 1, 0, 1)
+            # squeeze-conv backward on the tensor cores: the 13 gradient channels are padded to 32 (channels 13..15 hold
+            # finite don't-care values of the mask / pad quadrant channels, 16..31 zeros) and meet zero weight rows
+            dsq32 = Act.zeros(catS.B, h, w, 32, catS.dtype, catS.device)
+            ops._chk("octave_depth_to_space", ops.lib.octave_depth_to_space(ops._ref(dcatS), ops._ref(dsq32.slice(0, 16)), ops.stream_ptr()))
+            w32 = torch.zeros((32, sq.in_channels, 1, 1), dtype=torch.float32, device=catS.device)
+            w32[:13] = sq.weight.detach()
+            spec_sq = ConvSpec(w32, None, sq.in_channels, 32, 1, 1, 0, 1)
             if need_params:
-                # narrow (13-channel) weight gradient: CUDA-core kernel
-                dwq, dbq = ops.conv_wgrad_direct(s_in, dsq, spec_sq)
-                _acc(grads, sq.weight, dwq); _acc(grads, sq.bias, dbq)
-            ds = ops.conv_dgrad_direct(dsq, spec_sq, s_in.H, s_in.W)
+                dwq, _ = ops.conv_wgrad(s_in, dsq32, spec_sq)
+                _acc(grads, sq.weight, dwq[:13].contiguous())
+                _acc(grads, sq.bias, ops.chan_stats(dsq32)[:13].float())
+            ds = ops.conv_dgrad(dsq32, spec_sq, s_in.H, s_in.W)
         y0c, noise_dev, clip, X0, s0, (H, W) = tape["in"]
         dz0 = ops.act_bwd(s0, ds, ops.ACT_LEAKY, out=ds)
         c0 = self._conv0

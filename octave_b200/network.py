@@ -82,9 +82,11 @@ def bn_bwd(ctx, dy: Act, mask: Optional[Act], grads: Grads, out: Optional[Act] =
 
 
 def conv_bwd(conv: nn.Module, x: Act, dz: Act, grads: Grads, need_dx: bool = True, dx_out: Optional[Act] = None,
-             accumulate: bool = False) -> Optional[Act]:
+             accumulate: bool = False, zero_bias_grad: bool = False) -> Optional[Act]:
+    """zero_bias_grad: the conv feeds a training-mode BatchNorm, whose input gradient sums to zero over every channel,
+    so the bias gradient is identically zero (the reference computes rounding noise there) and its reduction is skipped."""
     spec = _spec(conv)
-    dw, db = ops.conv_wgrad(x, dz, spec)
+    dw, db = ops.conv_wgrad(x, dz, spec, zero_bias_grad)
     _acc(grads, conv.weight, dw)
     _acc(grads, conv.bias, db)
     if not need_dx:
@@ -143,7 +145,7 @@ class SplAtConv2d(nn.Module):
         _acc(grads, self.fc1.weight, dw1); _acc(grads, self.fc1.bias, db1)
         dU = ops.splat_bwd_du(dout, mask, att, dgap, 1.0)
         dz = bn_bwd(bn0ctx, dU, U, grads, out=dU)
-        return conv_bwd(self.conv, x, dz, grads, need_dx)
+        return conv_bwd(self.conv, x, dz, grads, need_dx, zero_bias_grad=tr)
 
 
 class Bottleneck(nn.Module):

@@ -115,7 +115,7 @@ _sigs = {
     "octave_pool_fwd": [C.POINTER(PoolDesc), _A, _A, _vp, _vp],
     "octave_pool_bwd": [C.POINTER(PoolDesc), _A, _vp, _A, _vp],
     "octave_head_fwd": [_A, _vp, _vp, C.c_int32, C.c_int32, _vp, _A, _vp],
-    "octave_head_bwd": [_A, _vp, _vp, C.c_int32, C.c_int32, _vp, _A, _A, _vp, _vp],
+    "octave_head_bwd": [_A, _vp, _vp, C.c_int32, C.c_int32, _vp, _A, _A, _vp, _vp, _vp, _vp],
     "octave_head_wgrad": [_A, _vp, C.c_int32, _vp, _vp, _vp],
     "octave_nchw_to_nhwc": [_vp, C.c_int32, _A, _vp],
     "octave_nhwc_to_nchw": [_A, _vp, C.c_int32, _vp],
@@ -314,12 +314,12 @@ def head_bwd(x: Act, w: torch.Tensor, b: torch.Tensor, mode: int, dout: Optional
     """-> dx Act, dw [K,C], db [K]"""
     K = w.shape[0]
     dx = x.like()
-    dlogits = torch.empty((x.B, K, x.H, x.W), dtype=torch.float32, device=x.device)
-    _chk("octave_head_bwd", lib.octave_head_bwd(_ref(x), w.data_ptr(), b.data_ptr(), K, mode, _p(dout), _ref(dgated), _ref(dx),
-                                                dlogits.data_ptr(), stream_ptr()))
     dw = torch.empty((K, x.C), dtype=torch.float32, device=x.device)
     db = torch.empty(K, dtype=torch.float32, device=x.device)
-    _chk("octave_head_wgrad", lib.octave_head_wgrad(_ref(x), dlogits.data_ptr(), K, dw.data_ptr(), db.data_ptr(), stream_ptr()))
+    # K == 2: one fused pass (dx + parameter gradients); otherwise the generic kernel pair through a dlogits scratch
+    dlogits = None if K == 2 and x.C >= 32 else torch.empty((x.B, K, x.H, x.W), dtype=torch.float32, device=x.device)
+    _chk("octave_head_bwd", lib.octave_head_bwd(_ref(x), w.data_ptr(), b.data_ptr(), K, mode, _p(dout), _ref(dgated), _ref(dx),
+                                                _p(dlogits), dw.data_ptr(), db.data_ptr(), stream_ptr()))
     return dx, dw, db
 
 
@@ -493,10 +493,15 @@ def conv_dgrad(dy: Act, spec: ConvSpec, H: int, W: int, out: Optional[Act] = Non
     return out
 
 
-def conv_wgrad(x: Act, dy: Act, spec: ConvSpec):
+def conv_wgrad(x: Act, dy: Act, spec: ConvSpec, zero_bias_grad: bool = False):
     """-> (dW in the torch parameter layout fp32, dbias or None)"""
     dw = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
     db = None
+    if zero_bias_grad and spec.bias is not None and spec.tc_ok(x.dtype):
+        d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.dense_groups, spec.k, 1, spec.k // 2, x, dy, dy.H, dy.W,
+                       real_groups=spec.groups)
+        _chk("octave_conv_tc_wgrad", lib.octave_conv_tc_wgrad(C.byref(d), x.buf.data_ptr(), dy.buf.data_ptr(), dw.data_ptr(), stream_ptr()))
+        return dw, torch.zeros(spec.cout, dtype=torch.float32, device=x.device)
     if spec.tc_ok(x.dtype):
         d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.dense_groups, spec.k, 1, spec.k // 2, x, dy, dy.H, dy.W,
                        real_groups=spec.groups)
