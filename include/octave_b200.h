@@ -127,6 +127,14 @@ int octave_conv_tc_supported(const OctaveConvDesc* d);
  * statistics of the BatchNorm that follows (resnest.py:25,86,182,224,338), fused into the conv epilogue. */
 int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
                        double* stats, void* stream);
+/* Narrow-layer variant of octave_conv_tc_fwd (3x3 s1 p1, Cin/groups and Cout/groups in {32, 64}, all taps of all groups
+ * <= 72 KB): weights resident in shared memory, one halo TMA box per output tile, tap shifts as descriptor offsets.
+ * octave_conv_tc_fwd forwards to it when octave_conv_halo_supported(); same arguments and semantics.
+ * octave_conv_halo_config(enabled, base_off_mode) overrides the OCTAVE_HALO / OCTAVE_HALO_BASEOFF environment switches. */
+int octave_conv_halo_supported(const OctaveConvDesc* d);
+int octave_conv_halo_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
+                         double* stats, void* stream);
+void octave_conv_halo_config(int32_t enabled, int32_t base_off_mode);
 /* dw: fp32 gradient in the torch parameter layout ([Cout][Cin/real_groups][k][k]; ConvT: [Cin][Cout][2][2]),
  * overwritten unless `accumulate`.  x = forward input view, dy = output-gradient view (x_* / y_* of the descriptor;
  * for ConvT dy is the space-to-depth view with 4*cout channels). */

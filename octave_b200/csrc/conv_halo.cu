@@ -1,0 +1,422 @@
+// K1b — 3x3 stride-1 convolution for NARROW layers (Cin/group in {32, 64}, Cout/group in {32, 64}) on tcgen05.
+//
+// The generic implicit-GEMM kernel (conv_tc.cu) fetches one shifted A patch and one weight tile per filter tap: for a
+// narrow layer that is 18 small TMA requests and 9x the input bytes over the L2 fabric per output tile, and ncu shows
+// the MMA lane starving on the full barrier while HBM idles (profiles/conv_3x3_narrow_r01.txt).  These layers are
+// HBM-bound (decoder_0/1, stem, critic: 400^2 and 200^2 maps), so this kernel moves every byte once:
+//
+//  * ALL filter taps of every group stay resident in shared memory for the life of the persistent CTA
+//    (9 * Cout_g * Cin_g * 2 B per group, <= 72 KB) — one TMA burst at start-up.
+//  * One TMA box per output tile brings the (TH+2) x TWp input patch INCLUDING its halo (hardware zero-fill outside
+//    the image = the conv padding).  The GEMM M index runs over the flattened patch, m = oh * TWp + ow, so the A operand
+//    of tap (dh, dw) is the very same shared-memory tile starting (dh * TWp + dw) rows further down: the tap shift is a
+//    byte offset in the UMMA shared-memory descriptor (the swizzle is a function of the absolute address, which TMA and
+//    UMMA share).  Rows with ow >= TW (two per patch row) are computed but not stored.
+//  * 9 * Cin_g/16 MMAs (128 x Cout_g x 16) per tile into one of two TMEM accumulators; the epilogue (bias / activation,
+//    bf16, fused BatchNorm statistics, coalesced 16-byte stores, optional accumulate) overlaps the next tile.
+//
+// Serves forward and data-gradient (the latter through the flipped/transposed weight pack, like conv_tc.cu) of
+//   ResNet deep stem, ResNestDecoder / SplAtConv2d at the two finest levels   /root/reference/architectures/extra/resnest.py:18-138,326-334
+//   DiscriminatorBlock 4x4 s2 convs in space-to-depth form                    /root/reference/architectures/discriminator/blocks.py:46-50,91-109
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/octave_b200.h"
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kHaloThreads = 10 * 32;  // warp 0 TMA producer, warp 1 MMA, warps 2..9 epilogue
+
+struct HaloParams {
+  int TWp, TW, TH;     // patch row pitch (TW + 2), stored patch width / height
+  int tiles_w, tiles_h;
+  int groups;
+  int H, W;            // output pixel grid
+  void* out;
+  long long ldc;
+  int c_off, Hout, Wout;
+  const float* bias;
+  int act, accumulate;
+  long long total_tiles;   // B * tiles_h * tiles_w * groups (group fastest)
+  double* stats;
+  int stats_stride;
+  int a_rows;              // rows of one halo box = (TH + 2) * TWp
+  int a_stage_bytes;       // shared-memory bytes reserved per stage (1024-aligned, >= (a_rows + 8) rows)
+  int stages;
+  int base_off_mode;       // 1: also fill the descriptor's matrix-base-offset field with (addr >> 7) & 7
+};
+
+__device__ __forceinline__ float halo_act(float v, int act) {
+  switch (act) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return v > 0.f ? v : 0.2f * v;
+    case 3: return 1.f / (1.f + __expf(-v));
+    case 4: return tanhf(v);
+    default: return v;
+  }
+}
+
+template <int BN, int CIN>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                       const __grid_constant__ CUtensorMap tmW,
+                                                                       const HaloParams p) {
+  constexpr int ROWB = CIN * 2;          // bytes per pixel row of the A tile = swizzle span
+  constexpr int TAPB = BN * ROWB;        // bytes of one tap's weight tile
+  constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  constexpr int COLS_W = BN / 2;         // columns handled by one epilogue warp
+  constexpr int NCHUNK_W = COLS_W / 16;
+  constexpr int PITCH = COLS_W * 2 + 16;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ __align__(8) uint64_t w_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
+  const uint32_t w_smem = smem_base;
+  const uint32_t w_bytes = (uint32_t)p.groups * 9u * TAPB;
+  const uint32_t a_smem = smem_base + ((w_bytes + 1023u) & ~1023u);
+  uint8_t* const stage_gen = smem_gen + ((w_bytes + 1023u) & ~1023u) + (size_t)p.stages * p.a_stage_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tc::smem_u32(&acc_full[b]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty[b]), 8);
+    }
+    tc::mbar_init(tc::smem_u32(&w_bar), 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async();
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_slot));
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ---- TMA producer: warp-uniform loop, one elected lane issues
+    const bool leader = tc::elect_one();
+    const uint32_t wb = tc::smem_u32(&w_bar);
+    if (leader) {
+      // resident weights: every tap of every group, once
+      tc::mbar_arrive_expect_tx(wb, w_bytes);
+      for (int g = 0; g < p.groups; ++g)
+        for (int tap = 0; tap < 9; ++tap) tc::tma_load_3d(w_smem + (g * 9 + tap) * TAPB, &tmW, wb, 0, g * BN, tap);
+    }
+    const uint32_t tx_bytes = (uint32_t)p.a_rows * ROWB;
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int tt = (int)t;
+      const int g = tt % p.groups;
+      const int m_tile = tt / p.groups;
+      const int img = m_tile / tiles_per_img;
+      const int trem = m_tile - img * tiles_per_img;
+      const int th_i = trem / p.tiles_w;
+      const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+      tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+      const uint32_t fb = tc::smem_u32(&full_bar[s]);
+      if (leader) {
+        tc::mbar_arrive_expect_tx(fb, tx_bytes);
+        tc::tma_load_4d(a_smem + s * p.a_stage_bytes, &tmA, fb, g * CIN, w0 - 1, h0 - 1, img);
+      }
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: warp-uniform loop; descriptors = per-tile base + per-tap constant (only the 14-bit address field moves)
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 0, 0);
+    uint32_t tap_off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((uint32_t)((tap / 3) * p.TWp + (tap % 3)) * ROWB) >> 4;
+    tc::mbar_wait(tc::smem_u32(&w_bar), 0);
+    tc::fence_after_sync();
+    int s = 0;
+    uint32_t ph = 0, it = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int g = (int)t % p.groups;
+      const uint32_t buf = it & 1u;
+      tc::mbar_wait(tc::smem_u32(&acc_empty[buf]), ((it >> 1) & 1u) ^ 1u);
+      tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+      const uint64_t da0 = tc::umma_smem_desc(a_smem + s * p.a_stage_bytes, ROWB, 16);
+      const uint64_t db0 = tc::umma_smem_desc(w_smem + g * 9 * TAPB, ROWB, 16);
+      if (leader) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+          for (int k = 0; k < CIN / 16; ++k)
+            tc::umma_bf16(d_tmem, da0 + tap_off[tap] + k * 2, db0 + (uint32_t)((tap * TAPB) >> 4) + k * 2, idesc, (tap | k) != 0);
+        }
+        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+        tc::umma_commit(tc::smem_u32(&acc_full[buf]));
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ---- 8 epilogue warps: TMEM lane quarter q <-> GEMM rows [32q, 32q+32); column half hsel
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int th = r / p.TWp, tw = r - th * p.TWp;
+    uint8_t* const stage = stage_gen + (warp - 2) * (32 * PITCH);
+    float ssum = 0.f, ssq = 0.f;   // COLS_W <= 32: one statistics column per lane
+    int stat_col0 = -1;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const int tt = (int)t;
+      const int g = tt % p.groups;
+      const int m_tile = tt / p.groups;
+      const int img = m_tile / tiles_per_img;
+      const int trem = m_tile - img * tiles_per_img;
+      const int th_i = trem / p.tiles_w;
+      const int h = th_i * p.TH + th, w = (trem - th_i * p.tiles_w) * p.TW + tw;
+      const bool valid = (tw < p.TW) && (th < p.TH) && (h < p.H) && (w < p.W) && (h < p.Hout) && (w < p.Wout);
+      const int cbase = g * BN + hsel * COLS_W;
+      const long long row_off = valid ? (((long long)img * p.Hout + h) * p.Wout + w) * p.ldc + p.c_off + cbase : -1;
+      stat_col0 = cbase;
+      tc::mbar_wait(tc::smem_u32(&acc_full[buf]), (it >> 1) & 1u);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < NCHUNK_W; ++c) {
+        uint32_t v[16];
+        tc::tmem_ld16(taddr + c * 16, v);
+        tc::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          f[i] = __uint_as_float(v[i]);
+          if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
+        }
+        if (p.act) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = halo_act(f[i], p.act);
+        }
+        if (!valid) {   // rows that are not stored stage zeros: they must not enter the statistics (and may be NaN junk)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = 0.f;
+        }
+        uint4 u0, u1;
+        u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
+        u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
+        u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
+        u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
+        *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
+        *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+      if (p.stats && lane < COLS_W) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const float val = __bfloat162float(*reinterpret_cast<const bf16*>(stage + rr * PITCH + lane * 2));
+          s1 += val;
+          s2 += val * val;
+        }
+        ssum += s1;
+        ssq += s2;
+      }
+      constexpr int LPR = (COLS_W * 2) / 16;   // lanes per row (16 B each): 2 or 4
+      constexpr int RPI = 32 / LPR;
+      const int sub = lane % LPR, rsel = lane / LPR;
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += RPI) {
+        const int row = r0 + rsel;
+        const long long off = __shfl_sync(0xffffffffu, row_off, row);
+        if (off >= 0) {
+          uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off + sub * 8;
+          if (p.accumulate) {
+            const uint4 e = *reinterpret_cast<const uint4*>(o);
+            float x0, x1, y0, y1;
+            bf16x2_unpack(val.x, x0, x1); bf16x2_unpack(e.x, y0, y1); val.x = bf16x2_pack(x0 + y0, x1 + y1);
+            bf16x2_unpack(val.y, x0, x1); bf16x2_unpack(e.y, y0, y1); val.y = bf16x2_pack(x0 + y0, x1 + y1);
+            bf16x2_unpack(val.z, x0, x1); bf16x2_unpack(e.z, y0, y1); val.z = bf16x2_pack(x0 + y0, x1 + y1);
+            bf16x2_unpack(val.w, x0, x1); bf16x2_unpack(e.w, y0, y1); val.w = bf16x2_pack(x0 + y0, x1 + y1);
+          }
+          *reinterpret_cast<uint4*>(o) = val;
+        }
+      }
+      __syncwarp();
+    }
+    if (p.stats && stat_col0 >= 0 && lane < COLS_W) {
+      atomicAdd(p.stats + stat_col0 + lane, (double)ssum);
+      atomicAdd(p.stats + p.stats_stride + stat_col0 + lane, (double)ssq);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 halo_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+CUtensorMapSwizzle swz_of(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+template <int BN, int CIN>
+int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, HaloParams& p, int grid, cudaStream_t s) {
+  constexpr int ROWB = CIN * 2;
+  constexpr int PITCH = (BN / 2) * 2 + 16;
+  const int w_bytes = ((p.groups * 9 * BN * ROWB) + 1023) & ~1023;
+  p.a_stage_bytes = (((p.a_rows + 8) * ROWB) + 1023) & ~1023;
+  const int fixed = w_bytes + 8 * 32 * PITCH + 1024;
+  int stages = (225 * 1024 - fixed) / p.a_stage_bytes;   // static barriers + alignment slack stay below 227 KB
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return OCT_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const int smem = fixed + stages * p.a_stage_bytes;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t ea = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (ea != cudaSuccess) {
+      if (getenv("OCTAVE_DEBUG")) fprintf(stderr, "[octave] halo: smem attribute: %s\n", cudaGetErrorString(ea));
+      return OCT_ERR_LAUNCH;
+    }
+    attr_smem = 226 * 1024;
+  }
+  conv3x3_halo_kernel<BN, CIN><<<grid, kHaloThreads, smem, s>>>(tmA, tmW, p);
+  if (getenv("OCTAVE_DEBUG")) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) fprintf(stderr, "[octave] halo launch<%d,%d> grid %d smem %d stages %d: %s\n", BN, CIN, grid, smem, stages, cudaGetErrorString(e));
+  }
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+}  // namespace
+
+static int g_halo_enabled = -1, g_halo_baseoff = -1;
+
+extern "C" void octave_conv_halo_config(int32_t enabled, int32_t base_off_mode) {
+  g_halo_enabled = enabled ? 1 : 0;
+  g_halo_baseoff = base_off_mode;
+}
+
+// 1 when the narrow-layer kernel takes this descriptor (see the header comment for the shape class)
+extern "C" int octave_conv_halo_supported(const OctaveConvDesc* d) {
+  if (g_halo_enabled < 0) {
+    const char* e = getenv("OCTAVE_HALO");
+    g_halo_enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!g_halo_enabled || !d) return 0;
+  if (d->ksize != 3 || d->mode != OCT_CONV_MODE_CONV || d->out_s2d_qs > 0) return 0;
+  if (d->groups <= 0 || d->cin % d->groups || d->cout % d->groups) return 0;
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  if (cin_g != 32 && cin_g != 64) return 0;
+  if (cout_g != 32 && cout_g != 64) return 0;
+  if ((long long)d->groups * 9 * cout_g * cin_g * 2 > 72 * 1024) return 0;
+  if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return 0;
+  if (d->out_dtype == OCT_DTYPE_F32) return 0;
+  if (d->Hout > d->H || d->Wout > d->W) return 0;
+  return 1;
+}
+
+extern "C" int octave_conv_halo_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
+                                    double* stats, void* stream) {
+  if (!octave_conv_halo_supported(d)) return OCT_ERR_UNSUPPORTED;
+  if (!x || !wpack || !y) return OCT_ERR_INVALID;
+  auto enc = halo_encode();
+  if (!enc) return OCT_ERR_LAUNCH;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  HaloParams p{};
+  // patch pitch: the candidate that wastes the fewest of the 128 GEMM rows (ties: the smaller halo overhead)
+  double best = -1.0;
+  const int cand[4] = {32, 64, 16, 128};
+  for (int i = 0; i < 4; ++i) {
+    const int twp = cand[i], tw = twp - 2, th = (128 - tw) / twp + 1;
+    const long long tiles = (long long)((d->Wout + tw - 1) / tw) * ((d->Hout + th - 1) / th);
+    const double eff = (double)d->Hout * d->Wout / ((double)tiles * 128.0);
+    if (eff > best + 0.02) { best = eff; p.TWp = twp; p.TW = tw; p.TH = th; }
+  }
+  p.tiles_w = (d->Wout + p.TW - 1) / p.TW;
+  p.tiles_h = (d->Hout + p.TH - 1) / p.TH;
+  p.groups = d->groups;
+  p.H = d->Hout; p.W = d->Wout;
+  p.out = y; p.ldc = d->y_ld; p.c_off = d->y_coff; p.Hout = d->Hout; p.Wout = d->Wout;
+  p.bias = bias; p.act = d->relu; p.accumulate = d->accumulate;
+  p.total_tiles = (long long)p.tiles_w * p.tiles_h * d->B * d->groups;
+  p.stats = stats; p.stats_stride = d->cout;
+  p.a_rows = (p.TH + 2) * p.TWp;
+  if (g_halo_baseoff < 0) {
+    const char* e = getenv("OCTAVE_HALO_BASEOFF");
+    g_halo_baseoff = e ? atoi(e) : 0;
+  }
+  p.base_off_mode = g_halo_baseoff;
+  const int rowb = cin_g * 2;
+  CUtensorMap tmA, tmW;
+  {
+    const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)d->x_ld * 2 * d->W, (cuuint64_t)d->x_ld * 2 * d->W * d->H};
+    cuuint32_t box[4] = {(cuuint32_t)cin_g, (cuuint32_t)p.TWp, (cuuint32_t)(p.TH + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(xb), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz_of(rowb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      if (getenv("OCTAVE_DEBUG")) fprintf(stderr, "[octave] halo: A tensor map rejected (box %d x %d x %d)\n", cin_g, p.TWp, p.TH + 2);
+      return OCT_ERR_LAUNCH;
+    }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)cin_g, (cuuint64_t)d->cout, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)cin_g * 2, (cuuint64_t)cin_g * 2 * d->cout};
+    cuuint32_t box[3] = {(cuuint32_t)cin_g, (cuuint32_t)cout_g, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz_of(rowb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      if (getenv("OCTAVE_DEBUG")) fprintf(stderr, "[octave] halo: W tensor map rejected\n");
+      return OCT_ERR_LAUNCH;
+    }
+  }
+  int sms = octave_sm_count();
+  if (sms <= 0) sms = 148;
+  long long grid = sms - sms % d->groups;   // a CTA keeps one group: its statistics columns never change
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  if (cin_g == 64) {
+    if (cout_g == 64) return launch_halo<64, 64>(tmA, tmW, p, (int)grid, s);
+    return launch_halo<32, 64>(tmA, tmW, p, (int)grid, s);
+  }
+  if (cout_g == 64) return launch_halo<64, 32>(tmA, tmW, p, (int)grid, s);
+  return launch_halo<32, 32>(tmA, tmW, p, (int)grid, s);
+}

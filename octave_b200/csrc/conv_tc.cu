@@ -123,65 +123,71 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
   const int ng = p.n_tiles * p.groups;
 
   if (warp == 0 || warp >= 10) {
-    // kProducers TMA producer warps (one lane each): measured, one thread sustains only ~1 UTMALDG per ~350 cycles, so a
-    // single producer starves narrow layers (ncu: MMA thread spinning on the full barrier, profiles/).  Even roles load
-    // the A tile of their k-iterations and arm the barrier with the stage's byte count, odd roles load the B tile.
-    if (lane == 0) {
-      const int role = warp == 0 ? 0 : warp - 9;       // 0 .. kProducers-1
-      const bool is_a = (role & 1) == 0;                // even roles load A (and arm the barrier), odd roles load B
-      const uint32_t it_sel = (uint32_t)(role >> 1);    // this producer serves k-iterations it % (kProducers/2) == it_sel
-      const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * SWZ + B_BYTES);
-      uint32_t it = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int n_tile = (int)(t % p.n_tiles);
-        const int g = (int)((t / p.n_tiles) % p.groups);
-        const int m_tile = (int)(t / ng);
-        const int img = m_tile / tiles_per_img;
-        const int trem = m_tile - img * tiles_per_img;
-        const int th_i = trem / p.tiles_w;
-        const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
-        const int n0 = n_tile * BN;
-        for (int kk = 0; kk < total_k; ++kk, ++it) {
-          if ((it % (kProducers / 2)) != it_sel) continue;
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
-          const uint32_t fb = tc::smem_u32(&full_bar[s]);
-          const int tap = kk / p.kchunks, kc = kk - tap * p.kchunks;
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          if (is_a) {
-            tc::mbar_arrive_expect_tx(fb, tx_bytes);
-            tc::tma_load_4d(sa, &tmA, fb, g * p.cin_g + kc * BK, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], img);
-          } else {
-            tc::tma_load_3d(sa + A_BYTES, &tmB, fb, kc * BK, g * p.cout_g + n0, tap);
+    // kProducers TMA producer warps.  Even roles load the A tile of their k-iterations and arm the barrier with the
+    // stage's byte count, odd roles load the B tile.  The loops are warp-uniform (every lane walks the tiles and waits on
+    // the barriers) and one elected lane issues, so coordinates and addresses stay in uniform registers.
+    const bool leader = tc::elect_one();
+    const int role = warp == 0 ? 0 : warp - 9;       // 0 .. kProducers-1
+    const bool is_a = (role & 1) == 0;                // even roles load A (and arm the barrier), odd roles load B
+    const uint32_t it_sel = (uint32_t)(role >> 1);    // this producer serves k-iterations it % (kProducers/2) == it_sel
+    const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * SWZ + B_BYTES);
+    uint32_t it = 0, ph = 0;
+    int s = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int tt = (int)t;
+      const int n_tile = tt % p.n_tiles;
+      const int g = (tt / p.n_tiles) % p.groups;
+      const int m_tile = tt / ng;
+      const int img = m_tile / tiles_per_img;
+      const int trem = m_tile - img * tiles_per_img;
+      const int th_i = trem / p.tiles_w;
+      const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+      const int n0 = n_tile * BN;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap];
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          if ((it % (kProducers / 2)) == it_sel) {
+            tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+            const uint32_t fb = tc::smem_u32(&full_bar[s]);
+            const uint32_t sa = smem_base + s * STAGE_BYTES;
+            if (leader) {
+              if (is_a) {
+                tc::mbar_arrive_expect_tx(fb, tx_bytes);
+                tc::tma_load_4d(sa, &tmA, fb, g * p.cin_g + kc * BK, cw, ch, img);
+              } else {
+                tc::tma_load_3d(sa + A_BYTES, &tmB, fb, kc * BK, g * p.cout_g + n0, tap);
+              }
+            }
           }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 0, 0);
-      uint32_t it = 0, li = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
-        const uint32_t buf = li & 1u;
-        tc::mbar_wait(tc::smem_u32(&acc_empty[buf]), ((li >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+    // MMA issuer: warp-uniform loop, one elected lane issues (see tc::elect_one)
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 0, 0);
+    uint32_t li = 0, ph = 0;
+    int s = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
+      const uint32_t buf = li & 1u;
+      tc::mbar_wait(tc::smem_u32(&acc_empty[buf]), ((li >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+      for (int kk = 0; kk < total_k; ++kk) {
+        tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
-        for (int kk = 0; kk < total_k; ++kk, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
-          tc::fence_after_sync();
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          const uint64_t da = tc::umma_smem_desc(sa, SWZ, 16);
-          const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, SWZ, 16);
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint64_t da = tc::umma_smem_desc(sa, SWZ, 16);
+        const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, SWZ, 16);
+        if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc::umma_bf16(d_tmem, tc::umma_desc_advance(da, k * 32), tc::umma_desc_advance(db, k * 32), idesc, (kk | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(d_tmem, da + k * 2, db + k * 2, idesc, (kk | k) != 0);
           tc::umma_commit(tc::smem_u32(&empty_bar[s]));
         }
-        tc::umma_commit(tc::smem_u32(&acc_full[buf]));
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
+      if (leader) tc::umma_commit(tc::smem_u32(&acc_full[buf]));
     }
   } else {
     // ---- 8 epilogue warps: TMEM lane quarter q <-> GEMM rows [32q, 32q+32); column half hsel
@@ -198,9 +204,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
     uint32_t li = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
       const uint32_t buf = li & 1u;
-      const int n_tile = (int)(t % p.n_tiles);
-      const int g = (int)((t / p.n_tiles) % p.groups);
-      const int m_tile = (int)(t / ng);
+      const int tt = (int)t;
+      const int n_tile = tt % p.n_tiles;
+      const int g = (tt / p.n_tiles) % p.groups;
+      const int m_tile = tt / ng;
       const int img = m_tile / tiles_per_img;
       const int trem = m_tile - img * tiles_per_img;
       const int th_i = trem / p.tiles_w;
@@ -422,26 +429,26 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
   const int b_boxes = min(NCH_B, (p.cin_g - ci0 + CWB - 1) / CWB);
 
   if (warp == 0 || warp >= 6) {
-    // kWgProducers TMA producer warps (one lane each); the boxes of a pixel tile are dealt round-robin, producer 0 also
-    // arms the barrier with the byte count (a single issuing thread sustains only ~1 UTMALDG per ~350 cycles)
-    if (lane == 0) {
-      const int role = warp == 0 ? 0 : warp - 5;
-      const uint32_t tx_bytes = (uint32_t)(rows * (PITCH_A * a_boxes + PITCH_B * b_boxes));
-      const int dh = p.tap_dhs[tap], dw = p.tap_dws[tap];
-      const int nbox = a_boxes + b_boxes;
-      if (role < nbox || role == 0) {
-        for (int it = 0; it < n_iter; ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
-          const uint32_t fb = tc::smem_u32(&full_bar[s]);
+    // kWgProducers TMA producer warps (warp-uniform loops, one elected lane issues); the boxes of a pixel tile are dealt
+    // round-robin, producer 0 also arms the barrier with the byte count
+    const bool leader = tc::elect_one();
+    const int role = warp == 0 ? 0 : warp - 5;
+    const uint32_t tx_bytes = (uint32_t)(rows * (PITCH_A * a_boxes + PITCH_B * b_boxes));
+    const int dh = p.tap_dhs[tap], dw = p.tap_dws[tap];
+    const int nbox = a_boxes + b_boxes;
+    if (role < nbox || role == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int img = t_begin / tiles_per_img;
+      int trem = t_begin - img * tiles_per_img;
+      for (int it = 0; it < n_iter; ++it) {
+        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t fb = tc::smem_u32(&full_bar[s]);
+        const int th_i = trem / p.tiles_w;
+        const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        if (leader) {
           if (role == 0) tc::mbar_arrive_expect_tx(fb, tx_bytes);
-          const int t = t_begin + it;
-          const int img = t / tiles_per_img;
-          const int trem = t - img * tiles_per_img;
-          const int th_i = trem / p.tiles_w;
-          const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
           for (int j = role; j < nbox; j += kWgProducers) {
             if (j < a_boxes)
               tc::tma_load_4d(sa + j * CHUNK_A, &tmDY, fb, g * p.cout_g + co0 + CWA * j, w0, h0, img);
@@ -450,26 +457,29 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
                               h0 + dh, img);
           }
         }
+        if (++trem == tiles_per_img) { trem = 0; ++img; }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 1, 1);
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
-        tc::fence_after_sync();
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint64_t da = tc::umma_smem_desc(sa, PITCH_A, CHUNK_A);
-        const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, PITCH_B, CHUNK_B);
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
+      tc::fence_after_sync();
+      const uint32_t sa = smem_base + s * STAGE_BYTES;
+      const uint64_t da = tc::umma_smem_desc(sa, PITCH_A, CHUNK_A);
+      const uint64_t db = tc::umma_smem_desc(sa + A_BYTES, PITCH_B, CHUNK_B);
+      if (leader) {
         for (int k = 0; k < ksteps; ++k)
-          tc::umma_bf16(tmem_base, tc::umma_desc_advance(da, k * 16 * PITCH_A), tc::umma_desc_advance(db, k * 16 * PITCH_B),
-                        idesc, (it | k) != 0);
+          tc::umma_bf16(tmem_base, da + (uint32_t)(k * PITCH_A), db + (uint32_t)(k * PITCH_B), idesc, (it | k) != 0);
         tc::umma_commit(tc::smem_u32(&empty_bar[s]));
       }
-      tc::umma_commit(tc::smem_u32(&acc_bar));
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
+    if (leader) tc::umma_commit(tc::smem_u32(&acc_bar));
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;  // output channel within the tile
@@ -635,6 +645,7 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
   if (rc != OCT_OK) return rc;
   if (!octave_conv_tc_supported(d)) return OCT_ERR_UNSUPPORTED;
   if (!x || !wpack || !y) return OCT_ERR_INVALID;
+  if (octave_conv_halo_supported(d)) return octave_conv_halo_fwd(d, x, wpack, bias, y, stats, stream);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
   const bool convt = d->mode == OCT_CONV_MODE_CONVT;

@@ -45,6 +45,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
+// One lane of a fully converged warp (all 32 lanes must execute this).  Role loops run warp-uniform — every lane walks
+// the tiles and waits on the barriers — and only the issuing instruction (TMA / MMA / commit) sits under this predicate:
+// descriptors and coordinates then live in uniform registers.  Issuing from inside an `if (lane == 0)` region instead
+// makes ptxas move every operand through R2UR + a BRA.U.ANY loop (~15 SASS instructions per tcgen05.mma, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA loads (tile mode, mbarrier completion)
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
