@@ -142,43 +142,139 @@ struct CellLoad {
 };
 
 __device__ __forceinline__ void softmax2(float& z0, float& z1) {
-  // softmax over dim=1 with C=2, same max-subtracted form torch uses
-  float m = fmaxf(z0, z1);
-  float e0 = __expf(z0 - m), e1 = __expf(z1 - m);
-  float inv = 1.f / (e0 + e1);
-  z0 = e0 * inv;
-  z1 = e1 * inv;
+  // softmax over dim=1 with C=2 in the max-subtracted form torch uses: the larger logit maps to exp(0) = 1, so one
+  // exponential and one reciprocal per pixel suffice (the kernel is MUFU-bound next to HBM-bound otherwise)
+  const float d = z1 - z0;
+  const float e = __expf(-fabsf(d));
+  const float inv = __fdividef(1.f, 1.f + e);
+  const float big = inv, small = e * inv;
+  z0 = d > 0.f ? small : big;
+  z1 = d > 0.f ? big : small;
 }
 
+#define FLG(a) (FL >= 0 ? FL : (a).flags)
+
+// Raw (storage-form) holders so that every global load of a cell is issued before the first dependent instruction:
+// a warp then has ~10 independent requests in flight instead of paying one DRAM round trip per map.
+template <typename T, int N> struct RawN;
+template <> struct RawN<bf16, 4> {
+  uint2 r;
+  __device__ __forceinline__ void ld(const bf16* p) { r = __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ __forceinline__ void get(float* v) const { bf16x2_unpack(r.x, v[0], v[1]); bf16x2_unpack(r.y, v[2], v[3]); }
+};
+template <> struct RawN<bf16, 2> {
+  uint32_t r;
+  __device__ __forceinline__ void ld(const bf16* p) { r = __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  __device__ __forceinline__ void get(float* v) const { bf16x2_unpack(r, v[0], v[1]); }
+};
+template <> struct RawN<bf16, 1> {
+  unsigned short r;
+  __device__ __forceinline__ void ld(const bf16* p) { r = __ldg(reinterpret_cast<const unsigned short*>(p)); }
+  __device__ __forceinline__ void get(float* v) const { v[0] = __uint_as_float((uint32_t)r << 16); }
+};
+template <> struct RawN<float, 4> {
+  float4 r;
+  __device__ __forceinline__ void ld(const float* p) { r = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void get(float* v) const { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+};
+template <> struct RawN<float, 2> {
+  float2 r;
+  __device__ __forceinline__ void ld(const float* p) { r = __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ __forceinline__ void get(float* v) const { v[0] = r.x; v[1] = r.y; }
+};
+template <> struct RawN<float, 1> {
+  float r;
+  __device__ __forceinline__ void ld(const float* p) { r = __ldg(p); }
+  __device__ __forceinline__ void get(float* v) const { v[0] = r; }
+};
+
 template <typename T>
-__device__ __forceinline__ void load_cell(const LossArgs& a, int b, int y, int x0, CellLoad<T>& c) {
+struct CellRaw {
+  Raw8<T> p0, p1, t0, t1, b0, b1;
+  RawN<T, 4> q1[2];
+  RawN<T, 2> q2[2];
+  RawN<T, 1> q3[2], q4[2];
+};
+
+// Touch the six full-resolution vectors of the warp's NEXT cell: by the time the grid-stride loop reaches it the lines
+// sit in L2 and the loads cost an L2 hit instead of a DRAM round trip (no registers are held across the iteration).
+template <typename T, int FL>
+__device__ __forceinline__ void prefetch_cell(const LossArgs& a, int b, int y, int x0) {
   const size_t plane = (size_t)a.H * a.W;
   const size_t off = (size_t)b * 2 * plane + (size_t)y * a.W + x0;
-  if (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+  if (FLG(a) & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
     const T* yh = reinterpret_cast<const T*>(a.yhat);
     const T* ys = reinterpret_cast<const T*>(a.ys);
-    VecIO<T, 8>::ld(yh + off, c.p0);
-    VecIO<T, 8>::ld(yh + off + plane, c.p1);
-    VecIO<T, 8>::ld(ys + off, c.t0);
-    VecIO<T, 8>::ld(ys + off + plane, c.t1);
-    if (a.flags & OCT_LOSS_FROM_LOGITS) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) softmax2(c.p0[j], c.p1[j]);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(yh + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(yh + off + plane));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ys + off + plane));
+  }
+  if (FLG(a) & OCT_LOSS_KLD) {
+    const T* a0 = reinterpret_cast<const T*>(a.att[0]);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + off + plane));
+  }
+}
+
+// phase 1: nothing but loads (uniform flag tests only)
+template <typename T, int FL, bool PYR>
+__device__ __forceinline__ void issue_cell(const LossArgs& a, int b, int y, int x0, CellRaw<T>& r) {
+  const size_t plane = (size_t)a.H * a.W;
+  const size_t off = (size_t)b * 2 * plane + (size_t)y * a.W + x0;
+  if (FLG(a) & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+    const T* yh = reinterpret_cast<const T*>(a.yhat);
+    const T* ys = reinterpret_cast<const T*>(a.ys);
+    r.p0.ld(yh + off);
+    r.p1.ld(yh + off + plane);
+    r.t0.ld(ys + off);
+    r.t1.ld(ys + off + plane);
+  }
+  if (FLG(a) & OCT_LOSS_KLD) {
+    const T* a0 = reinterpret_cast<const T*>(a.att[0]);
+    r.b0.ld(a0 + off);
+    r.b1.ld(a0 + off + plane);
+    if (PYR || ((PYR || a.n_att > 1) && a.aw8[0] != 0.f)) {
+      const size_t pl = plane >> 2;
+      const T* q = reinterpret_cast<const T*>(a.att[1]) + (size_t)b * 2 * pl + (size_t)(y >> 1) * (a.W >> 1) + (x0 >> 1);
+      r.q1[0].ld(q);
+      r.q1[1].ld(q + pl);
+    }
+    if (PYR || ((PYR || a.n_att > 2) && a.aw8[1] != 0.f)) {
+      const size_t pl = plane >> 4;
+      const T* q = reinterpret_cast<const T*>(a.att[2]) + (size_t)b * 2 * pl + (size_t)(y >> 2) * (a.W >> 2) + (x0 >> 2);
+      r.q2[0].ld(q);
+      r.q2[1].ld(q + pl);
+    }
+    if (PYR || ((PYR || a.n_att > 3) && a.aw8[2] != 0.f)) {
+      const size_t pl = plane >> 6;
+      const T* q = reinterpret_cast<const T*>(a.att[3]) + (size_t)b * 2 * pl + (size_t)(y >> 3) * (a.W >> 3) + (x0 >> 3);
+      r.q3[0].ld(q);
+      r.q3[1].ld(q + pl);
+    }
+    if (PYR || ((PYR || a.n_att > 4) && a.aw8[3] != 0.f)) {
+      const size_t pl = plane >> 8;
+      const T* q = reinterpret_cast<const T*>(a.att[4]) + (size_t)b * 2 * pl + (size_t)(y >> 4) * (a.W >> 4) + (x0 >> 4);
+      r.q4[0].ld(q);
+      r.q4[1].ld(q + pl);
     }
   }
-  if (a.flags & OCT_LOSS_KLD) {
-    const T* a0 = reinterpret_cast<const T*>(a.att[0]);
-    VecIO<T, 8>::ld(a0 + off, c.b0);
-    VecIO<T, 8>::ld(a0 + off + plane, c.b1);
+}
+
+// phase 2: conversions, softmax and the coarse-level logarithms
+template <typename T, int FL, bool PYR>
+__device__ __forceinline__ void finish_cell(const LossArgs& a, const CellRaw<T>& r, CellLoad<T>& c) {
+  if (FLG(a) & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+    // c.p0 / c.p1 stay logits here: cell_probs() turns them into probabilities only for cells that need them
+    r.p0.get(c.p0); r.p1.get(c.p1); r.t0.get(c.t0); r.t1.get(c.t1);
+  }
+  if (FLG(a) & OCT_LOSS_KLD) {
+    r.b0.get(c.b0); r.b1.get(c.b1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) c.m0[j] = c.m1[j] = 0.f;
-    if (a.n_att > 1 && a.aw8[0] != 0.f) {
+    if (PYR || ((PYR || a.n_att > 1) && a.aw8[0] != 0.f)) {
       const float w = a.aw8[0];
-      const size_t pl = plane >> 2;
-      const T* q = reinterpret_cast<const T*>(a.att[1]) + (size_t)b * 2 * pl +
-                   (size_t)(y >> 1) * (a.W >> 1) + (x0 >> 1);
-      VecIO<T, 4>::ld(q, c.q1[0]);
-      VecIO<T, 4>::ld(q + pl, c.q1[1]);
+      r.q1[0].get(c.q1[0]); r.q1[1].get(c.q1[1]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float l0 = __logf(w * c.q1[0][j] + kEps), l1 = __logf(w * c.q1[1][j] + kEps);
@@ -186,13 +282,9 @@ __device__ __forceinline__ void load_cell(const LossArgs& a, int b, int y, int x
         c.m1[2 * j] += l1; c.m1[2 * j + 1] += l1;
       }
     }
-    if (a.n_att > 2 && a.aw8[1] != 0.f) {
+    if (PYR || ((PYR || a.n_att > 2) && a.aw8[1] != 0.f)) {
       const float w = a.aw8[1];
-      const size_t pl = plane >> 4;
-      const T* q = reinterpret_cast<const T*>(a.att[2]) + (size_t)b * 2 * pl +
-                   (size_t)(y >> 2) * (a.W >> 2) + (x0 >> 2);
-      VecIO<T, 2>::ld(q, c.q2[0]);
-      VecIO<T, 2>::ld(q + pl, c.q2[1]);
+      r.q2[0].get(c.q2[0]); r.q2[1].get(c.q2[1]);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         float l0 = __logf(w * c.q2[0][j] + kEps), l1 = __logf(w * c.q2[1][j] + kEps);
@@ -200,24 +292,16 @@ __device__ __forceinline__ void load_cell(const LossArgs& a, int b, int y, int x
         for (int i = 0; i < 4; ++i) { c.m0[4 * j + i] += l0; c.m1[4 * j + i] += l1; }
       }
     }
-    if (a.n_att > 3 && a.aw8[2] != 0.f) {
+    if (PYR || ((PYR || a.n_att > 3) && a.aw8[2] != 0.f)) {
       const float w = a.aw8[2];
-      const size_t pl = plane >> 6;
-      const T* q = reinterpret_cast<const T*>(a.att[3]) + (size_t)b * 2 * pl +
-                   (size_t)(y >> 3) * (a.W >> 3) + (x0 >> 3);
-      VecIO<T, 1>::ld(q, &c.q3[0]);
-      VecIO<T, 1>::ld(q + pl, &c.q3[1]);
+      r.q3[0].get(&c.q3[0]); r.q3[1].get(&c.q3[1]);
       float l0 = __logf(w * c.q3[0] + kEps), l1 = __logf(w * c.q3[1] + kEps);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { c.m0[i] += l0; c.m1[i] += l1; }
     }
-    if (a.n_att > 4 && a.aw8[3] != 0.f) {
+    if (PYR || ((PYR || a.n_att > 4) && a.aw8[3] != 0.f)) {
       const float w = a.aw8[3];
-      const size_t pl = plane >> 8;
-      const T* q = reinterpret_cast<const T*>(a.att[4]) + (size_t)b * 2 * pl +
-                   (size_t)(y >> 4) * (a.W >> 4) + (x0 >> 4);
-      VecIO<T, 1>::ld(q, &c.q4[0]);
-      VecIO<T, 1>::ld(q + pl, &c.q4[1]);
+      r.q4[0].get(&c.q4[0]); r.q4[1].get(&c.q4[1]);
       float l0 = __logf(w * c.q4[0] + kEps), l1 = __logf(w * c.q4[1] + kEps);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { c.m0[i] += l0; c.m1[i] += l1; }
@@ -225,67 +309,114 @@ __device__ __forceinline__ void load_cell(const LossArgs& a, int b, int y, int x
   }
 }
 
+template <typename T, int FL, bool PYR>
+__device__ __forceinline__ void load_cell(const LossArgs& a, int b, int y, int x0, CellLoad<T>& c) {
+  CellRaw<T> r;
+  issue_cell<T, FL, PYR>(a, b, y, x0, r);
+  finish_cell<T, FL, PYR>(a, r, c);
+}
+
+template <typename T, int FL>
+__device__ __forceinline__ void cell_probs(const LossArgs& a, CellLoad<T>& c) {
+  if (FLG(a) & OCT_LOSS_FROM_LOGITS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) softmax2(c.p0[j], c.p1[j]);
+  }
+}
+
+// true when some pixel of the warp's cell carries a label (any non-zero ys)
 template <typename T>
-__global__ void __launch_bounds__(256) loss_fast_fwd_kernel(const LossArgs a) {
+__device__ __forceinline__ bool cell_labelled(const CellLoad<T>& c) {
+  float tsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tsum += fabsf(c.t0[j]) + fabsf(c.t1[j]);
+  return __any_sync(0xffffffffu, tsum != 0.f);
+}
+
+// Persistent: one wave of blocks, every warp walks 16x16 cells (all images) with a grid stride; sums stay in registers
+// until one block reduction + one set of fp64 atomics per block (the Dice sums, which are per image, go out per cell).
+template <typename T, int FL, bool PYR>
+__global__ void __launch_bounds__(256, 3) loss_fast_fwd_kernel(const LossArgs a) {
   __shared__ float red[10 * 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cw = a.W >> 4, cells = cw * (a.H >> 4);
-  const int cell = blockIdx.x * 8 + warp;
-  const int b = blockIdx.y;
+  const long long total = (long long)cells * a.B;
   // acc: n0 n1 S0 S1 kld I Card lsg lsdr lsdf
   float acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.f;
 
-  if (cell < cells && (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD))) {
-    const int cy = cell / cw, cx = cell - cy * cw;
-    const int y = cy * 16 + (lane >> 1), x0 = cx * 16 + (lane & 1) * 8;
-    CellLoad<T> c;
-    load_cell<T>(a, b, y, x0, c);
-    if (a.flags & OCT_LOSS_WPCE) {
-      const bool full = a.flags & OCT_LOSS_WPCE_FULL;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a0 = full ? c.p0[j] : c.p0[j] * c.t0[j];
-        float a1 = full ? c.p1[j] : c.p1[j] * c.t1[j];
-        acc[0] += c.t0[j];
-        acc[1] += c.t1[j];
-        acc[2] += c.t0[j] * __logf(a0 + kEps);
-        acc[3] += c.t1[j] * __logf(a1 + kEps);
+  if (FLG(a) & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD)) {
+    for (long long id = (long long)blockIdx.x * 8 + warp; id < total; id += (long long)gridDim.x * 8) {
+      const int b = (int)(id / cells), cell = (int)(id - (long long)b * cells);
+      const int cy = cell / cw, cx = cell - cy * cw;
+      const int y = cy * 16 + (lane >> 1), x0 = cx * 16 + (lane & 1) * 8;
+      {
+        const long long nid = id + (long long)gridDim.x * 8;
+        if (nid < total) {
+          const int nb = (int)(nid / cells), nc = (int)(nid - (long long)nb * cells);
+          const int ncy = nc / cw, ncx = nc - ncy * cw;
+          prefetch_cell<T, FL>(a, nb, ncy * 16 + (lane >> 1), ncx * 16 + (lane & 1) * 8);
+        }
       }
-    }
-    if (a.flags & OCT_LOSS_DICE) {
+      CellLoad<T> c;
+      load_cell<T, FL, PYR>(a, b, y, x0, c);
+      // unlabelled cells (most of a scribble mask) contribute ys * log(.) = 0 exactly: no softmax, no logarithms
+      const bool need_p = (FLG(a) & OCT_LOSS_DICE) || ((FLG(a) & OCT_LOSS_WPCE) && ((FLG(a) & OCT_LOSS_WPCE_FULL) || cell_labelled(c)));
+      if (need_p) cell_probs<T, FL>(a, c);
+      if (FLG(a) & OCT_LOSS_WPCE) {
+        const bool full = FLG(a) & OCT_LOSS_WPCE_FULL;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[5] += c.p0[j] * c.t0[j] + c.p1[j] * c.t1[j];
-        acc[6] += (c.p0[j] + c.t0[j]) + (c.p1[j] + c.t1[j]);
+        for (int j = 0; j < 8; ++j) {
+          acc[0] += c.t0[j];
+          acc[1] += c.t1[j];
+        }
+        if (need_p) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a0 = full ? c.p0[j] : c.p0[j] * c.t0[j];
+            float a1 = full ? c.p1[j] : c.p1[j] * c.t1[j];
+            acc[2] += c.t0[j] * __logf(a0 + kEps);
+            acc[3] += c.t1[j] * __logf(a1 + kEps);
+          }
+        }
       }
-    }
-    if (a.flags & OCT_LOSS_KLD) {
+      if (FLG(a) & OCT_LOSS_DICE) {
+        float di = 0.f, dc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[4] += c.b0[j] * (__logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw) +
-                  c.b1[j] * (__logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw);
+        for (int j = 0; j < 8; ++j) {
+          di += c.p0[j] * c.t0[j] + c.p1[j] * c.t1[j];
+          dc += (c.p0[j] + c.t0[j]) + (c.p1[j] + c.t1[j]);
+        }
+        di = warp_sum(di);
+        dc = warp_sum(dc);
+        if (lane == 0) {
+          atomic_add_f64(a.stats + ST_DICE + b, di);
+          atomic_add_f64(a.stats + ST_DICE + a.B + b, dc);
+        }
+      }
+      if (FLG(a) & OCT_LOSS_KLD) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[4] += c.b0[j] * (__logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw) +
+                    c.b1[j] * (__logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw);
+        }
       }
     }
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0) ls_partial(a, acc[7], acc[8], acc[9]);
+  if (blockIdx.x == 0) ls_partial(a, acc[7], acc[8], acc[9]);
 
   block_sum<10>(acc, red);
   if (threadIdx.x == 0) {
     double* st = a.stats;
-    if (a.flags & OCT_LOSS_WPCE) {
+    if (FLG(a) & OCT_LOSS_WPCE) {
       atomic_add_f64(st + ST_N + 0, acc[0]);
       atomic_add_f64(st + ST_N + 1, acc[1]);
       atomic_add_f64(st + ST_S + 0, acc[2]);
       atomic_add_f64(st + ST_S + 1, acc[3]);
     }
-    if (a.flags & OCT_LOSS_KLD) atomic_add_f64(st + ST_KLD, acc[4]);
-    if (a.flags & OCT_LOSS_DICE) {
-      atomic_add_f64(st + ST_DICE + b, acc[5]);
-      atomic_add_f64(st + ST_DICE + a.B + b, acc[6]);
-    }
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
+    if (FLG(a) & OCT_LOSS_KLD) atomic_add_f64(st + ST_KLD, acc[4]);
+    if (blockIdx.x == 0) {
       atomic_add_f64(st + ST_LSG, acc[7]);
       atomic_add_f64(st + ST_LSDR, acc[8]);
       atomic_add_f64(st + ST_LSDF, acc[9]);
@@ -315,29 +446,26 @@ __device__ __forceinline__ void ls_backward(const LossArgs& a) {
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cw = a.W >> 4, cells = cw * (a.H >> 4);
-  const int cell = blockIdx.x * 8 + warp;
-  const int b = blockIdx.y;
-  if (blockIdx.x == 0 && blockIdx.y == 0) ls_backward(a);
-  if (cell >= cells || !(a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD))) return;
-
+template <typename T, int FL, bool PYR>
+__device__ __forceinline__ void loss_bwd_cell(const LossArgs& a, int b, int cell, int cw, int lane) {
   const int cy = cell / cw, cx = cell - cy * cw;
   const int r = lane >> 1;
   const int y = cy * 16 + r, x0 = cx * 16 + (lane & 1) * 8;
   const size_t plane = (size_t)a.H * a.W;
   const size_t off = (size_t)b * 2 * plane + (size_t)y * a.W + x0;
   CellLoad<T> c;
-  load_cell<T>(a, b, y, x0, c);
+  load_cell<T, FL, PYR>(a, b, y, x0, c);
 
-  if (a.flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
+  if (FLG(a) & (OCT_LOSS_WPCE | OCT_LOSS_DICE)) {
     float g0[8], g1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) g0[j] = g1[j] = 0.f;
-    if (a.flags & OCT_LOSS_WPCE) {
-      const bool full = a.flags & OCT_LOSS_WPCE_FULL;
+    // an unlabelled cell has an all-zero WPCE gradient (with WPCE_FULL the log argument is not masked, but ys = 0 still
+    // zeroes the numerator): only Dice needs the probabilities there
+    const bool need_p = (FLG(a) & OCT_LOSS_DICE) || cell_labelled(c);
+    if (need_p) cell_probs<T, FL>(a, c);
+    if ((FLG(a) & OCT_LOSS_WPCE) && need_p) {
+      const bool full = FLG(a) & OCT_LOSS_WPCE_FULL;
       const float k = -a.gscale[OCT_LOSS_OUT_WPCE] * a.wpce_scale;
       const float w0 = k * (float)a.stats[ST_W + 0], w1 = k * (float)a.stats[ST_W + 1];
 #pragma unroll
@@ -347,11 +475,11 @@ __global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
         float a1 = full ? c.p1[j] : c.p1[j] * c.t1[j];
         float m0 = full ? c.t0[j] : c.t0[j] * c.t0[j];
         float m1 = full ? c.t1[j] : c.t1[j] * c.t1[j];
-        g0[j] += w0 * m0 / (a0 + kEps);
-        g1[j] += w1 * m1 / (a1 + kEps);
+        g0[j] += __fdividef(w0 * m0, a0 + kEps);
+        g1[j] += __fdividef(w1 * m1, a1 + kEps);
       }
     }
-    if (a.flags & OCT_LOSS_DICE) {
+    if (FLG(a) & OCT_LOSS_DICE) {
       // L = mean_b(1 - 2 I/(Card+eps)); dL/dp = (-2 t/(Card+eps) + 2 I/(Card+eps)^2)/B
       const float I = (float)a.stats[ST_DICE + b];
       const float card = (float)a.stats[ST_DICE + a.B + b] + a.dice_eps;
@@ -363,7 +491,7 @@ __global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
         g1[j] += ka * c.t1[j] + kb;
       }
     }
-    if (a.flags & OCT_LOSS_FROM_LOGITS) {
+    if ((FLG(a) & OCT_LOSS_FROM_LOGITS) && need_p) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float dot = g0[j] * c.p0[j] + g1[j] * c.p1[j];
@@ -376,16 +504,16 @@ __global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
     VecIO<T, 8>::st(gy + off + plane, g1);
   }
 
-  if (a.flags & OCT_LOSS_KLD) {
+  if (FLG(a) & OCT_LOSS_KLD) {
     const float gk = a.gscale[OCT_LOSS_OUT_KLD] / ((float)a.B * (float)a.H * (float)a.W);
     {
       float g0[8], g1[8];
-      const bool stop = a.flags & OCT_LOSS_KLD_STOPGRAD;
+      const bool stop = FLG(a) & OCT_LOSS_KLD_STOPGRAD;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         // d/db [ b (log(b+eps) - m) ] = log(b+eps) - m + b/(b+eps)
-        g0[j] = stop ? 0.f : gk * (__logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw + c.b0[j] / (c.b0[j] + kEps));
-        g1[j] = stop ? 0.f : gk * (__logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw + c.b1[j] / (c.b1[j] + kEps));
+        g0[j] = stop ? 0.f : gk * (__logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw + __fdividef(c.b0[j], c.b0[j] + kEps));
+        g1[j] = stop ? 0.f : gk * (__logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw + __fdividef(c.b1[j], c.b1[j] + kEps));
       }
       T* g = reinterpret_cast<T*>(a.g_att[0]);
       VecIO<T, 8>::st(g + off, g0);
@@ -413,7 +541,7 @@ __global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
       v4[ch] = v3[ch] + __shfl_xor_sync(0xffffffffu, v3[ch], 1);
       v4[ch] += __shfl_xor_sync(0xffffffffu, v4[ch], 16);
     }
-    if (a.n_att > 1 && (r & 1) == 0) {
+    if ((PYR || a.n_att > 1) && (r & 1) == 0) {
       const size_t pl = plane >> 2;
       T* g = reinterpret_cast<T*>(a.g_att[1]) + (size_t)b * 2 * pl + (size_t)(y >> 1) * (a.W >> 1) + (x0 >> 1);
       const float w = a.aw8[0];
@@ -421,11 +549,11 @@ __global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[ch][j] = (w != 0.f) ? kq * w / (w * c.q1[ch][j] + kEps) * v1[ch][j] : 0.f;
+        for (int j = 0; j < 4; ++j) o[ch][j] = (PYR || w != 0.f) ? __fdividef(kq * w * v1[ch][j], w * c.q1[ch][j] + kEps) : 0.f;
       VecIO<T, 4>::st(g, o[0]);
       VecIO<T, 4>::st(g + pl, o[1]);
     }
-    if (a.n_att > 2 && (r & 3) == 0) {
+    if ((PYR || a.n_att > 2) && (r & 3) == 0) {
       const size_t pl = plane >> 4;
       T* g = reinterpret_cast<T*>(a.g_att[2]) + (size_t)b * 2 * pl + (size_t)(y >> 2) * (a.W >> 2) + (x0 >> 2);
       const float w = a.aw8[1];
@@ -433,28 +561,50 @@ __global__ void __launch_bounds__(256) loss_fast_bwd_kernel(const LossArgs a) {
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) o[ch][j] = (w != 0.f) ? kq * w / (w * c.q2[ch][j] + kEps) * v2[ch][j] : 0.f;
+        for (int j = 0; j < 2; ++j) o[ch][j] = (PYR || w != 0.f) ? __fdividef(kq * w * v2[ch][j], w * c.q2[ch][j] + kEps) : 0.f;
       VecIO<T, 2>::st(g, o[0]);
       VecIO<T, 2>::st(g + pl, o[1]);
     }
-    if (a.n_att > 3 && (r & 7) == 0) {
+    if ((PYR || a.n_att > 3) && (r & 7) == 0) {
       const size_t pl = plane >> 6;
       T* g = reinterpret_cast<T*>(a.g_att[3]) + (size_t)b * 2 * pl + (size_t)(y >> 3) * (a.W >> 3) + (x0 >> 3);
       const float w = a.aw8[2];
-      float o0 = (w != 0.f) ? kq * w / (w * c.q3[0] + kEps) * v3[0] : 0.f;
-      float o1 = (w != 0.f) ? kq * w / (w * c.q3[1] + kEps) * v3[1] : 0.f;
+      float o0 = (PYR || w != 0.f) ? __fdividef(kq * w * v3[0], w * c.q3[0] + kEps) : 0.f;
+      float o1 = (PYR || w != 0.f) ? __fdividef(kq * w * v3[1], w * c.q3[1] + kEps) : 0.f;
       VecIO<T, 1>::st(g, &o0);
       VecIO<T, 1>::st(g + pl, &o1);
     }
-    if (a.n_att > 4 && lane == 0) {
+    if ((PYR || a.n_att > 4) && lane == 0) {
       const size_t pl = plane >> 8;
       T* g = reinterpret_cast<T*>(a.g_att[4]) + (size_t)b * 2 * pl + (size_t)(y >> 4) * (a.W >> 4) + (x0 >> 4);
       const float w = a.aw8[3];
-      float o0 = (w != 0.f) ? kq * w / (w * c.q4[0] + kEps) * v4[0] : 0.f;
-      float o1 = (w != 0.f) ? kq * w / (w * c.q4[1] + kEps) * v4[1] : 0.f;
+      float o0 = (PYR || w != 0.f) ? __fdividef(kq * w * v4[0], w * c.q4[0] + kEps) : 0.f;
+      float o1 = (PYR || w != 0.f) ? __fdividef(kq * w * v4[1], w * c.q4[1] + kEps) : 0.f;
       VecIO<T, 1>::st(g, &o0);
       VecIO<T, 1>::st(g + pl, &o1);
     }
+  }
+}
+
+
+template <typename T, int FL, bool PYR>
+__global__ void __launch_bounds__(256, 3) loss_fast_bwd_kernel(const LossArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cw = a.W >> 4, cells = cw * (a.H >> 4);
+  const long long total = (long long)cells * a.B;
+  if (blockIdx.x == 0) ls_backward(a);
+  if (!(FLG(a) & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD))) return;
+  for (long long id = (long long)blockIdx.x * 8 + warp; id < total; id += (long long)gridDim.x * 8) {
+    const int b = (int)(id / cells), cell = (int)(id - (long long)b * cells);
+    {
+      const long long nid = id + (long long)gridDim.x * 8;
+      if (nid < total) {
+        const int nb = (int)(nid / cells), nc = (int)(nid - (long long)nb * cells);
+        const int ncy = nc / cw, ncx = nc - ncy * cw;
+        prefetch_cell<T, FL>(a, nb, ncy * 16 + (lane >> 1), ncx * 16 + (lane & 1) * 8);
+      }
+    }
+    loss_bwd_cell<T, FL, PYR>(a, b, cell, cw, lane);
   }
 }
 
@@ -652,6 +802,32 @@ int validate(const OctaveLossDesc* d) {
   return OCT_OK;
 }
 
+constexpr int kGStepFlags = OCT_LOSS_WPCE | OCT_LOSS_KLD | OCT_LOSS_FROM_LOGITS;
+// map flags of the G-step (LS-G rides along: it is handled by block 0 outside the specialised code)
+bool gstep_config(const OctaveLossDesc* d) {
+  if ((d->flags & ~(OCT_LOSS_LSG)) != kGStepFlags) return false;
+  if (d->flags & OCT_LOSS_LSG) return false;
+  if (d->n_att != OCT_LOSS_MAX_ATT) return false;
+  for (int k = 0; k < OCT_LOSS_MAX_ATT - 1; ++k)
+    if (d->att_weight[k] == 0.f) return false;
+  return true;
+}
+
+// one wave of 8-warp blocks (2 resident blocks per SM by the launch bounds), never more blocks than cells / 8
+int fast_grid(const OctaveLossDesc* d, bool maps) {
+  if (!maps) return 1;
+  static int sms = 0;
+  if (!sms) {
+    sms = octave_sm_count();
+    if (sms <= 0) sms = 148;
+  }
+  const long long total = (long long)(d->H >> 4) * (d->W >> 4) * d->B;
+  long long need = (total + 7) / 8;
+  const long long wave = 3LL * sms;
+  if (need > wave) need = wave;
+  return (int)(need < 1 ? 1 : need);
+}
+
 void fill_args(LossArgs& a, const OctaveLossDesc* d, const void* yhat, const void* ys, const void* const* att,
                const float* d_real, const float* d_fake, void* stats) {
   a.yhat = yhat; a.ys = ys; a.d_real = d_real; a.d_fake = d_fake;
@@ -696,10 +872,15 @@ extern "C" int octave_loss_fwd(const OctaveLossDesc* d, const void* yhat, const 
   if (cudaMemsetAsync(stats, 0, octave_loss_stats_bytes(d), s) != cudaSuccess) return OCT_ERR_LAUNCH;
   const bool maps = d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
   if (fast_ok(d)) {
-    dim3 grid(1, 1);
-    if (maps) grid = dim3(((d->H >> 4) * (d->W >> 4) + 7) / 8, d->B);
-    if (d->dtype == OCT_DTYPE_F32) loss_fast_fwd_kernel<float><<<grid, 256, 0, s>>>(a);
-    else loss_fast_fwd_kernel<bf16><<<grid, 256, 0, s>>>(a);
+    const int grid = fast_grid(d, maps);
+    // the G-step configuration (WPCE + KLD on logits, full 5-level pyramid) runs a kernel specialised at compile time
+    if (gstep_config(d)) {
+      if (d->dtype == OCT_DTYPE_F32) loss_fast_fwd_kernel<float, kGStepFlags, true><<<grid, 256, 0, s>>>(a);
+      else loss_fast_fwd_kernel<bf16, kGStepFlags, true><<<grid, 256, 0, s>>>(a);
+    } else {
+      if (d->dtype == OCT_DTYPE_F32) loss_fast_fwd_kernel<float, -1, false><<<grid, 256, 0, s>>>(a);
+      else loss_fast_fwd_kernel<bf16, -1, false><<<grid, 256, 0, s>>>(a);
+    }
   } else {
     int gx = (d->H * d->W + 255) / 256;
     if (gx > 1024) gx = 1024;
@@ -730,10 +911,14 @@ extern "C" int octave_loss_bwd(const OctaveLossDesc* d, const void* yhat, const 
     }
   const bool maps = d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
   if (fast_ok(d)) {
-    dim3 grid(1, 1);
-    if (maps) grid = dim3(((d->H >> 4) * (d->W >> 4) + 7) / 8, d->B);
-    if (d->dtype == OCT_DTYPE_F32) loss_fast_bwd_kernel<float><<<grid, 256, 0, s>>>(a);
-    else loss_fast_bwd_kernel<bf16><<<grid, 256, 0, s>>>(a);
+    const int grid = fast_grid(d, maps);
+    if (gstep_config(d)) {
+      if (d->dtype == OCT_DTYPE_F32) loss_fast_bwd_kernel<float, kGStepFlags, true><<<grid, 256, 0, s>>>(a);
+      else loss_fast_bwd_kernel<bf16, kGStepFlags, true><<<grid, 256, 0, s>>>(a);
+    } else {
+      if (d->dtype == OCT_DTYPE_F32) loss_fast_bwd_kernel<float, -1, false><<<grid, 256, 0, s>>>(a);
+      else loss_fast_bwd_kernel<bf16, -1, false><<<grid, 256, 0, s>>>(a);
+    }
   } else {
     // coarse-level gradients are accumulated with atomics: zero them first
     if (d->flags & OCT_LOSS_KLD)

@@ -576,10 +576,10 @@ class ResnestUNet(nn.Module):
             hook = self._grad_ready_hook
             if hook is None:
                 return
-            new = [g for p, g in grads.items() if p not in emitted]
+            new = [(p, g) for p, g in grads.items() if p not in emitted]
             emitted.update(grads.keys())
             if new:
-                hook(None, new)
+                hook([p for p, _ in new], [g for _, g in new])
 
         d_f, wfc, bfc = tape["fc"]
         dd, dw, db = ops.head_bwd(d_f, wfc, bfc, 0, cont(g_agg), None)

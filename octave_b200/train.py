@@ -22,39 +22,55 @@ from .model import OctaScribbleNet
 
 
 class GradAllReducer:
-    """Bucketed gradient averaging over NCCL/gloo.  `reduce(grads)` may be called several times per backward with
-    disjoint gradient lists (in the order they become ready); `finish()` waits and writes averaged values back."""
+    """Bucketed gradient averaging over NCCL/gloo.  `reduce(params, grads)` may be called several times per backward
+    with disjoint lists (in the order the gradients become ready): every ~bucket_bytes the gradients gathered so far are
+    packed into ONE flat buffer (a single concat kernel) whose all-reduce starts at once on a side stream, overlapping the
+    rest of the backward pass.  `finish()` waits for the buckets and re-points each `param.grad` at its slice of the
+    averaged flat buffer — no copy back, no per-tensor kernels."""
 
     def __init__(self, bucket_bytes: int = 25 << 20, process_group=None):
         self.bucket_bytes = bucket_bytes
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self._pending = []          # (flat, tensors, work)
-        self._cur: List[Tensor] = []
+        self._pending = []          # (flat, params, grads, work)
+        self._cur_p: List[Optional[nn.Parameter]] = []
+        self._cur_g: List[Tensor] = []
         self._cur_bytes = 0
         self._stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        backend = dist.get_backend(process_group) if dist.is_initialized() else ""
+        self._avg = backend == "nccl"      # ncclAvg; gloo has no AVG: sum, then scale
 
     def _flush(self):
-        if not self._cur:
+        if not self._cur_g:
             return
-        tensors, self._cur, self._cur_bytes = self._cur, [], 0
-        if self._stream is not None and tensors[0].is_cuda:
+        params, grads = self._cur_p, self._cur_g
+        self._cur_p, self._cur_g, self._cur_bytes = [], [], 0
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        if self._stream is not None and grads[0].is_cuda:
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
-                flat = torch.cat([t.reshape(-1) for t in tensors])
-                work = dist.all_reduce(flat, group=self.pg, async_op=True)
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                work = dist.all_reduce(flat, op=op, group=self.pg, async_op=True)
+            for g in grads:
+                g.record_stream(self._stream)
         else:
-            flat = torch.cat([t.reshape(-1) for t in tensors])
-            work = dist.all_reduce(flat, group=self.pg, async_op=True)
-        self._pending.append((flat, tensors, work))
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            work = dist.all_reduce(flat, op=op, group=self.pg, async_op=True)
+        self._pending.append((flat, params, grads, work))
 
-    def reduce(self, grads: Sequence[Optional[Tensor]]):
+    def reduce(self, params, grads: Optional[Sequence[Optional[Tensor]]] = None):
+        """reduce(params, grads) — or reduce(grads): gradients without an owning parameter are averaged in place."""
         if self.world == 1:
             return
-        for g in grads:
+        if grads is None:
+            params, grads = None, params
+        if params is None:
+            params = [None] * len(grads)
+        for p, g in zip(params, grads):
             if g is None:
                 continue
-            self._cur.append(g)
+            self._cur_p.append(p)
+            self._cur_g.append(g)
             self._cur_bytes += g.numel() * g.element_size()
             if self._cur_bytes >= self.bucket_bytes:
                 self._flush()
@@ -63,17 +79,23 @@ class GradAllReducer:
         if self.world == 1:
             return
         self._flush()
-        for flat, tensors, work in self._pending:
+        on_side = self._stream is not None and self._pending and self._pending[0][0].is_cuda
+        for flat, params, grads, work in self._pending:
             work.wait()
-            ctxm = torch.cuda.stream(self._stream) if (self._stream is not None and flat.is_cuda) else _null()
+            ctxm = torch.cuda.stream(self._stream) if on_side else _null()
             with ctxm:
-                flat.div_(self.world)
-                off = 0
-                for t in tensors:
-                    n = t.numel()
-                    t.copy_(flat[off:off + n].view_as(t))
-                    off += n
-        if self._stream is not None and self._pending and self._pending[0][0].is_cuda:
+                if not self._avg:
+                    flat.div_(self.world)
+            off = 0
+            for p, g in zip(params, grads):
+                n = g.numel()
+                view = flat[off:off + n].view(g.shape)
+                if p is not None:
+                    p.grad = view.view_as(p)          # the optimiser reads the averaged bucket slice directly
+                else:
+                    g.copy_(view)
+                off += n
+        if on_side:
             torch.cuda.current_stream().wait_stream(self._stream)
         self._pending = []
 
@@ -106,7 +128,7 @@ class TrainStep:
         self.reducer = GradAllReducer(bucket_bytes) if distributed else None
         if self.reducer is not None:
             red = self.reducer
-            net.segmentor._grad_ready_hook = lambda params, grads: red.reduce(grads)
+            net.segmentor._grad_ready_hook = lambda params, grads: red.reduce(params, grads)
 
     def _set_d_grad(self, flag: bool):
         if self.has_d:
@@ -138,7 +160,7 @@ class TrainStep:
         loss = self.lsd(net.discriminator(list(real)), net.discriminator([f.detach() for f in fake]))
         loss.backward()
         if self.reducer is not None:
-            self.reducer.reduce([p.grad for p in self.dis_params])
+            self.reducer.reduce(self.dis_params, [p.grad for p in self.dis_params])
             self.reducer.finish()
         self.opt_d.step()
         return loss.detach()

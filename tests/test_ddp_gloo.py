@@ -30,6 +30,12 @@ def _worker(rank, world, port, q):
     g2 = [torch.full((10,), float(rank))]
     red.reduce(g2); red.finish()
     ok = ok and torch.allclose(g2[0], torch.full((10,), (world - 1) / 2))
+    # parameter-owning form: .grad is re-pointed at the averaged bucket slice (what TrainStep uses)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    g3 = [b * (rank + 1) for b in base]
+    red.reduce(params[:3], g3[:3]); red.reduce(params[3:], g3[3:]); red.finish()
+    ok = ok and all(p.grad is not None and p.grad.shape == p.shape and torch.allclose(p.grad, b * mean, rtol=1e-6, atol=1e-6)
+                    for p, b in zip(params, base))
     q.put((rank, ok))
     dist.destroy_process_group()
 
