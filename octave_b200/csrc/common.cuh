@@ -210,3 +210,31 @@ __device__ __forceinline__ void fold_lanes(float (&v)[NV], float* sm, int Gb) {
   }
 }
 
+
+// Per-column sum / sum of squares of a warp's staged 32 x COLS_W bf16 tile (row pitch PITCH bytes), for the BatchNorm
+// statistics fused into the conv epilogues.  A lane owns the column PAIR cp = lane % (COLS_W/2) (one 32-bit shared load
+// covers both columns) and every (32 / (COLS_W/2))-th row; the row groups are folded with shuffles.  acc = {sum a, sum b,
+// sum sq a, sum sq b} accumulates across tiles and is meaningful on lanes < COLS_W/2.
+template <int COLS_W, int PITCH>
+__device__ __forceinline__ void tile_col_stats(const uint8_t* stage, int lane, float (&acc)[4]) {
+  constexpr int CP = COLS_W / 2, RG = 32 / CP, RPG = 32 / RG;
+  const int cp = lane % CP, rg = lane / CP;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPG; ++i) {
+    const int row = i * RG + rg;
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(stage + row * PITCH + cp * 4);
+    float a, b;
+    bf16x2_unpack(u, a, b);
+    s0 += a; s1 += b;
+    q0 += a * a; q1 += b * b;
+  }
+#pragma unroll
+  for (int off = 16; off >= CP; off >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, off);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, off);
+  }
+  acc[0] += s0; acc[1] += s1; acc[2] += q0; acc[3] += q1;
+}

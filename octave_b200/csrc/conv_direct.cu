@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include "../../include/octave_b200.h"
 
+int oct_act_bwd_vec(const OctaveAct* y, const OctaveAct* dy, int act, const OctaveAct* dz, cudaStream_t s);
+
 namespace {
 
 constexpr int TM = 32, TN = 32, TK = 32;
@@ -307,6 +309,13 @@ extern "C" int octave_act_bwd(const OctaveAct* y, const OctaveAct* dy, int32_t a
   if (!y || !dy || !dz || !y->data || !dy->data || !dz->data) return OCT_ERR_INVALID;
   if (y->dtype != dy->dtype || y->dtype != dz->dtype || y->C != dy->C || y->C != dz->C) return OCT_ERR_INVALID;
   const long long total = (long long)y->B * y->H * y->W * y->C;
+  if (act >= 1 && act <= 4) {
+    const int rc = oct_act_bwd_vec(y, dy, act, dz, (cudaStream_t)stream);
+    if (rc == OCT_OK) {
+      OCT_CHECK_LAUNCH();
+      return OCT_OK;
+    }
+  }
   long long g = (total + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;
   if (y->dtype == OCT_DTYPE_F32) act_bwd_kernel<float><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(*y, *dy, act, *dz);

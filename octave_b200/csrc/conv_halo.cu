@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
     const int r = q * 32 + lane;
     const int th = r / p.TWp, tw = r - th * p.TWp;
     uint8_t* const stage = stage_gen + (warp - 2) * (32 * PITCH);
-    float ssum = 0.f, ssq = 0.f;   // COLS_W <= 32: one statistics column per lane
+    float sacc[4] = {0.f, 0.f, 0.f, 0.f};   // statistics of this lane's column pair (tile_col_stats)
     int stat_col0 = -1;
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -228,43 +228,53 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
-      if (p.stats && lane < COLS_W) {
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-          const float val = __bfloat162float(*reinterpret_cast<const bf16*>(stage + rr * PITCH + lane * 2));
-          s1 += val;
-          s2 += val * val;
-        }
-        ssum += s1;
-        ssq += s2;
-      }
+      if (p.stats) tile_col_stats<COLS_W, PITCH>(stage, lane, sacc);
       constexpr int LPR = (COLS_W * 2) / 16;   // lanes per row (16 B each): 2 or 4
       constexpr int RPI = 32 / LPR;
+      constexpr int NIT = 32 / RPI;
       const int sub = lane % LPR, rsel = lane / LPR;
+      if (p.accumulate) {
+        // y += result: all old values are fetched first (independent loads in flight), then added and stored
+        uint4 old[NIT];
+        long long offs[NIT];
 #pragma unroll
-      for (int r0 = 0; r0 < 32; r0 += RPI) {
-        const int row = r0 + rsel;
-        const long long off = __shfl_sync(0xffffffffu, row_off, row);
-        if (off >= 0) {
-          uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
-          bf16* o = reinterpret_cast<bf16*>(p.out) + off + sub * 8;
-          if (p.accumulate) {
-            const uint4 e = *reinterpret_cast<const uint4*>(o);
+        for (int i = 0; i < NIT; ++i) {
+          const int row = i * RPI + rsel;
+          offs[i] = __shfl_sync(0xffffffffu, row_off, row);
+          if (offs[i] >= 0) old[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.out) + offs[i] + sub * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          if (offs[i] >= 0) {
+            const int row = i * RPI + rsel;
+            uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
+            const uint4 e = old[i];
             float x0, x1, y0, y1;
             bf16x2_unpack(val.x, x0, x1); bf16x2_unpack(e.x, y0, y1); val.x = bf16x2_pack(x0 + y0, x1 + y1);
             bf16x2_unpack(val.y, x0, x1); bf16x2_unpack(e.y, y0, y1); val.y = bf16x2_pack(x0 + y0, x1 + y1);
             bf16x2_unpack(val.z, x0, x1); bf16x2_unpack(e.z, y0, y1); val.z = bf16x2_pack(x0 + y0, x1 + y1);
             bf16x2_unpack(val.w, x0, x1); bf16x2_unpack(e.w, y0, y1); val.w = bf16x2_pack(x0 + y0, x1 + y1);
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + sub * 8) = val;
           }
-          *reinterpret_cast<uint4*>(o) = val;
+        }
+      } else {
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+          const int row = r0 + rsel;
+          const long long off = __shfl_sync(0xffffffffu, row_off, row);
+          if (off >= 0) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + sub * 8) = val;
+          }
         }
       }
       __syncwarp();
     }
-    if (p.stats && stat_col0 >= 0 && lane < COLS_W) {
-      atomicAdd(p.stats + stat_col0 + lane, (double)ssum);
-      atomicAdd(p.stats + p.stats_stride + stat_col0 + lane, (double)ssq);
+    if (p.stats && stat_col0 >= 0 && lane < COLS_W / 2) {
+      atomicAdd(p.stats + stat_col0 + 2 * lane, (double)sacc[0]);
+      atomicAdd(p.stats + stat_col0 + 2 * lane + 1, (double)sacc[1]);
+      atomicAdd(p.stats + p.stats_stride + stat_col0 + 2 * lane, (double)sacc[2]);
+      atomicAdd(p.stats + p.stats_stride + stat_col0 + 2 * lane + 1, (double)sacc[3]);
     }
   }
   __syncthreads();

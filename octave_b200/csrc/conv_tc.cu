@@ -85,7 +85,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   constexpr int COLS_W = BN >= 32 ? BN / 2 : BN;   // columns handled by one epilogue warp
   constexpr int NCHUNK_W = COLS_W / 16;
-  constexpr int NSTAT = (COLS_W + 31) / 32;
   constexpr int PITCH = COLS_W * 2 + 16;           // bytes per staged row (+16 spreads the banks)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -197,9 +196,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
     const int r = q * 32 + lane;
     const int th = r / p.TW, tw = r - th * p.TW;
     uint8_t* const stage = smem_gen + STAGES * STAGE_BYTES + (warp - 2) * (32 * PITCH);
-    float ssum[NSTAT], ssq[NSTAT];
-#pragma unroll
-    for (int c = 0; c < NSTAT; ++c) ssum[c] = ssq[c] = 0.f;
+    float sacc[4] = {0.f, 0.f, 0.f, 0.f};   // statistics of this lane's column pair (tile_col_stats)
     int stat_col0 = -1;  // global channel of this warp's column 0 (fixed across the CTA's tiles when stats are on)
     uint32_t li = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
@@ -267,58 +264,63 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
       if (works) {
-        if (p.stats) {
-          // per-channel sum / sum of squares of the staged (bf16-rounded) values: lane <-> column(s)
-#pragma unroll
-          for (int k = 0; k < NSTAT; ++k) {
-            const int col = lane + 32 * k;
-            if (col < COLS_W) {
-              float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-              for (int rr = 0; rr < 32; ++rr) {
-                const float val = __bfloat162float(*reinterpret_cast<const bf16*>(stage + rr * PITCH + col * 2));
-                s1 += val;
-                s2 += val * val;
-              }
-              ssum[k] += s1;
-              ssq[k] += s2;
-            }
-          }
-        }
+        // per-channel sum / sum of squares of the staged (bf16-rounded) values
+        if (p.stats) tile_col_stats<COLS_W, PITCH>(stage, lane, sacc);
         // coalesced write-out of the warp's 32 staged rows: LPR lanes cover one row (16 B each)
         constexpr int LPR = (COLS_W * 2) / 16;   // lanes per row: 8 (64 cols), 4, 2
         constexpr int RPI = 32 / LPR;            // rows per instruction
+        constexpr int NIT = 32 / RPI;            // store instructions per lane
         const int sub = lane % LPR, rsel = lane / LPR;
-#pragma unroll 4
-        for (int r0 = 0; r0 < 32; r0 += RPI) {
-          const int row = r0 + rsel;
-          const long long off = __shfl_sync(0xffffffffu, row_off, row);
-          if (off >= 0 && sub * 8 < nvalid) {
-            uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
-            bf16* o = reinterpret_cast<bf16*>(p.out) + off + sub * 8;
-            if (p.accumulate) {
-              const uint4 e = *reinterpret_cast<const uint4*>(o);
+        if (p.accumulate) {
+          // y += result: fetch all the old values first (NIT independent 16-byte loads in flight), then add and store
+          uint4 old[NIT];
+          long long offs[NIT];
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int row = i * RPI + rsel;
+            long long off = __shfl_sync(0xffffffffu, row_off, row);
+            if (sub * 8 >= nvalid) off = -1;
+            offs[i] = off;
+            if (off >= 0) old[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.out) + off + sub * 8);
+          }
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            if (offs[i] >= 0) {
+              const int row = i * RPI + rsel;
+              uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
+              const uint4 e = old[i];
               float x0, x1, y0, y1;
               bf16x2_unpack(val.x, x0, x1); bf16x2_unpack(e.x, y0, y1); val.x = bf16x2_pack(x0 + y0, x1 + y1);
               bf16x2_unpack(val.y, x0, x1); bf16x2_unpack(e.y, y0, y1); val.y = bf16x2_pack(x0 + y0, x1 + y1);
               bf16x2_unpack(val.z, x0, x1); bf16x2_unpack(e.z, y0, y1); val.z = bf16x2_pack(x0 + y0, x1 + y1);
               bf16x2_unpack(val.w, x0, x1); bf16x2_unpack(e.w, y0, y1); val.w = bf16x2_pack(x0 + y0, x1 + y1);
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + sub * 8) = val;
             }
-            *reinterpret_cast<uint4*>(o) = val;
+          }
+        } else {
+#pragma unroll 4
+          for (int r0 = 0; r0 < 32; r0 += RPI) {
+            const int row = r0 + rsel;
+            const long long off = __shfl_sync(0xffffffffu, row_off, row);
+            if (off >= 0 && sub * 8 < nvalid) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + sub * 8) = val;
+            }
           }
         }
         __syncwarp();  // staging rows are rewritten by the next tile
       }
     }
-    if (p.stats && works && stat_col0 >= 0) {
+    if (p.stats && works && stat_col0 >= 0 && lane < COLS_W / 2) {
       const int nvalid_cols = p.cout_g - (stat_col0 % p.cout_g);
-#pragma unroll
-      for (int k = 0; k < NSTAT; ++k) {
-        const int col = lane + 32 * k;
-        if (col < COLS_W && col < nvalid_cols) {
-          atomicAdd(p.stats + stat_col0 + col, (double)ssum[k]);
-          atomicAdd(p.stats + p.stats_stride + stat_col0 + col, (double)ssq[k]);
-        }
+      const int col = 2 * lane;
+      if (col < nvalid_cols) {
+        atomicAdd(p.stats + stat_col0 + col, (double)sacc[0]);
+        atomicAdd(p.stats + p.stats_stride + stat_col0 + col, (double)sacc[2]);
+      }
+      if (col + 1 < nvalid_cols) {
+        atomicAdd(p.stats + stat_col0 + col + 1, (double)sacc[1]);
+        atomicAdd(p.stats + p.stats_stride + stat_col0 + col + 1, (double)sacc[3]);
       }
     }
   }

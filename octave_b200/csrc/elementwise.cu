@@ -360,7 +360,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bn_bwd_apply_kern
   }
 }
 
-// OP 0: dst += src; OP 1: dst = src * (mask > 0)  (a = dst/dy, b = src/mask)
+// OP 0: dst += src; OP 1: dst = src * (mask > 0)  (a = dst/dy, b = src/mask);
+// OP 2..5: activation backward, a = dy, b = y (stored activation output): ReLU, LeakyReLU(0.2), sigmoid, tanh
 constexpr int U_BIN = 4;
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) binary_kernel(const OctaveAct a, const OctaveAct b, int Gb, const OctaveAct out) {
@@ -383,7 +384,13 @@ __global__ void __launch_bounds__(256) binary_kernel(const OctaveAct a, const Oc
         ra[u].get(f);
         rb[u].get(g);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = OP == 0 ? f[i] + g[i] : (g[i] > 0.f ? f[i] : 0.f);
+        for (int i = 0; i < 8; ++i) {
+          if (OP == 0) f[i] = f[i] + g[i];
+          else if (OP == 1 || OP == 2) f[i] = g[i] > 0.f ? f[i] : 0.f;
+          else if (OP == 3) f[i] = g[i] > 0.f ? f[i] : 0.2f * f[i];
+          else if (OP == 4) f[i] = f[i] * g[i] * (1.f - g[i]);
+          else f[i] = f[i] * (1.f - g[i] * g[i]);
+        }
         VecIO<T, 8>::st(at<T>(out, t.base + q, t.cg * 8), f);
       }
     }
@@ -659,6 +666,22 @@ static int launch_binary(const OctaveAct* a, const OctaveAct* b, const OctaveAct
   if (!make_geo(a, &g, U_BIN, false, ONE_WAVE(fn, 256, 0))) return OCT_ERR_UNSUPPORTED;
   fn<<<g.grid, g.bs, 0, s>>>(*a, *b, g.Gb, *out);
   return OCT_OK;
+}
+
+// vectorised path of octave_act_bwd (conv_direct.cu) for views with 8-channel granularity
+int oct_act_bwd_vec(const OctaveAct* y, const OctaveAct* dy, int act, const OctaveAct* dz, cudaStream_t s) {
+  if (!view_ok(y) || !view_ok(dy) || !view_ok(dz) || !same_shape(y, dy) || !same_shape(y, dz)) return OCT_ERR_UNSUPPORTED;
+  int rc = OCT_OK;
+  DISPATCH_T(y->dtype, {
+    switch (act) {
+      case 1: rc = launch_binary<T, 2>(dy, y, dz, s); break;
+      case 2: rc = launch_binary<T, 3>(dy, y, dz, s); break;
+      case 3: rc = launch_binary<T, 4>(dy, y, dz, s); break;
+      case 4: rc = launch_binary<T, 5>(dy, y, dz, s); break;
+      default: rc = OCT_ERR_UNSUPPORTED;
+    }
+  });
+  return rc;
 }
 
 extern "C" int octave_add_inplace(const OctaveAct* dst, const OctaveAct* src, void* stream) {
