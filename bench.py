@@ -155,9 +155,13 @@ def kernel_rooflines(peaks, B, H, W):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     ach = flops / (ms * 1e-3) / 1e12
-    out["roofline"] = {"kernel": "conv_tc_kernel<128,64,4> (decoder_2.conv.0 fwd 3x3 512->256)", "bound": "tensor",
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=32, 400^2 from one `ncu --set full` capture
+    # (profiles/ncu_conv_fat_512x256_r01.txt: 330.2 MB + 141.0 MB; algorithmic minimum x + y + w = 494 MB)
+    traffic = 471.1e6 if (B, H, W) == (32, 400, 400) else None
+    out["roofline"] = {"kernel": "conv_tc_kernel<128,64,5> (decoder_2.conv.0 fwd 3x3 512->256)", "bound": "tensor",
                        "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                       "traffic": None, "peak_source": peaks["source"] + " burst (kernel timed alone)", "ms_per_launch": ms}
+                       "traffic": traffic, "algorithmic_flop": flops,
+                       "peak_source": peaks["source"] + " burst (kernel timed alone)", "ms_per_launch": ms}
     # (2) fused loss kernel, forward statistics + gradient pass, bf16 maps (36.0 B/pixel algorithmic)
     g = torch.Generator(device=dev).manual_seed(0)
     agg = torch.randn(B, 2, H, W, device=dev, generator=g).bfloat16().requires_grad_()
@@ -276,7 +280,7 @@ def run_gpu(args):
         sampler.stop_flag.set(); sampler.join(timeout=3)
     peaks = load_peaks()
     line = {
-        "metric": "train images/s, 400x400 synthetic OCTA (adversarial step: G-step + D-step)",
+        "metric": f"train images/s, {H}x{W} synthetic OCTA (adversarial step: G-step + D-step)",
         "value": world * B / (ms_step * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
@@ -314,7 +318,7 @@ def run_reference(args):
         return
     B, H, W = CONFIGS[args.config]
     cb = run_cpu(H, W, 2, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
-    line = {"impl": "reference", "metric": "train images/s, 400x400 synthetic OCTA (adversarial step: G-step + D-step)",
+    line = {"impl": "reference", "metric": f"train images/s, {H}x{W} synthetic OCTA (adversarial step: G-step + D-step)",
             "value": cb["value"], "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
