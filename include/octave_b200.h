@@ -294,6 +294,17 @@ int octave_rowdot_bwd(const OctaveAct* x, const float* w, const float* g, const 
 #define OCT_PACK_CONVT_DGRAD 3  /* w [Cin][Cout][2][2] -> [Cin][4*Cout] */
 int octave_pack_weight(const float* w, int32_t mode, int32_t cout, int32_t cin, int32_t groups, int32_t dense_groups,
                        int32_t ksize, void* out_bf16, void* stream);
+/* Every operand pack of a network in ONE launch (the per-step re-pack after the optimiser update).
+ * jobs_device: device array sorted by block_start; job i owns the blocks [block_start_i, block_start_i +
+ * octave_pack_job_blocks(...)); total_blocks = their sum. */
+typedef struct OctavePackJob {
+  const float* w;        /* fp32 weight, torch layout */
+  void* out;             /* bf16 operand pack */
+  int32_t mode, cout, cin, groups, dense_groups, ksize;
+  int64_t block_start;
+} OctavePackJob;
+int64_t octave_pack_job_blocks(int32_t mode, int32_t cout, int32_t cin, int32_t dense_groups, int32_t ksize);
+int octave_pack_weight_multi(const OctavePackJob* jobs_device, int32_t n_jobs, int64_t total_blocks, void* stream);
 
 #ifdef __cplusplus
 }

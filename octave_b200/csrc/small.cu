@@ -147,42 +147,114 @@ __global__ void rsoftmax_bwd_kernel(const float* datt, const float* att, int B, 
   for (int r = 0; r < R; ++r) dlogits[base + r * C] = att[base + r * C] * (datt[base + r * C] - dot);
 }
 
-__global__ void pack_weight_kernel(const float* w, int mode, int cout, int cin, int groups, int dg, int k, bf16* out) {
+// value of element idx of the packed operand (see OCT_PACK_* in the header)
+__device__ __forceinline__ float pack_value(const float* __restrict__ w, int mode, int cout, int cin, int groups, int dg,
+                                            int k, long long idx) {
   const int taps = k * k;
   const int cin_g = cin / groups, cout_g = cout / groups;
   const int cin_d = cin / dg, cout_d = cout / dg;
-  long long total;
-  if (mode == OCT_PACK_FWD) total = (long long)taps * cout * cin_d;
-  else if (mode == OCT_PACK_DGRAD) total = (long long)taps * cin * cout_d;
-  else total = (long long)4 * cout * cin;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    if (mode == OCT_PACK_FWD) {
-      const int ci_d = (int)(idx % cin_d);
-      const int co = (int)((idx / cin_d) % cout);
-      const int tap = (int)(idx / ((long long)cin_d * cout));
-      const int ci = (co / cout_d) * cin_d + ci_d;  // global input channel
-      if (ci / cin_g == co / cout_g) v = w[((long long)co * cin_g + (ci % cin_g)) * taps + tap];
-    } else if (mode == OCT_PACK_DGRAD) {
-      const int co_d = (int)(idx % cout_d);
-      const int ci = (int)((idx / cout_d) % cin);
-      const int tap = (int)(idx / ((long long)cout_d * cin));
+  float v = 0.f;
+  if (mode == OCT_PACK_FWD) {
+    const int ci_d = (int)(idx % cin_d);
+    const int co = (int)((idx / cin_d) % cout);
+    const int tap = (int)(idx / ((long long)cin_d * cout));
+    const int ci = (co / cout_d) * cin_d + ci_d;  // global input channel
+    if (ci / cin_g == co / cout_g) v = w[((long long)co * cin_g + (ci % cin_g)) * taps + tap];
+  } else if (mode == OCT_PACK_DGRAD) {
+    const int co_d = (int)(idx % cout_d);
+    const int ci = (int)((idx / cout_d) % cin);
+    const int tap = (int)(idx / ((long long)cout_d * cin));
+    const int co = (ci / cin_d) * cout_d + co_d;
+    if (ci / cin_g == co / cout_g) v = w[((long long)co * cin_g + (ci % cin_g)) * taps + (taps - 1 - tap)];
+  } else if (mode == OCT_PACK_CONVT_FWD) {
+    // out[(t*cout + co)][ci] = w[ci][co][t]
+    const int ci = (int)(idx % cin);
+    const int co = (int)((idx / cin) % cout);
+    const int t = (int)(idx / ((long long)cin * cout));
+    v = w[((long long)ci * cout + co) * 4 + t];
+  } else {
+    // out[ci][t*cout + co] = w[ci][co][t]
+    const int co = (int)(idx % cout);
+    const int t = (int)((idx / cout) % 4);
+    const int ci = (int)(idx / ((long long)4 * cout));
+    v = w[((long long)ci * cout + co) * 4 + t];
+  }
+  return v;
+}
+
+__device__ __host__ inline long long pack_total(int mode, int cout, int cin, int dg, int k) {
+  const int taps = k * k;
+  if (mode == OCT_PACK_FWD) return (long long)taps * cout * (cin / dg);
+  if (mode == OCT_PACK_DGRAD) return (long long)taps * cin * (cout / dg);
+  return 4LL * cout * cin;
+}
+
+__global__ void pack_weight_kernel(const float* w, int mode, int cout, int cin, int groups, int dg, int k, bf16* out) {
+  const long long total = pack_total(mode, cout, cin, dg, k);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    out[idx] = __float2bfloat16_rn(pack_value(w, mode, cout, cin, groups, dg, k, idx));
+}
+
+// Every operand pack of a network in ONE launch: block -> job by binary search over the jobs' first block, then
+// kItemsPerBlock consecutive ITEMS of that job.  An item is one (output row, K index) pair and carries all taps: a thread
+// reads the taps of its weight (contiguous in the torch layout) and writes one element into every tap plane, with the
+// lane-fastest item index chosen so that the 2-byte stores of a warp are contiguous.
+constexpr int kItemsPerBlock = 1024;
+__device__ __host__ inline long long pack_items(int mode, int cout, int cin, int dg) {
+  if (mode == OCT_PACK_FWD) return (long long)cout * (cin / dg);
+  if (mode == OCT_PACK_DGRAD) return (long long)cin * (cout / dg);
+  return (long long)cout * cin;
+}
+
+__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const OctavePackJob* __restrict__ jobs, int n_jobs) {
+  int lo = 0, hi = n_jobs - 1;
+  const long long b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_start <= b) lo = mid; else hi = mid - 1;
+  }
+  const OctavePackJob j = jobs[lo];
+  const float* __restrict__ w = j.w;
+  bf16* out = reinterpret_cast<bf16*>(j.out);
+  const int cout = j.cout, cin = j.cin, dg = j.dense_groups;
+  const int taps = j.mode <= OCT_PACK_DGRAD ? j.ksize * j.ksize : 4;
+  const int cin_g = cin / j.groups, cout_g = cout / j.groups;
+  const int cin_d = cin / dg, cout_d = cout / dg;
+  const long long items = pack_items(j.mode, cout, cin, dg);
+  const long long base = (b - j.block_start) * kItemsPerBlock;
+  for (int i = threadIdx.x; i < kItemsPerBlock; i += 256) {
+    const long long it = base + i;
+    if (it >= items) break;
+    if (j.mode == OCT_PACK_FWD) {
+      const int ci_d = (int)(it % cin_d), co = (int)(it / cin_d);
+      const int ci = (co / cout_d) * cin_d + ci_d;
+      const bool on = ci / cin_g == co / cout_g;
+      const float* src = w + ((long long)co * cin_g + (ci % cin_g)) * taps;
+      for (int t = 0; t < taps; ++t)
+        out[((long long)t * cout + co) * cin_d + ci_d] = __float2bfloat16_rn(on ? src[t] : 0.f);
+    } else if (j.mode == OCT_PACK_DGRAD) {
+      const int co_d = (int)(it % cout_d), ci = (int)(it / cout_d);
       const int co = (ci / cin_d) * cout_d + co_d;
-      if (ci / cin_g == co / cout_g) v = w[((long long)co * cin_g + (ci % cin_g)) * taps + (taps - 1 - tap)];
-    } else if (mode == OCT_PACK_CONVT_FWD) {
-      // out[(t*cout + co)][ci] = w[ci][co][t]
-      const int ci = (int)(idx % cin);
-      const int co = (int)((idx / cin) % cout);
-      const int t = (int)(idx / ((long long)cin * cout));
-      v = w[((long long)ci * cout + co) * 4 + t];
+      const bool on = ci / cin_g == co / cout_g;
+      const float* src = w + ((long long)co * cin_g + (ci % cin_g)) * taps;
+      for (int t = 0; t < taps; ++t)
+        out[((long long)t * cin + ci) * cout_d + co_d] = __float2bfloat16_rn(on ? src[taps - 1 - t] : 0.f);
+    } else if (j.mode == OCT_PACK_CONVT_FWD) {
+      const int ci = (int)(it % cin), co = (int)(it / cin);
+      const float4 v = *reinterpret_cast<const float4*>(w + ((long long)ci * cout + co) * 4);
+      out[((long long)0 * cout + co) * cin + ci] = __float2bfloat16_rn(v.x);
+      out[((long long)1 * cout + co) * cin + ci] = __float2bfloat16_rn(v.y);
+      out[((long long)2 * cout + co) * cin + ci] = __float2bfloat16_rn(v.z);
+      out[((long long)3 * cout + co) * cin + ci] = __float2bfloat16_rn(v.w);
     } else {
-      // out[ci][t*cout + co] = w[ci][co][t]
-      const int co = (int)(idx % cout);
-      const int t = (int)((idx / cout) % 4);
-      const int ci = (int)(idx / ((long long)4 * cout));
-      v = w[((long long)ci * cout + co) * 4 + t];
+      const int co = (int)(it % cout), ci = (int)(it / cout);
+      const float4 v = *reinterpret_cast<const float4*>(w + ((long long)ci * cout + co) * 4);
+      bf16* o = out + (long long)ci * 4 * cout + co;
+      o[0] = __float2bfloat16_rn(v.x);
+      o[cout] = __float2bfloat16_rn(v.y);
+      o[2 * cout] = __float2bfloat16_rn(v.z);
+      o[3 * cout] = __float2bfloat16_rn(v.w);
     }
-    out[idx] = __float2bfloat16_rn(v);
   }
 }
 
@@ -262,14 +334,24 @@ extern "C" int octave_pack_weight(const float* w, int32_t mode, int32_t cout, in
   if (!w || !out || cout <= 0 || cin <= 0 || groups <= 0 || dense_groups <= 0) return OCT_ERR_INVALID;
   if (mode < 0 || mode > 3) return OCT_ERR_INVALID;
   if (mode <= OCT_PACK_DGRAD && (cin % groups || cout % groups || groups % dense_groups)) return OCT_ERR_INVALID;
-  long long total;
-  const int taps = ksize * ksize;
-  if (mode == OCT_PACK_FWD) total = (long long)taps * cout * (cin / dense_groups);
-  else if (mode == OCT_PACK_DGRAD) total = (long long)taps * cin * (cout / dense_groups);
-  else total = 4LL * cout * cin;
+  const long long total = pack_total(mode, cout, cin, dense_groups, ksize);
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_weight_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, mode, cout, cin, groups, dense_groups, ksize, (bf16*)out);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int64_t octave_pack_job_blocks(int32_t mode, int32_t cout, int32_t cin, int32_t dense_groups, int32_t ksize) {
+  if (mode < 0 || mode > 3 || cout <= 0 || cin <= 0 || dense_groups <= 0 || ksize <= 0) return 0;
+  (void)ksize;
+  const long long items = pack_items(mode, cout, cin, dense_groups);
+  return (items + kItemsPerBlock - 1) / kItemsPerBlock;
+}
+
+extern "C" int octave_pack_weight_multi(const OctavePackJob* jobs_device, int32_t n_jobs, int64_t total_blocks, void* stream) {
+  if (!jobs_device || n_jobs <= 0 || total_blocks <= 0 || total_blocks > 0x7fffffffLL) return OCT_ERR_INVALID;
+  pack_weight_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_device, n_jobs);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

@@ -501,6 +501,8 @@ class ResnestUNet(nn.Module):
                              f"fail otherwise, compose.py:141-169)")
         dt, dev = compute_dtype(), x.device
         tape = {}
+        if dt == torch.bfloat16:
+            self._repack()
         xa = ops.nchw_to_nhwc(x, dt) if dt != torch.bfloat16 else x.detach()
         cat1 = Act.empty(B, H // 2, W // 2, 128, dt, dev)
         cat2 = Act.empty(B, H // 4, W // 4, 512, dt, dev)
@@ -631,6 +633,22 @@ class ResnestUNet(nn.Module):
         ops.add_inplace(dx00, dcat1.slice(0, 64))
         self._stem_bwd(tape["stem"], dx00, grads)
         emit()
+
+    def _repack(self) -> None:
+        """bf16 operand packs of every tensor-core conv, refreshed in one launch when the weights have changed"""
+        mp = getattr(self, "_multi_packer", None)
+        if mp is None or mp.specs[0].weight.device != self.fc.weight.device:
+            specs = []
+            for name, m in self.named_modules():
+                if name.startswith("linear_head_") or m is self.fc or name.endswith((".fc1", ".fc2")):
+                    continue   # heads / attention-branch linears do not run on the conv kernels
+                if isinstance(m, (Conv2d, ConvTranspose2d)):
+                    sp = _spec(m)
+                    if sp.tc_ok(torch.bfloat16):
+                        specs.append(sp)
+            mp = ops.MultiPacker(specs)
+            self._multi_packer = mp
+        mp.run()
 
     # ---- public interface ----------------------------------------------------------------------------
     def forward(self, x):

@@ -36,6 +36,11 @@ class PoolDesc(C.Structure):
                 ("ceil_mode", C.c_int32), ("count_include_pad", C.c_int32)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", _vp), ("out", _vp), ("mode", C.c_int32), ("cout", C.c_int32), ("cin", C.c_int32), ("groups", C.c_int32),
+                ("dense_groups", C.c_int32), ("ksize", C.c_int32), ("block_start", C.c_int64)]
+
+
 class Act:
     """NHWC channel view: pixel p, channel c at buf.data_ptr + (p*ld + coff + c) elements."""
     __slots__ = ("buf", "B", "H", "W", "C", "ld", "coff")
@@ -138,10 +143,13 @@ _sigs = {
     "octave_rsoftmax_fwd": [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
     "octave_rsoftmax_bwd": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
     "octave_pack_weight": [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+    "octave_pack_weight_multi": [_vp, C.c_int32, C.c_int64, _vp],
 }
 for _n, _a in _sigs.items():
     getattr(lib, _n).restype = C.c_int
     getattr(lib, _n).argtypes = _a
+lib.octave_pack_job_blocks.restype = C.c_int64
+lib.octave_pack_job_blocks.argtypes = [C.c_int32] * 5
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 
@@ -389,21 +397,31 @@ class ConvSpec:
             return self.cin % 32 == 0 and self.cout % 32 == 0
         return self.dense_groups > 0 and self.stride == 1 and self.k in (1, 3) and self.pad == self.k // 2
 
-    def pack(self, mode: int) -> torch.Tensor:
+    def _pack_key(self, mode: int):
         w = self.weight
-        key = (mode, w._version, w.data_ptr())
-        hit = self._packs.get(mode)
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        return (mode, w._version, w.data_ptr())
+
+    def _pack_numel(self, mode: int) -> int:
         taps = self.k * self.k
         dg = max(self.dense_groups, 1)
         if mode == _lib_pack.FWD:
-            n = taps * self.cout * (self.cin // dg)
-        elif mode == _lib_pack.DGRAD:
-            n = taps * self.cin * (self.cout // dg)
-        else:
-            n = 4 * self.cout * self.cin
-        out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+            return taps * self.cout * (self.cin // dg)
+        if mode == _lib_pack.DGRAD:
+            return taps * self.cin * (self.cout // dg)
+        return 4 * self.cout * self.cin
+
+    def pack_modes(self):
+        """operand packs the tensor-core kernels of this conv consume (forward, data gradient)"""
+        return (_lib_pack.CONVT_FWD, _lib_pack.CONVT_DGRAD) if self.transposed else (_lib_pack.FWD, _lib_pack.DGRAD)
+
+    def pack(self, mode: int) -> torch.Tensor:
+        key = self._pack_key(mode)
+        hit = self._packs.get(mode)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        w = self.weight
+        out = hit[1] if hit is not None and hit[1].device == w.device else \
+            torch.empty(self._pack_numel(mode), dtype=torch.bfloat16, device=w.device)
         wd = w.detach()
         if wd.dtype != torch.float32 or not wd.is_contiguous():
             wd = wd.float().contiguous()
@@ -411,6 +429,56 @@ class ConvSpec:
                                                           max(self.dense_groups, 1), self.k, out.data_ptr(), stream_ptr()))
         self._packs[mode] = (key, out)
         return out
+
+
+class MultiPacker:
+    """Re-packs every stale bf16 operand of a list of ConvSpecs in ONE kernel launch (the per-step re-pack after the
+    optimiser update).  The device job table is rebuilt only when a weight or pack buffer moves."""
+
+    def __init__(self, specs):
+        self.specs = [s for s in specs if s.weight.dtype == torch.float32]
+        self._sig = None
+        self._table = None
+        self._n = 0
+        self._blocks = 0
+
+    def run(self) -> None:
+        specs = self.specs
+        if not specs:
+            return
+        stale = False
+        for s in specs:
+            for m in s.pack_modes():
+                hit = s._packs.get(m)
+                if hit is None or hit[0] != s._pack_key(m):
+                    stale = True
+                    break
+            if stale:
+                break
+        if not stale:
+            return
+        dev = specs[0].weight.device
+        jobs, sig, start = [], [], 0
+        for s in specs:
+            w = s.weight
+            if not w.is_contiguous():
+                raise RuntimeError("octave_b200: conv weights must be contiguous")
+            for m in s.pack_modes():
+                hit = s._packs.get(m)
+                out = hit[1] if hit is not None and hit[1].device == dev else \
+                    torch.empty(s._pack_numel(m), dtype=torch.bfloat16, device=dev)
+                s._packs[m] = (s._pack_key(m), out)
+                dg = max(s.dense_groups, 1)
+                nb = lib.octave_pack_job_blocks(m, s.cout, s.cin, dg, s.k)
+                jobs.append((w.data_ptr(), out.data_ptr(), m, s.cout, s.cin, s.groups, dg, s.k, start))
+                sig.append((w.data_ptr(), out.data_ptr()))
+                start += nb
+        if sig != self._sig:
+            arr = (PackJob * len(jobs))(*[PackJob(*j) for j in jobs])
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+            self._table = host.to(dev)
+            self._sig, self._n, self._blocks = sig, len(jobs), start
+        _chk("octave_pack_weight_multi", lib.octave_pack_weight_multi(self._table.data_ptr(), self._n, self._blocks, stream_ptr()))
 
 
 class _lib_pack:

@@ -29,7 +29,7 @@ def enable():
         fn = getattr(_lib.lib, name)
         if not name.endswith(("_fwd", "_bwd", "_wgrad", "_dgrad", "_stats", "_prepare", "_act", "_reduce", "_apply", "_inplace",
                               "_combine", "_du", "_nhwc", "_nchw", "_window", "_depth", "_space", "_weight", "_data", "_s2d",
-                              "_noise", "_clipmask")):
+                              "_noise", "_clipmask", "_multi")):
             continue
         _orig[name] = fn
 
