@@ -5,69 +5,118 @@
 
 namespace {
 
-constexpr int BCHUNK = 8;  // batch rows processed per pass of a warp
+// ---- grouped linear layers on [B][K] vectors (fc1 / fc2 of the split-attention branch) --------------------------------
+// These GEMMs are tiny (B = batch rows, <= 17 MMAC) and latency-bound: the kernels below keep many independent 16-byte
+// loads in flight, split the contraction over the warps of a block and reuse the activation rows across output columns.
+constexpr int kJB = 8;   // output columns per block of glinear_fwd (= warps per block)
 
-// one warp per output feature j; lanes stride over the K inputs of j's group
-__global__ void glinear_fwd_kernel(const float* in, const float* w, const float* bias, int B, int Kt, int N, int groups,
-                                   float scale, float* out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const int Kg = Kt / groups, g = warp / (N / groups);
-  const float* wr = w + (long long)warp * Kg;
-  for (int b0 = 0; b0 < B; b0 += BCHUNK) {
-    float acc[BCHUNK];
+// block: kJB columns j0.. of one group; lane = batch row (blockIdx.y selects the 32-row slab); warp w = K slice w
+__global__ void __launch_bounds__(256) glinear_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int B, int Kt, int N, int groups,
+                                                          float scale, float* __restrict__ out) {
+  __shared__ float red[8][kJB][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Kg = Kt / groups, Ng = N / groups;
+  const int j0 = blockIdx.x * kJB, g = j0 / Ng;
+  const int b = blockIdx.y * 32 + lane;
+  const int bb = b < B ? b : B - 1;
+  const int Ks = Kg / 8;                    // floats of this warp's K slice (multiple of 4)
+  const float* arow = in + (long long)bb * Kt + g * Kg + warp * Ks;
+  const float* wrow = w + (long long)j0 * Kg + warp * Ks;
+  float acc[kJB];
 #pragma unroll
-    for (int r = 0; r < BCHUNK; ++r) acc[r] = 0.f;
-    for (int i = lane; i < Kg; i += 32) {
-      const float wv = wr[i];
+  for (int jj = 0; jj < kJB; ++jj) acc[jj] = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < Ks; i += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(arow + i);
 #pragma unroll
-      for (int r = 0; r < BCHUNK; ++r)
-        if (b0 + r < B) acc[r] += wv * in[(long long)(b0 + r) * Kt + g * Kg + i];
-    }
-#pragma unroll
-    for (int r = 0; r < BCHUNK; ++r) {
-      const float s = warp_sum(acc[r]);
-      if (lane == 0 && b0 + r < B) out[(long long)(b0 + r) * N + warp] = s * scale + (bias ? bias[warp] : 0.f);
+    for (int jj = 0; jj < kJB; ++jj) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + (long long)jj * Kg + i));
+      acc[jj] += a.x * wv.x + a.y * wv.y + a.z * wv.z + a.w * wv.w;
     }
   }
+#pragma unroll
+  for (int jj = 0; jj < kJB; ++jj) red[warp][jj][lane] = acc[jj];
+  __syncthreads();
+  // warp w finalises column j0 + w
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += red[k][warp][lane];
+  const int j = j0 + warp;
+  if (b < B) out[(long long)b * N + j] = sum * scale + (bias ? bias[j] : 0.f);
 }
 
-// thread per input feature i (weight reads coalesced over i), blockIdx.y splits the outputs j of i's group,
-// BCHUNK batch rows share every weight load; partial sums are merged with atomics into the zeroed din
-__global__ void glinear_bwd_data_kernel(const float* dout, const float* w, int B, int Kt, int N, int groups, float scale,
-                                        float* din) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Kt) return;
-  const int Kg = Kt / groups, Ng = N / groups, g = i / Kg, il = i - g * Kg;
-  const int chunk = (Ng + gridDim.y - 1) / gridDim.y;
-  const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, Ng);
-  for (int b0 = 0; b0 < B; b0 += BCHUNK) {
-    float acc[BCHUNK];
+// din[b][i] = scale * sum_{j in group(i)} dout[b][j] * w[j][i_local]
+// block: 32 consecutive inputs i (lane) x 8 j slices (warp); all 32 batch rows of the slab are accumulators of a thread
+constexpr int kJC = 64;   // outputs staged per pass
+__global__ void __launch_bounds__(256) glinear_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                                               int B, int Kt, int N, int groups, float scale,
+                                                               float* __restrict__ din) {
+  __shared__ __align__(16) float tile[kJC][32];     // dout^T of the current pass: [j][b]
+  __shared__ float red[8][32][33];                  // [warp][b][i]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Kg = Kt / groups, Ng = N / groups;
+  const int i = blockIdx.x * 32 + lane;             // global input index (Kt % 32 == 0)
+  const int g = i / Kg, il = i - g * Kg;
+  const int b0 = blockIdx.y * 32;
+  float acc[32];
 #pragma unroll
-    for (int r = 0; r < BCHUNK; ++r) acc[r] = 0.f;
-    for (int j = j0; j < j1; ++j) {
-      const float wv = w[(long long)(g * Ng + j) * Kg + il];
-#pragma unroll
-      for (int r = 0; r < BCHUNK; ++r)
-        if (b0 + r < B) acc[r] += dout[(long long)(b0 + r) * N + g * Ng + j] * wv;
+  for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+  // blockIdx.z splits the outputs j of the group: partial sums meet in din through atomics (din zeroed by the launcher)
+  const int jper = ((Ng + gridDim.z - 1) / gridDim.z + kJC - 1) / kJC * kJC;
+  const int jbeg = blockIdx.z * jper, jend = min(Ng, jbeg + jper);
+  for (int jc = jbeg; jc < jend; jc += kJC) {
+    __syncthreads();
+    // stage dout[b0 + r][g*Ng + jc + jj] -> tile[jj][r]   (lanes run over r: conflict-free shared stores)
+    for (int e = threadIdx.x; e < kJC * 32; e += 256) {
+      const int jj = e >> 5, r = e & 31;
+      const int bq = b0 + r;
+      tile[jj][r] = (bq < B && jc + jj < jend) ? __ldg(dout + (long long)bq * N + g * Ng + jc + jj) : 0.f;
     }
+    __syncthreads();
+    const int jn = min(kJC, jend - jc);
+#pragma unroll 2
+    for (int jj = warp; jj < jn; jj += 8) {
+      const float wv = __ldg(w + (long long)(g * Ng + jc + jj) * Kg + il);
 #pragma unroll
-    for (int r = 0; r < BCHUNK; ++r)
-      if (b0 + r < B) atomicAdd(din + (long long)(b0 + r) * Kt + i, acc[r] * scale);
+      for (int r4 = 0; r4 < 8; ++r4) {
+        const float4 d = *reinterpret_cast<const float4*>(&tile[jj][r4 * 4]);
+        acc[r4 * 4 + 0] += d.x * wv;
+        acc[r4 * 4 + 1] += d.y * wv;
+        acc[r4 * 4 + 2] += d.z * wv;
+        acc[r4 * 4 + 3] += d.w * wv;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 32; ++r) red[warp][r][lane] = acc[r];
+  __syncthreads();
+  // thread (warp, lane): rows r = warp, warp + 8, ... ; column lane
+  for (int r = warp; r < 32; r += 8) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += red[k][r][lane];
+    if (b0 + r < B) {
+      float* o = din + (long long)(b0 + r) * Kt + i;
+      if (gridDim.z > 1) atomicAdd(o, sum * scale); else *o = sum * scale;
+    }
   }
 }
 
 // one thread per (j, i)
-__global__ void glinear_bwd_weight_kernel(const float* dout, const float* in, int B, int Kt, int N, int groups,
-                                          float scale, float* dw, float* dbias) {
+__global__ void glinear_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ in, int B, int Kt, int N,
+                                          int groups, float scale, float* __restrict__ dw, float* __restrict__ dbias) {
   const int Kg = Kt / groups, Ng = N / groups;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * Kg) return;
   const int j = (int)(idx / Kg), il = (int)(idx % Kg), g = j / Ng;
   float acc = 0.f, accb = 0.f;
+  const float* dp = dout + j;
+  const float* ip = in + g * Kg + il;
+#pragma unroll 8
   for (int b = 0; b < B; ++b) {
-    const float d = dout[(long long)b * N + j];
-    acc += d * in[(long long)b * Kt + g * Kg + il];
+    const float d = __ldg(dp + (long long)b * N);
+    acc += d * __ldg(ip + (long long)b * Kt);
     accb += d;
   }
   dw[idx] = acc * scale;
@@ -260,26 +309,79 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const OctavePack
 
 }  // namespace
 
+// shapes the tiled kernels take: 8-column blocks inside one group, 8 K slices of whole float4s, 32-input blocks
+static bool glinear_tiled_ok(int Kt, int N, int groups) {
+  const int Kg = Kt / groups, Ng = N / groups;
+  return Ng % kJB == 0 && Kg % 32 == 0;
+}
+
+// fallback (any shape): one warp per output element (b, j), lanes stride over K
+__global__ void glinear_fwd_ref_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                       int B, int Kt, int N, int groups, float scale, float* __restrict__ out) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)B * N) return;
+  const int b = (int)(wid / N), j = (int)(wid % N);
+  const int Kg = Kt / groups, g = j / (N / groups);
+  const float* ip = in + (long long)b * Kt + g * Kg;
+  const float* wp = w + (long long)j * Kg;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int i = lane; i < Kg; i += 32) acc += __ldg(ip + i) * __ldg(wp + i);
+  acc = warp_sum(acc);
+  if (lane == 0) out[wid] = acc * scale + (bias ? bias[j] : 0.f);
+}
+
+// fallback (any Kg): thread per input i, blockIdx.y = slice of the outputs j, blockIdx.z = batch row; partial sums meet
+// in the zeroed din through atomics.  Serves the B = 1 power-iteration matvecs of the critic's spectral norm.
+__global__ void glinear_bwd_data_ref_kernel(const float* __restrict__ dout, const float* __restrict__ w, int B, int Kt, int N,
+                                            int groups, float scale, float* __restrict__ din) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Kt) return;
+  const int b = blockIdx.z;
+  const int Kg = Kt / groups, Ng = N / groups, g = i / Kg, il = i - g * Kg;
+  const int chunk = (Ng + gridDim.y - 1) / gridDim.y;
+  const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, Ng);
+  const float* dp = dout + (long long)b * N + g * Ng;
+  const float* wp = w + (long long)g * Ng * Kg + il;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int j = j0; j < j1; ++j) acc += __ldg(dp + j) * __ldg(wp + (long long)j * Kg);
+  atomicAdd(din + (long long)b * Kt + i, acc * scale);
+}
+
 extern "C" int octave_glinear_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t Kt, int32_t N,
                                   int32_t groups, float in_scale, float* out, void* stream) {
   if (!in || !w || !out || B <= 0 || Kt <= 0 || N <= 0 || groups <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
-  const int warps_per_block = 8;
-  glinear_fwd_kernel<<<(N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-      in, w, bias, B, Kt, N, groups, in_scale, out);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (glinear_tiled_ok(Kt, N, groups))
+    glinear_fwd_kernel<<<dim3(N / kJB, (B + 31) / 32), 256, 0, s>>>(in, w, bias, B, Kt, N, groups, in_scale, out);
+  else
+    glinear_fwd_ref_kernel<<<(unsigned)(((long long)B * N * 32 + 255) / 256), 256, 0, s>>>(in, w, bias, B, Kt, N, groups, in_scale, out);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
 
 extern "C" int octave_glinear_bwd_data(const float* dout, const float* w, int32_t B, int32_t Kt, int32_t N, int32_t groups,
                                        float in_scale, float* din, void* stream) {
-  if (!dout || !w || !din || B <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
+  if (!dout || !w || !din || B <= 0 || Kt <= 0 || N <= 0 || groups <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(din, 0, sizeof(float) * (size_t)B * Kt, s) != cudaSuccess) return OCT_ERR_LAUNCH;
-  const int Ng = N / groups;
-  int split = Ng / 16;
-  if (split < 1) split = 1;
-  if (split > 64) split = 64;
-  glinear_bwd_data_kernel<<<dim3((Kt + 127) / 128, split), 128, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din);
+  if ((Kt / groups) % 32 == 0) {
+    // enough blocks to occupy the machine: split the contraction when there are few 32-input column blocks
+    const int Ng = N / groups;
+    int split = 1;
+    while (split < 16 && (Kt / 32) * split < 96 && Ng / (split * 2) >= kJC) split *= 2;
+    if (split > 1 && cudaMemsetAsync(din, 0, sizeof(float) * (size_t)B * Kt, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+    glinear_bwd_data_kernel<<<dim3(Kt / 32, (B + 31) / 32, split), 256, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din);
+  }
+  else {
+    if (B > 65535) return OCT_ERR_UNSUPPORTED;
+    if (cudaMemsetAsync(din, 0, sizeof(float) * (size_t)B * Kt, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+    const int Ng = N / groups;
+    int split = (Ng + 15) / 16;
+    if (split > 128) split = 128;
+    glinear_bwd_data_ref_kernel<<<dim3((Kt + 127) / 128, split, B), 128, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din);
+  }
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
