@@ -234,14 +234,19 @@ def run_gpu(args):
         host.append((x.pin_memory(), ys.pin_memory(), [r.pin_memory() for r in real]))
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4 + sum(r.numel() * 4 for r in host[0][2])
 
+    # one CUDA graph per step on a single GPU; data-parallel runs launch eagerly (capturing the bucketed NCCL
+    # all-reduces together with the autograd backward hung at N=2 in this round: not enabled)
+    use_graph = not args.no_graph and world == 1
+
     def one_step(i, e2e: bool, dev_batches=None):
         if e2e:
-            xh, yh, rh = host[i % nb]
-            x = xh.to(dev, non_blocking=True); ys = yh.to(dev, non_blocking=True)
-            real = [r.to(dev, non_blocking=True) for r in rh]
+            x, ys, real = host[i % nb]          # pinned host buffers: the H2D copies are part of the step
+            if not use_graph:
+                x = x.to(dev, non_blocking=True); ys = ys.to(dev, non_blocking=True)
+                real = [r.to(dev, non_blocking=True) for r in real]
         else:
             x, ys, real = dev_batches[i % nb]
-        res = ts.step(x, ys, real)
+        res = ts.step_graphed(x, ys, real) if use_graph else ts.step(x, ys, real)
         if e2e:
             return float(res['total'].item())     # device -> host read of the step's loss
         return res['total']
@@ -269,7 +274,10 @@ def run_gpu(args):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps, _lib.lib.octave_launch_count() - l0
+        n_launch = _lib.lib.octave_launch_count() - l0
+        if use_graph and getattr(ts, "_graph", None) is not None:
+            n_launch = steps * ts.graph_kernel_nodes      # replayed kernel nodes of this library (host-side counter sees none)
+        return float(ms.item()) / steps, n_launch
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -291,6 +299,9 @@ def run_gpu(args):
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
     }
+    line["config"]["cuda_graph"] = bool(use_graph and getattr(ts, "_graph", None) is not None)
+    if use_graph and getattr(ts, "graph_error", None):
+        line["config"]["cuda_graph_error"] = ts.graph_error
     if rank == 0:
         line["clocks"] = sampler.summary()
         flops = 3.0 * FLOP_PER_IMG_FWD.get(H, 158e9 * (H * W) / 160000.0) * B
@@ -338,6 +349,7 @@ if __name__ == "__main__":
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the ~1100 kernels of a step eagerly instead of replaying one CUDA graph")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -49,6 +49,48 @@ class LabelNoise(nn.Module):
         return bool(rand_uniform() < self.prob)                               # blocks.py:165-167
 
 
+class HostRandomFeed:
+    """Static pinned + device buffers for the per-call CPU draws of InstanceNoise / LabelNoise.  With a feed installed
+    (`DiscriminatorBlock._rand_feed`) a forward call takes its noise plane and label-flip sign from slot k of these
+    buffers instead of drawing: `draw()` makes the very same CPU draws in the same order for all the calls of one step,
+    `upload()` is the (capturable) host-to-device copy.  A captured CUDA graph of the training step therefore sees fresh
+    host randomness at every replay while the CPU generator advances exactly as in eager mode."""
+
+    def __init__(self, disc: "DiscriminatorBlock", n_calls: int, device):
+        self.disc, self.n_calls, self.slot = disc, n_calls, 0
+        inst = disc._inst
+        self.has_noise = inst is not None and inst.is_training
+        if self.has_noise:
+            self.noise_pin = [torch.empty(inst.size, dtype=torch.float32).pin_memory() for _ in range(n_calls)]
+            self.noise_dev = [torch.empty(inst.size, dtype=torch.float32, device=device) for _ in range(n_calls)]
+        self.sign_pin = torch.ones(n_calls, dtype=torch.float32).pin_memory()
+        self.sign_dev = torch.ones(n_calls, dtype=torch.float32, device=device)
+
+    def draw(self) -> None:
+        d = self.disc
+        for k in range(self.n_calls):
+            if d._inst is not None:
+                noise = d._inst.draw()
+                if self.has_noise:
+                    self.noise_pin[k].copy_(noise)
+            if d._label is not None:
+                self.sign_pin[k] = -1.0 if d._label.draw_flip() else 1.0
+
+    def upload(self) -> None:
+        if self.has_noise:
+            for k in range(self.n_calls):
+                self.noise_dev[k].copy_(self.noise_pin[k], non_blocking=True)
+        self.sign_dev.copy_(self.sign_pin, non_blocking=True)
+        self.slot = 0
+
+    def next(self):
+        k = self.slot
+        if k >= self.n_calls:
+            raise RuntimeError("octave_b200: more discriminator calls in one step than the random feed was sized for")
+        self.slot += 1
+        return (self.noise_dev[k] if self.has_noise else None), self.sign_dev[k:k + 1]
+
+
 class _DiscFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net: "DiscriminatorBlock", n_maps: int, *args):
@@ -145,12 +187,18 @@ class DiscriminatorBlock(nn.Module):
 
     # ---- tensor-core path: every 4x4 s2 conv becomes a 3x3 conv over a space-to-depth input -----------------
     def _noise_and_flip(self, dev):
-        noise_dev, clip = None, False
+        """-> (noise plane on the device or None, clip flag, flip): flip is a host bool, or — with a HostRandomFeed
+        installed — a one-element device tensor holding the sign (+1 / -1) the logits are multiplied with."""
+        feed = getattr(self, "_rand_feed", None)
+        clip = self._inst.clipping if self._inst is not None else False
+        if feed is not None:
+            noise_dev, sign = feed.next()
+            return noise_dev, clip, (sign if self._label is not None else False)
+        noise_dev = None
         if self._inst is not None:
             noise = self._inst.draw()
             if self._inst.is_training:
                 noise_dev = noise.pin_memory().to(dev, non_blocking=True)
-            clip = self._inst.clipping
         flip = self._label.draw_flip() if self._label is not None else False
         return noise_dev, clip, flip
 
@@ -203,14 +251,18 @@ class DiscriminatorBlock(nn.Module):
             raise RuntimeError(f"octave_b200: final feature map {s.H}x{s.W} != output kernel {kh}x{kw}")
         w_hwc = fc.weight.detach().float().permute(0, 2, 3, 1).reshape(-1).contiguous()
         logits = ops.rowdot_fwd(s, w_hwc, fc.bias.detach().float())
-        if flip:
+        if isinstance(flip, Tensor):
+            logits = logits * flip                                                        # :167-168, sign as data
+        elif flip:
             logits = -1 * logits
         tape["levels"], tape["out"], tape["flip"] = levels, (s, w_hwc), flip
         return logits, tape
 
     def _bwd_tc(self, tape, g: Tensor, grads: Grads, need_params: bool, need_maps: bool):
         g = g.contiguous().float()
-        if tape["flip"]:
+        if isinstance(tape["flip"], Tensor):
+            g = g * tape["flip"]
+        elif tape["flip"]:
             g = -1 * g
         s_last, w_hwc = tape["out"]
         fc = self.out[0]

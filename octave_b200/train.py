@@ -170,3 +170,66 @@ class TrainStep:
         if self.has_d and real is not None:
             res['discriminator'] = self.d_step(real, res['attentions'])
         return res
+
+    # ---- whole step as one CUDA graph ---------------------------------------------------------------------------
+    def step_graphed(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> Dict[str, Tensor]:
+        """Same arithmetic as `step`, replayed from one captured CUDA graph (forward, losses, backward, gradient
+        all-reduce, optimiser steps, weight re-pack): ~1100 kernel launches cost one graph launch.  Inputs are copied into
+        static device buffers (x / ys / real may live in pinned host memory); the returned tensors are static too and are
+        overwritten by the next call.  The critic's per-call CPU randomness is drawn on the host before every replay in
+        the eager order (discriminator.HostRandomFeed), so the CPU generator advances exactly as in eager mode.
+        Falls back to `step` (and says so in `self.graph_error`) when capture is not possible."""
+        if getattr(self, "_graph", None) is None and getattr(self, "graph_error", None) is None:
+            self._capture(x, ys, real)
+        if self._graph is None:
+            dev = next(self.net.parameters()).device
+            return self.step(x.to(dev, non_blocking=True), ys.to(dev, non_blocking=True), [r.to(dev, non_blocking=True) for r in real])
+        self._sx.copy_(x, non_blocking=True)
+        self._sys.copy_(ys, non_blocking=True)
+        for d, r in zip(self._sreal, real):
+            d.copy_(r, non_blocking=True)
+        if self._feed is not None:
+            self._feed.draw()
+        self._graph.replay()
+        return self._sout
+
+    def _capture(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> None:
+        from .discriminator import HostRandomFeed
+        self._graph, self.graph_error, self._feed = None, None, None
+        net = self.net
+        dev = next(net.parameters()).device
+        try:
+            if not self.has_d or not net.discriminator._use_tc():
+                raise RuntimeError("graph mode needs the bf16 tensor-core critic path")
+            if self.reducer is not None:
+                raise RuntimeError("graph mode is single-GPU: the bucketed NCCL all-reduce is launched eagerly")
+            self._sx = x.to(dev).clone()
+            self._sys = ys.to(dev).clone()
+            self._sreal = [r.to(dev).clone() for r in real]
+            self._feed = HostRandomFeed(net.discriminator, 3, dev)       # D(fake) in the G-step, D(real) + D(fake) in the D-step
+            net.discriminator._rand_feed = self._feed
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                                        # warm-up on a side stream (allocator, lazy state)
+                    self._feed.draw(); self._feed.upload()
+                    self.step(self._sx, self._sys, self._sreal)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            from . import _lib
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.lib.octave_launch_count()             # (no host draw here: capture executes nothing)
+            with torch.cuda.graph(g):
+                self._feed.upload()
+                out = self.step(self._sx, self._sys, self._sreal)
+            self.graph_kernel_nodes = int(_lib.lib.octave_launch_count() - l0)   # this library's kernels per replay
+            out.pop('attentions', None)
+            self._sout = out
+            self._graph = g
+        except Exception as e:  # capture is an optimisation: keep training eagerly, but say why
+            self.graph_error = repr(e)[:500]
+            self._graph = None
+            if self.has_d and getattr(net.discriminator, "_rand_feed", None) is not None:
+                net.discriminator._rand_feed = None
+            self._feed = None
+            torch.cuda.synchronize()
