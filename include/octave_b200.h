@@ -181,10 +181,12 @@ int octave_affine_act(const OctaveAct* x, const float* ab, const OctaveAct* res,
 int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
                          const float* mean_invstd, double* sums2, void* stream);
 /* dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or gamma*invstd*dz (eval, mean_invstd then
- * holds the running statistics).  dgamma = sum dz*xhat, dbeta = sum dz (nullable) are overwritten. */
+ * holds the running statistics).  dgamma = sum dz*xhat, dbeta = sum dz (nullable) are overwritten.
+ * dmasked (nullable): also store dz = dy * (mask > 0) itself — the gradient of the residual branch that was added
+ * before the ReLU (resnest.py:42,264-265), saving the separate octave_relu_bwd pass over dy and the mask. */
 int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
                         const float* mean_invstd, const float* gamma, const double* sums2, int32_t training,
-                        const OctaveAct* dx, float* dgamma, float* dbeta, void* stream);
+                        const OctaveAct* dx, float* dgamma, float* dbeta, const OctaveAct* dmasked, void* stream);
 /* dst += src (same shape); used where gradients of two branches merge. */
 int octave_add_inplace(const OctaveAct* dst, const OctaveAct* src, void* stream);
 /* dst = src * (mask > 0) */
@@ -238,8 +240,10 @@ int octave_nhwc_to_nchw_clipmask(const OctaveAct* src, const float* x, const flo
                                  void* stream);
 /* dst(h,w) = [accumulate ? dst : 0] + (h < src.H && w < src.W ? src(h,w) : 0): zero-pad (compose.py:125-130) and crop. */
 int octave_copy_window(const OctaveAct* src, const OctaveAct* dst, int32_t accumulate, void* stream);
-/* space-to-depth by 2: dst[h][w][(i*2+j)*C + c] = src[2h+i][2w+j][c] (0 outside src) — data-gradient view of ConvT k2s2 */
-int octave_space_to_depth(const OctaveAct* src, const OctaveAct* dst, void* stream);
+/* space-to-depth by 2: dst[h][w][(i*2+j)*C + c] = src[2h+i][2w+j][c] (0 outside src) — data-gradient view of ConvT k2s2.
+ * chan_sum (nullable, fp64 [C], overwritten): per-channel sum of src = the ConvTranspose2d bias gradient
+ * (Upsampling.up.bias, resnest.py:50), fused because this pass reads every element of the output gradient once. */
+int octave_space_to_depth(const OctaveAct* src, const OctaveAct* dst, double* chan_sum, void* stream);
 /* inverse: dst[2h+i][2w+j][c] = src[h][w][(i*2+j)*C + c] for the pixels that exist in dst (fp32-mode ConvT k2s2) */
 int octave_depth_to_space(const OctaveAct* src, const OctaveAct* dst, void* stream);
 

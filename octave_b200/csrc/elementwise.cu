@@ -304,7 +304,8 @@ template <typename T, int MASK>
 __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bn_bwd_apply_kernel(const OctaveAct dy, const OctaveAct mask, int Gb,
                                                               const float* ab, const OctaveAct x, const float* mi,
                                                               const float* gamma, const double* sums2, int training,
-                                                              const OctaveAct dx, float* dgamma, float* dbeta) {
+                                                              const OctaveAct dx, float* dgamma, float* dbeta,
+                                                              const OctaveAct dmasked, int has_dm) {
   const Tix t = make_tix<U_BNA>(x, Gb);
   const float inv_n = 1.f / ((float)x.B * (float)x.H * (float)x.W);
   float P[8], Q[8], R[8], aa[8], bb[8];
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) bn_bwd_apply_kern
 #pragma unroll
           for (int i = 0; i < 8; ++i) d[i] = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? d[i] : 0.f;
         }
+        if (has_dm) VecIO<T, 8>::st(at<T>(dmasked, t.base + q, t.cg * 8), d);   // dy * (mask > 0): the residual branch's gradient
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = P[i] * d[i] + (Q[i] * f[i] + R[i]);
         VecIO<T, 8>::st(at<T>(dx, t.base + q, t.cg * 8), d);
@@ -631,18 +633,20 @@ extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, 
 template <typename T, int MASK>
 static int launch_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* m, const float* relu_ab, const OctaveAct* x,
                                const float* mi, const float* gamma, const double* sums2, int training,
-                               const OctaveAct* dx, float* dgamma, float* dbeta, cudaStream_t s) {
+                               const OctaveAct* dx, float* dgamma, float* dbeta, const OctaveAct* dmasked, cudaStream_t s) {
   auto fn = bn_bwd_apply_kernel<T, MASK>;
   Geo g;
   if (!make_geo(x, &g, U_BNA, false, ONE_WAVE(fn, 256, 0))) return OCT_ERR_UNSUPPORTED;
-  fn<<<g.grid, g.bs, 0, s>>>(*dy, *m, g.Gb, relu_ab, *x, mi, gamma, sums2, training, *dx, dgamma, dbeta);
+  fn<<<g.grid, g.bs, 0, s>>>(*dy, *m, g.Gb, relu_ab, *x, mi, gamma, sums2, training, *dx, dgamma, dbeta,
+                             dmasked ? *dmasked : *dx, dmasked != nullptr);
   return OCT_OK;
 }
 
 extern "C" int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
                                    const float* mean_invstd, const float* gamma, const double* sums2, int32_t training,
-                                   const OctaveAct* dx, float* dgamma, float* dbeta, void* stream) {
+                                   const OctaveAct* dx, float* dgamma, float* dbeta, const OctaveAct* dmasked, void* stream) {
   if (!view_ok(dy) || !view_ok(x) || !view_ok(dx) || !same_shape(dy, x) || !same_shape(dx, x)) return OCT_ERR_INVALID;
+  if (dmasked && (!view_ok(dmasked) || !same_shape(dmasked, x))) return OCT_ERR_INVALID;
   if (!mean_invstd || !sums2) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, x))) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
@@ -650,9 +654,9 @@ extern "C" int octave_bn_bwd_apply(const OctaveAct* dy, const OctaveAct* mask, c
   const int mmode = mask ? 1 : (relu_ab ? 2 : 0);
   int rc = OCT_OK;
   DISPATCH_T(x->dtype, {
-    if (mmode == 0) rc = launch_bn_bwd_apply<T, 0>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, s);
-    else if (mmode == 1) rc = launch_bn_bwd_apply<T, 1>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, s);
-    else rc = launch_bn_bwd_apply<T, 2>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, s);
+    if (mmode == 0) rc = launch_bn_bwd_apply<T, 0>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, dmasked, s);
+    else if (mmode == 1) rc = launch_bn_bwd_apply<T, 1>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, dmasked, s);
+    else rc = launch_bn_bwd_apply<T, 2>(dy, m, relu_ab, x, mean_invstd, gamma, sums2, training, dx, dgamma, dbeta, dmasked, s);
   });
   if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();

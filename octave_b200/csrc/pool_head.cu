@@ -433,10 +433,16 @@ __global__ void copy_window_kernel(const OctaveAct src, const OctaveAct dst, int
   }
 }
 
+// chan_sum (nullable, fp64 [C], pre-zeroed): per-channel sum of src over all pixels — the bias gradient of the
+// ConvTranspose2d whose output gradient is being rearranged (every src element is read exactly once here).
 template <typename T>
-__global__ void space_to_depth_kernel(const OctaveAct src, const OctaveAct dst) {
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const OctaveAct src, const OctaveAct dst, double* chan_sum) {
+  __shared__ float sm[8 * 256];
   const int G = src.C >> 3;
   const long long total = (long long)dst.B * dst.H * dst.W * 4 * G;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % G);
     long long r = idx / G;
@@ -450,6 +456,16 @@ __global__ void space_to_depth_kernel(const OctaveAct src, const OctaveAct dst) 
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
     if (sh < src.H && sw < src.W) VecIO<T, 8>::ld(at<T>(src, (n * src.H + sh) * src.W + sw, cg * 8), v);
     VecIO<T, 8>::st(at<T>(dst, pix, t * src.C + cg * 8), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+  if (chan_sum) {
+    // launcher guarantees 256 % G == 0: a thread keeps the channel group tid % G for the whole grid-stride loop
+    fold_lanes<8>(acc, sm, G);
+    if (threadIdx.x < G) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(chan_sum + threadIdx.x * 8 + i, (double)acc[i]);
+    }
   }
 }
 
@@ -699,10 +715,16 @@ extern "C" int octave_copy_window(const OctaveAct* src, const OctaveAct* dst, in
   return OCT_OK;
 }
 
-extern "C" int octave_space_to_depth(const OctaveAct* src, const OctaveAct* dst, void* stream) {
+extern "C" int octave_space_to_depth(const OctaveAct* src, const OctaveAct* dst, double* chan_sum, void* stream) {
   if (!view_ok(src) || !view_ok(dst) || dst->C != 4 * src->C || src->B != dst->B || src->dtype != dst->dtype) return OCT_ERR_INVALID;
-  const long long total = (long long)dst->B * dst->H * dst->W * 4 * (src->C / 8);
-  DISPATCH_T(dst->dtype, (space_to_depth_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*src, *dst)));
+  const int G = src->C / 8;
+  if (chan_sum && (G > 256 || 256 % G)) return OCT_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (chan_sum && cudaMemsetAsync(chan_sum, 0, sizeof(double) * src->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  const long long total = (long long)dst->B * dst->H * dst->W * 4 * G;
+  int grid = grid_for(total, 256);
+  if (chan_sum && grid > 148 * 8) grid = 148 * 8;    // bounds the atomics per channel
+  DISPATCH_T(dst->dtype, (space_to_depth_kernel<T><<<grid, 256, 0, s>>>(*src, *dst, chan_sum)));
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

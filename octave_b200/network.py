@@ -68,14 +68,14 @@ def bn_fwd(bn: BatchNorm2d, z: Act, training: bool, relu: bool, res: Optional[Ac
     return y, (bn, z, mi, ab, training, relu and res is None, y), gap
 
 
-def bn_bwd(ctx, dy: Act, mask: Optional[Act], grads: Grads, out: Optional[Act] = None) -> Act:
+def bn_bwd(ctx, dy: Act, mask: Optional[Act], grads: Grads, out: Optional[Act] = None, dmasked: Optional[Act] = None) -> Act:
     """mask: the activation whose ReLU gates dy.  When it is this BN's own output (y = relu(BN(z)), no residual) the
     mask is recomputed from z inside the kernels instead of being read (one tensor pass less in each kernel)."""
     bn, z, mi, ab, training, relu_self, y = ctx
     relu_ab = None
     if mask is not None and relu_self and mask is y:
         mask, relu_ab = None, ab
-    dz, dg, db = ops.bn_bwd(dy, mask, z, mi, bn.weight.detach(), training, out, relu_ab)
+    dz, dg, db = ops.bn_bwd(dy, mask, z, mi, bn.weight.detach(), training, out, relu_ab, dmasked)
     _acc(grads, bn.weight, dg)
     _acc(grads, bn.bias, db)
     return dz
@@ -200,7 +200,9 @@ class Bottleneck(nn.Module):
 
     def bwd(self, ctx, dy: Act, grads: Grads) -> Act:
         x, y1, c1, c2, s, sp, c3, cd, y = ctx
-        dz3 = bn_bwd(c3, dy, y, grads)
+        # identity shortcut: its gradient dy * (y > 0) comes out of the same pass as bn3's input gradient
+        dres = dy.like() if cd is None else None
+        dz3 = bn_bwd(c3, dy, y, grads, dmasked=dres)
         dsp = conv_bwd(self.conv3, sp, dz3, grads)
         ds = ops.pool_bwd(self._avd_pd, dsp, None, s.H, s.W) if self.avd else dsp
         dy1 = self.conv2.bwd(c2, ds, grads)
@@ -212,7 +214,7 @@ class Bottleneck(nn.Module):
             dr = conv_bwd(convd, r, dzr, grads)
             dx = ops.pool_bwd(pd, dr, None, x.H, x.W) if r is not x else dr
         else:
-            dx = ops.relu_bwd(dy, y)
+            dx = dres
         conv_bwd(self.conv1, x, dz1, grads, dx_out=dx, accumulate=True)
         return dx
 
@@ -325,8 +327,8 @@ class ResNestDecoder(nn.Module):
 
     def bwd(self, ctx, dy: Act, grads: Grads) -> Act:
         x, y0, c0, cs, s, cr, y = ctx
-        dzr = bn_bwd(cr, dy, y, grads)
-        dsum = ops.relu_bwd(dy, y)
+        dsum = dy.like()
+        dzr = bn_bwd(cr, dy, y, grads, dmasked=dsum)      # dsum = dy * (y > 0): gradient of the split-attention branch
         dy0 = self.conv[3].bwd(cs, dsum, grads)
         dz0 = bn_bwd(c0, dy0, y0, grads, out=dy0)
         dx = conv_bwd(self.conv[0], x, dz0, grads)

@@ -110,7 +110,7 @@ _sigs = {
     "octave_bn_prepare": [C.c_int32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_int32, _vp, _vp, _vp],
     "octave_affine_act": [_A, _vp, _A, C.c_int32, _A, _vp, _vp],
     "octave_bn_bwd_reduce": [_A, _A, _vp, _A, _vp, _vp, _vp],
-    "octave_bn_bwd_apply": [_A, _A, _vp, _A, _vp, _vp, _vp, C.c_int32, _A, _vp, _vp, _vp],
+    "octave_bn_bwd_apply": [_A, _A, _vp, _A, _vp, _vp, _vp, C.c_int32, _A, _vp, _vp, _A, _vp],
     "octave_add_inplace": [_A, _A, _vp],
     "octave_relu_bwd": [_A, _A, _A, _vp],
     "octave_splat_combine": [_A, _vp, C.c_int32, _A, _vp],
@@ -127,7 +127,7 @@ _sigs = {
     "octave_nchw_to_nhwc_noise": [_vp, C.c_int32, _vp, C.c_int32, _A, _vp],
     "octave_nhwc_to_nchw_clipmask": [_A, _vp, _vp, C.c_int32, _vp, _vp],
     "octave_copy_window": [_A, _A, C.c_int32, _vp],
-    "octave_space_to_depth": [_A, _A, _vp],
+    "octave_space_to_depth": [_A, _A, _vp, _vp],
     "octave_depth_to_space": [_A, _A, _vp],
     "octave_nchw_to_s2d": [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32, _A, C.c_int32, C.c_int32, _vp],
     "octave_s2d_to_nchw": [_A, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp],
@@ -178,15 +178,16 @@ def affine_act(x: Act, ab: Optional[torch.Tensor], res: Optional[Act], relu: boo
 
 
 def bn_bwd(dy: Act, mask: Optional[Act], x: Act, mi: torch.Tensor, gamma: Optional[torch.Tensor], training: bool,
-           out: Optional[Act] = None, relu_ab: Optional[torch.Tensor] = None):
-    """-> dx, dgamma, dbeta.  relu_ab (with mask None): recompute this BN's own ReLU mask from x instead of reading it."""
+           out: Optional[Act] = None, relu_ab: Optional[torch.Tensor] = None, dmasked: Optional[Act] = None):
+    """-> dx, dgamma, dbeta.  relu_ab (with mask None): recompute this BN's own ReLU mask from x instead of reading it.
+    dmasked: also receives dy * (mask > 0) (the residual branch's gradient)."""
     sums2 = torch.empty(2 * x.C, dtype=torch.float64, device=x.device)
     _chk("octave_bn_bwd_reduce", lib.octave_bn_bwd_reduce(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), sums2.data_ptr(), stream_ptr()))
     dx = out if out is not None else x.like()
     dgamma = torch.empty(x.C, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(x.C, dtype=torch.float32, device=x.device)
     _chk("octave_bn_bwd_apply", lib.octave_bn_bwd_apply(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), _p(gamma), sums2.data_ptr(),
-                                                        int(training), _ref(dx), dgamma.data_ptr(), dbeta.data_ptr(), stream_ptr()))
+                                                        int(training), _ref(dx), dgamma.data_ptr(), dbeta.data_ptr(), _ref(dmasked), stream_ptr()))
     return dx, dgamma, dbeta
 
 
@@ -363,9 +364,15 @@ def copy_window(src: Act, dst: Act, accumulate: bool = False) -> None:
     _chk("octave_copy_window", lib.octave_copy_window(_ref(src), _ref(dst), int(accumulate), stream_ptr()))
 
 
-def space_to_depth(src: Act, H: int, W: int) -> Act:
+def space_to_depth(src: Act, H: int, W: int, want_chan_sum: bool = False):
+    """-> dst, or (dst, per-channel fp64 sum of src) with want_chan_sum"""
     dst = Act.empty(src.B, H, W, 4 * src.C, src.dtype, src.device)
-    _chk("octave_space_to_depth", lib.octave_space_to_depth(_ref(src), _ref(dst), stream_ptr()))
+    G = src.C // 8
+    fused = want_chan_sum and G <= 256 and 256 % G == 0
+    cs = torch.empty(src.C, dtype=torch.float64, device=src.device) if fused else None
+    _chk("octave_space_to_depth", lib.octave_space_to_depth(_ref(src), _ref(dst), _p(cs), stream_ptr()))
+    if want_chan_sum:
+        return dst, (cs if fused else chan_stats(src)[:src.C])
     return dst
 
 
@@ -601,7 +608,8 @@ def conv_dgrad_direct(dy: Act, spec: ConvSpec, H: int, W: int) -> Act:
 
 def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
     """Backward of ConvTranspose2d(k=2,s=2): dy (possibly cropped view [B,Ho,Wo,cout]) -> (dx, dW [Cin,Cout,2,2], dbias)."""
-    dys = space_to_depth(dy, x.H, x.W)  # [B,H,W,4*cout], zeros where dy was cropped
+    # [B,H,W,4*cout], zeros where dy was cropped; the same pass yields the bias gradient sum_pixels dy
+    dys, dy_sum = space_to_depth(dy, x.H, x.W, want_chan_sum=spec.bias is not None) if spec.bias is not None else (space_to_depth(dy, x.H, x.W), None)
     if not spec.tc_ok(x.dtype):
         w4 = _f32(spec.weight).permute(2, 3, 1, 0).reshape(4 * spec.cout, spec.cin, 1, 1).contiguous()
         dw4 = torch.empty_like(w4)
@@ -619,7 +627,7 @@ def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
     dw = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
     d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, 1, 1, 1, 0, x, dys, x.H, x.W, mode=_lib.CONV_MODE_CONVT)
     _chk("octave_conv_tc_wgrad(convT)", lib.octave_conv_tc_wgrad(C.byref(d), x.buf.data_ptr(), dys.buf.data_ptr(), dw.data_ptr(), stream_ptr()))
-    db = chan_stats(dy)[:spec.cout].float() if spec.bias is not None else None
+    db = dy_sum.float() if spec.bias is not None else None
     dx = None
     if need_dx:
         dx = Act.empty(x.B, x.H, x.W, spec.cin, x.dtype, x.device)
