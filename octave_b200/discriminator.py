@@ -157,19 +157,40 @@ class DiscriminatorBlock(nn.Module):
         return self.out[2] if self._has_label else None
 
     # ---- spectral norm (torch.nn.utils.spectral_norm legacy semantics, n_power_iterations=1, eps=1e-12) ----
-    def _spectral_weight(self, conv: nn.Module):
+    def _spectral_weight(self, conv: nn.Module, need_w: bool = True):
+        """-> (W_orig / sigma or None, sigma, u, v) after one power iteration in training mode."""
         w = conv.weight_orig.detach()
         wm = w.reshape(w.shape[0], -1).float().contiguous()
         u, v = conv.weight_u, conv.weight_v
         if self.training:
             v_new = ops.glinear_bwd_data_only(u.reshape(1, -1), wm)          # W^T u
             v_new = v_new / v_new.norm().clamp_min(1e-12)
-            u_new = ops.glinear_fwd(v_new, wm, None, 1, 1.0)                  # W v
-            u_new = u_new / u_new.norm().clamp_min(1e-12)
+            wv = ops.glinear_fwd(v_new, wm, None, 1, 1.0)                     # W v
+            u_new = wv / wv.norm().clamp_min(1e-12)
             u.copy_(u_new.reshape(-1)); v.copy_(v_new.reshape(-1))
-        wv = ops.glinear_fwd(v.reshape(1, -1).contiguous(), wm, None, 1, 1.0).reshape(-1)
+            wv = wv.reshape(-1)                                               # = W v for the updated v: reused for sigma
+        else:
+            wv = ops.glinear_fwd(v.reshape(1, -1).contiguous(), wm, None, 1, 1.0).reshape(-1)
         sigma = (u * wv).sum()
-        return w.float() / sigma, sigma, u.clone(), v.clone()
+        return (w.float() / sigma if need_w else None), sigma, u.clone(), v.clone()
+
+    def _padded_squeeze(self, i: int, rows: int):
+        """13-row squeeze conv weight / bias zero-padded to `rows` output channels for the tensor-core kernels; rebuilt
+        only when the parameter changes (once per optimiser step, not once per critic call)."""
+        sq = self.squeeze_dict[f'squeeze_{i}'][0]
+        cache = self.__dict__.setdefault("_sq_cache", {})
+        key = (sq.weight._version, sq.weight.data_ptr(), sq.bias._version, sq.bias.data_ptr())
+        hit = cache.get((i, rows))
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        dev = sq.weight.device
+        wpad = torch.zeros((rows, sq.in_channels, 1, 1), dtype=torch.float32, device=dev)
+        wpad[:13] = sq.weight.detach()
+        bpad = torch.zeros(rows, dtype=torch.float32, device=dev)
+        bpad[:13] = sq.bias.detach()
+        spec = ConvSpec(wpad, None, sq.in_channels, rows, 1, 1, 0, 1)
+        cache[(i, rows)] = (key, spec, bpad)
+        return spec, bpad
 
     # ---- explicit passes -------------------------------------------------------------------------------
     def _use_tc(self) -> bool:
@@ -230,14 +251,10 @@ class DiscriminatorBlock(nn.Module):
                 raise Exception(f'Exception raised in depth = {i}')
             h, w = s.H, s.W
             catS = Act.zeros(B, (h + 1) // 2, (w + 1) // 2, 64, dt, dev)                   # quadrant stride 16: 13 + Cin (+pad)
-            w16 = torch.zeros((16, sq.in_channels, 1, 1), dtype=torch.float32, device=dev)
-            w16[:13] = sq.weight.detach()
-            b16 = torch.zeros(16, dtype=torch.float32, device=dev)
-            b16[:13] = sq.bias.detach()
-            spec_sq = ConvSpec(w16, None, sq.in_channels, 16, 1, 1, 0, 1)
+            spec_sq, b16 = self._padded_squeeze(i, 16)
             ops.conv1x1_tc_s2d_store(s, spec_sq.pack(0), b16, 16, catS, 16, ops.ACT_SIGMOID)   # :121
             ops.nchw_to_s2d(yi.detach(), catS, 16, 13)                                    # :122 (overwrites pad channels 13,14)
-            w_sn, sigma, u, v = self._spectral_weight(sn)
+            _, sigma, u, v = self._spectral_weight(sn, need_w=False)
             inv_sigma = (1.0 / sigma).reshape(1).float()
             wo_ = sn.weight_orig.detach()
             ho, wo = (h + 2 - 4) // 2 + 1, (w + 2 - 4) // 2 + 1
@@ -293,9 +310,7 @@ class DiscriminatorBlock(nn.Module):
             # finite don't-care values of the mask / pad quadrant channels, 16..31 zeros) and meet zero weight rows
             dsq32 = Act.zeros(catS.B, h, w, 32, catS.dtype, catS.device)
             ops._chk("octave_depth_to_space", ops.lib.octave_depth_to_space(ops._ref(dcatS), ops._ref(dsq32.slice(0, 16)), ops.stream_ptr()))
-            w32 = torch.zeros((32, sq.in_channels, 1, 1), dtype=torch.float32, device=catS.device)
-            w32[:13] = sq.weight.detach()
-            spec_sq = ConvSpec(w32, None, sq.in_channels, 32, 1, 1, 0, 1)
+            spec_sq, _ = self._padded_squeeze(i, 32)
             if need_params:
                 dwq, _ = ops.conv_wgrad(s_in, dsq32, spec_sq)
                 _acc(grads, sq.weight, dwq[:13].contiguous())
