@@ -247,6 +247,8 @@ def run_gpu(args):
         else:
             x, ys, real = dev_batches[i % nb]
         res = ts.step_graphed(x, ys, real) if use_graph else ts.step(x, ys, real)
+        if e2e and use_graph:
+            ts.prefetch(*host[(i + 1) % nb])      # input pipelining: next batch's H2D overlaps this step's compute
         if e2e:
             return float(res['total'].item())     # device -> host read of the step's loss
         return res['total']

@@ -184,14 +184,44 @@ class TrainStep:
         if self._graph is None:
             dev = next(self.net.parameters()).device
             return self.step(x.to(dev, non_blocking=True), ys.to(dev, non_blocking=True), [r.to(dev, non_blocking=True) for r in real])
-        self._sx.copy_(x, non_blocking=True)
-        self._sys.copy_(ys, non_blocking=True)
-        for d, r in zip(self._sreal, real):
+        pf = getattr(self, "_prefetched", None)
+        if pf is not None and pf[0] is x and pf[1] is ys:
+            # this batch was uploaded by prefetch() while the previous step computed: device-to-device hand-over
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
+            src_x, src_ys, src_real = self._stage
+            self._prefetched = None
+        else:
+            src_x, src_ys, src_real = x, ys, real
+        self._sx.copy_(src_x, non_blocking=True)
+        self._sys.copy_(src_ys, non_blocking=True)
+        for d, r in zip(self._sreal, src_real):
             d.copy_(r, non_blocking=True)
+        if getattr(self, "_copy_stream", None) is not None:
+            self._handover.record()          # staging buffers are free again once these copies have run
         if self._feed is not None:
             self._feed.draw()
         self._graph.replay()
         return self._sout
+
+    def prefetch(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> None:
+        """Start the host-to-device upload of the NEXT batch (pinned host tensors) on a copy stream so that it overlaps
+        the step that is computing now; the following `step_graphed(x, ys, real)` with the same tensors picks it up with a
+        device-to-device copy.  No-op until the graph exists."""
+        if getattr(self, "_graph", None) is None:
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._handover = torch.cuda.Event()
+            self._handover.record()
+            self._stage = (torch.empty_like(self._sx), torch.empty_like(self._sys), [torch.empty_like(r) for r in self._sreal])
+        cs = self._copy_stream
+        cs.wait_event(self._handover)        # only the last hand-over reads the staging buffers — NOT the running replay
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(x, non_blocking=True)
+            self._stage[1].copy_(ys, non_blocking=True)
+            for d, r in zip(self._stage[2], real):
+                d.copy_(r, non_blocking=True)
+        self._prefetched = (x, ys)
 
     def _capture(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> None:
         from .discriminator import HostRandomFeed
