@@ -135,6 +135,10 @@ int octave_conv_halo_supported(const OctaveConvDesc* d);
 int octave_conv_halo_fwd(const OctaveConvDesc* d, const void* x, const void* wpack, const float* bias, void* y,
                          double* stats, void* stream);
 void octave_conv_halo_config(int32_t enabled, int32_t base_off_mode);
+/* Narrow-layer variant of octave_conv_tc_wgrad (3x3 s1 p1, channels per group in {32, 64} with one side 32): one CTA
+ * keeps all nine tap accumulators in TMEM and loads every dy / x patch once.  octave_conv_tc_wgrad forwards to it. */
+int octave_conv_halo_wgrad_supported(const OctaveConvDesc* d);
+int octave_conv_halo_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dw, void* stream);
 /* dw: fp32 gradient in the torch parameter layout ([Cout][Cin/real_groups][k][k]; ConvT: [Cin][Cout][2][2]),
  * overwritten unless `accumulate`.  x = forward input view, dy = output-gradient view (x_* / y_* of the descriptor;
  * for ConvT dy is the space-to-depth view with 4*cout channels). */

@@ -284,6 +284,181 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient of the same narrow 3x3 layers.  dW[tap][co][ci] = sum_pixels dy[p][co] * x[p + tap][ci]: the GEMM K
+// dimension is the pixel index, so with the flattened-patch indexing of the forward kernel (row i = oh * 32 + ow of a
+// 4 x 30 output patch, pitch 32) BOTH operands are MN-major views of two TMA boxes — the dy patch (128 rows) and the x
+// patch with halo (192 rows) — and the nine taps are nine row offsets into the SAME x tile.  One CTA owns a contiguous
+// range of patches and keeps all nine tap accumulators in TMEM (9 x 32 columns): per patch it loads dy once and x once
+// (the generic kernel loads both nine times, from nine CTAs) and issues 9 taps x 8 K-steps of 128 x 32 x 16 MMAs.
+// The two junk columns of every patch row (ow = 30, 31: real pixels of the neighbouring patch) are zeroed in the dy
+// tile by the MMA warp before it issues, so they contribute nothing.  The side with 32 channels is the N operand; the
+// other side (32 or 64 channels) is the M operand, padded to 128 rows by aliasing (those accumulator rows are not read).
+// ---------------------------------------------------------------------------------------------------
+struct HaloWgradParams {
+  int tiles_w, tiles_h, B;
+  int groups;                 // dense groups (blockIdx.y)
+  int cin_g, cout_g;          // per dense group
+  int real_cin_g, real_cout_g;
+  int x_is_n;                 // 1: x (Cin_g = 32) is the N operand, dy the M operand; 0: dy (Cout_g = 32) is N, x is M
+  int total_tiles;            // B * tiles_h * tiles_w
+  int tiles_per_cta;
+  float* dw;                  // [Cout][Cin/real_groups][3][3], pre-zeroed
+};
+
+constexpr int kHwThreads = 6 * 32;   // warp 0 TMA producer, warp 1 MMA (+ junk-row zeroing), warps 2..5 epilogue
+constexpr int kHwTWp = 32, kHwTW = 30, kHwTH = 4;
+
+template <int CY, int CX, int STAGES>    // channels per group of dy / x (32 or 64)
+__global__ void __launch_bounds__(kHwThreads, 1) conv3x3_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                                           const __grid_constant__ CUtensorMap tmX,
+                                                                           const HaloWgradParams p) {
+  constexpr int ROWY = CY * 2, ROWX = CX * 2;                 // bytes per pixel row = swizzle span
+  constexpr int Y_ROWS = kHwTH * kHwTWp;                      // 128
+  constexpr int X_ROWS = (kHwTH + 2) * kHwTWp;                // 192
+  constexpr int Y_BYTES = Y_ROWS * ROWY;
+  constexpr int X_BYTES = ((X_ROWS + 8) * ROWX + 1023) & ~1023;  // + rows read past the box by the last taps
+  constexpr int STAGE_BYTES = Y_BYTES + X_BYTES;
+  constexpr int TMEM_COLS = 512;                              // 9 taps x 32 columns
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
+  const int g = blockIdx.y;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(t_begin + p.tiles_per_cta, p.total_tiles);
+  const int n_iter = t_end - t_begin;
+
+  // rows [X_ROWS, X_ROWS + 8) of every x stage are read (against zeroed dy rows) but never written by TMA: keep them zero
+  for (int st = 0; st < STAGES; ++st) {
+    uint8_t* q = smem_gen + st * STAGE_BYTES + Y_BYTES + X_ROWS * ROWX;
+    for (int i = threadIdx.x * 16; i < 8 * ROWX; i += kHwThreads * 16) *reinterpret_cast<uint4*>(q + i) = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+      tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+    }
+    tc::mbar_init(tc::smem_u32(&acc_bar), 1);
+    tc::fence_barrier_init();
+    tc::tma_prefetch_desc(&tmDY);
+    tc::tma_prefetch_desc(&tmX);
+  }
+  tc::fence_proxy_async();
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_slot));
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  if (n_iter <= 0) {  // uniform across the CTA
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    return;
+  }
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    const bool leader = tc::elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    int img = t_begin / tiles_per_img;
+    int trem = t_begin - img * tiles_per_img;
+    for (int it = 0; it < n_iter; ++it) {
+      tc::mbar_wait(tc::smem_u32(&empty_bar[s]), ph ^ 1u);
+      const uint32_t fb = tc::smem_u32(&full_bar[s]);
+      const int th_i = trem / p.tiles_w;
+      const int h0 = th_i * kHwTH, w0 = (trem - th_i * p.tiles_w) * kHwTW;
+      const uint32_t sa = smem_base + s * STAGE_BYTES;
+      if (leader) {
+        tc::mbar_arrive_expect_tx(fb, (uint32_t)(Y_ROWS * ROWY + X_ROWS * ROWX));
+        tc::tma_load_4d(sa, &tmDY, fb, g * CY, w0, h0, img);
+        tc::tma_load_4d(sa + Y_BYTES, &tmX, fb, g * CX, w0 - 1, h0 - 1, img);
+      }
+      if (++trem == tiles_per_img) { trem = 0; ++img; }
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc = tc::umma_idesc_bf16(128, 32, 1, 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      tc::mbar_wait(tc::smem_u32(&full_bar[s]), ph);
+      // zero the junk rows of the dy tile (ow = 30, 31 of each of the 4 patch rows): 8 rows x ROWY bytes
+      {
+        uint8_t* yb = smem_gen + s * STAGE_BYTES;
+        constexpr int V = ROWY / 16;                       // uint4 per row
+        for (int e = lane; e < 8 * V; e += 32) {
+          const int jr = e / V, v = e - jr * V;
+          const int row = (jr >> 1) * kHwTWp + kHwTW + (jr & 1);
+          *reinterpret_cast<uint4*>(yb + row * ROWY + v * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      tc::fence_after_sync();
+      const uint32_t sy = smem_base + s * STAGE_BYTES, sx = sy + Y_BYTES;
+      // MN-major operands: LBO (distance between 64-element MN chunks) = 0 aliases the padding chunks onto the real one
+      const uint64_t dY = tc::umma_smem_desc(sy, ROWY, 0);
+      const uint64_t dX = tc::umma_smem_desc(sx, ROWX, 0);
+      if (leader) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t xoff = (uint32_t)(((tap / 3) * kHwTWp + (tap % 3)) * ROWX) >> 4;
+#pragma unroll
+          for (int k = 0; k < Y_ROWS / 16; ++k) {
+            const uint64_t ay = dY + (uint32_t)(k * ROWY);            // 16 pixel rows further
+            const uint64_t ax = dX + xoff + (uint32_t)(k * ROWX);
+            if (p.x_is_n) tc::umma_bf16(tmem_base + tap * 32, ay, ax, idesc, (it | k) != 0);
+            else          tc::umma_bf16(tmem_base + tap * 32, ax, ay, idesc, (it | k) != 0);
+          }
+        }
+        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+      }
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    if (leader) tc::umma_commit(tc::smem_u32(&acc_bar));
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;   // accumulator row = channel of the M operand
+    const int m_ch = p.x_is_n ? p.cout_g : p.cin_g;
+    tc::mbar_wait(tc::smem_u32(&acc_bar), 0);
+    tc::fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(taddr + tap * 32 + c0, v);
+        tc::tmem_ld_wait();
+        if (r < m_ch) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = c0 + i;
+            const int co = g * p.cout_g + (p.x_is_n ? r : n);
+            const int ci = g * p.cin_g + (p.x_is_n ? n : r);
+            if (ci / p.real_cin_g == co / p.real_cout_g)
+              atomicAdd(p.dw + ((long long)co * p.real_cin_g + (ci % p.real_cin_g)) * 9 + tap, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 halo_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -429,4 +604,106 @@ extern "C" int octave_conv_halo_fwd(const OctaveConvDesc* d, const void* x, cons
   }
   if (cout_g == 64) return launch_halo<64, 32>(tmA, tmW, p, (int)grid, s);
   return launch_halo<32, 32>(tmA, tmW, p, (int)grid, s);
+}
+
+template <int CY, int CX, int STAGES>
+static int launch_halo_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const HaloWgradParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int ROWY = CY * 2, ROWX = CX * 2;
+  constexpr int stage = 128 * ROWY + (((192 + 8) * ROWX + 1023) & ~1023);
+  constexpr int smem = STAGES * stage + 1024;
+  static_assert(smem <= 226 * 1024, "shared memory budget");
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv3x3_halo_wgrad_kernel<CY, CX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return OCT_ERR_LAUNCH;
+    attr_done = true;
+  }
+  conv3x3_halo_wgrad_kernel<CY, CX, STAGES><<<grid, kHwThreads, smem, s>>>(tmDY, tmX, p);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+// 1 when the halo weight-gradient kernel takes this descriptor: 3x3 s1 p1, channels per (dense) group in {32, 64} with
+// at least one side 32, not accumulate
+extern "C" int octave_conv_halo_wgrad_supported(const OctaveConvDesc* d) {
+  if (g_halo_enabled < 0) {
+    const char* e = getenv("OCTAVE_HALO");
+    g_halo_enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!g_halo_enabled || !d) return 0;
+  // Opt-in (OCTAVE_HALO_WGRAD=1).  Measured on B200 (tools/probe_halo.py, B=32): it cuts the L2->SM traffic ~5x but not
+  // the time (400^2 64->32: 774 vs 751 us generic; 400^2 32->64: 786 vs 916 us; 200^2: 3-10 % slower): both kernels issue
+  // the same 72 tcgen05.mma (128x32x16) per 128-pixel patch and such small-N MMAs cost ~64 cycles each whatever the
+  // operand source, which puts the floor at ~2x the HBM time of these layers.
+  static int wg_on = -1;
+  if (wg_on < 0) {
+    const char* e = getenv("OCTAVE_HALO_WGRAD");
+    wg_on = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (!wg_on) return 0;
+  if (d->ksize != 3 || d->mode != OCT_CONV_MODE_CONV || d->accumulate) return 0;
+  if (d->groups <= 0 || d->cin % d->groups || d->cout % d->groups) return 0;
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  if ((cin_g != 32 && cin_g != 64) || (cout_g != 32 && cout_g != 64)) return 0;
+  if (cin_g != 32 && cout_g != 32) return 0;
+  if (d->x_ld % 8 || d->x_coff % 8 || d->y_ld % 8 || d->y_coff % 8) return 0;
+  if (d->Hout != d->H || d->Wout != d->W) return 0;
+  if ((long long)d->B * d->H * d->W < 4096) return 0;   // tiny maps: the generic split-K kernel is fine
+  return 1;
+}
+
+extern "C" int octave_conv_halo_wgrad(const OctaveConvDesc* d, const void* x, const void* dy, float* dw, void* stream) {
+  if (!octave_conv_halo_wgrad_supported(d)) return OCT_ERR_UNSUPPORTED;
+  if (!x || !dy || !dw) return OCT_ERR_INVALID;
+  auto enc = halo_encode();
+  if (!enc) return OCT_ERR_LAUNCH;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+  const int real_groups = d->real_groups > 0 ? d->real_groups : d->groups;
+  HaloWgradParams p{};
+  p.tiles_w = (d->W + kHwTW - 1) / kHwTW;
+  p.tiles_h = (d->H + kHwTH - 1) / kHwTH;
+  p.B = d->B;
+  p.groups = d->groups;
+  p.cin_g = cin_g; p.cout_g = cout_g;
+  p.real_cin_g = d->cin / real_groups; p.real_cout_g = d->cout / real_groups;
+  p.x_is_n = cin_g == 32 ? 1 : 0;
+  p.total_tiles = d->B * p.tiles_w * p.tiles_h;
+  int sms = octave_sm_count();
+  if (sms <= 0) sms = 148;
+  int ctas = sms / d->groups;
+  if (ctas < 1) ctas = 1;
+  if (ctas > p.total_tiles) ctas = p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + ctas - 1) / ctas;
+  ctas = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.dw = dw;
+  CUtensorMap tmDY, tmX;
+  {
+    const bf16* yb = reinterpret_cast<const bf16*>(dy) + d->y_coff;
+    cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->y_ld * 2, (cuuint64_t)d->y_ld * 2 * d->W, (cuuint64_t)d->y_ld * 2 * d->W * d->H};
+    cuuint32_t box[4] = {(cuuint32_t)cout_g, (cuuint32_t)kHwTWp, (cuuint32_t)kHwTH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(yb), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz_of(cout_g * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return OCT_ERR_LAUNCH;
+  }
+  {
+    const bf16* xb = reinterpret_cast<const bf16*>(x) + d->x_coff;
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)d->x_ld * 2 * d->W, (cuuint64_t)d->x_ld * 2 * d->W * d->H};
+    cuuint32_t box[4] = {(cuuint32_t)cin_g, (cuuint32_t)kHwTWp, (cuuint32_t)(kHwTH + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(xb), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz_of(cin_g * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return OCT_ERR_LAUNCH;
+  }
+  const size_t wbytes = (size_t)d->cout * p.real_cin_g * 9 * sizeof(float);
+  if (cudaMemsetAsync(dw, 0, wbytes, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  dim3 grid(ctas, d->groups);
+  if (cout_g == 64) return launch_halo_wgrad<64, 32, 5>(tmDY, tmX, p, grid, s);
+  if (cin_g == 64) return launch_halo_wgrad<32, 64, 5>(tmDY, tmX, p, grid, s);
+  return launch_halo_wgrad<32, 32, 6>(tmDY, tmX, p, grid, s);
 }

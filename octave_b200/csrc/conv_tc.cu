@@ -739,6 +739,7 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   if (rc != OCT_OK) return rc;
   if (!octave_conv_tc_wgrad_supported(d)) return OCT_ERR_UNSUPPORTED;
   if (!x || !dy || !dw) return OCT_ERR_INVALID;
+  if (octave_conv_halo_wgrad_supported(d)) return octave_conv_halo_wgrad(d, x, dy, dw, stream);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool convt = d->mode == OCT_CONV_MODE_CONVT;
   const int cout_all = convt ? 4 * d->cout : d->cout;

@@ -13,8 +13,9 @@ def run(B, H, W, cin, cout, groups, mode, want_stats=True):
     y, st = ops.conv_fwd(x, spec, want_stats=want_stats)
     dx = ops.conv_dgrad(y, spec, H, W)
     dx2 = ops.conv_dgrad(y, spec, H, W, out=Act(dx.buf.clone(), B, H, W, cin), accumulate=True)
+    dw, _ = ops.conv_wgrad(x, y, spec)
     torch.cuda.synchronize()
-    return y.buf.float(), (st.clone() if st is not None else None), dx.buf.float(), dx2.buf.float()
+    return y.buf.float(), (st.clone() if st is not None else None), dx.buf.float(), dx2.buf.float(), dw.float()
 
 def timeit(fn, reps=10):
     for _ in range(3): fn()
@@ -48,7 +49,7 @@ for mode in MODES:
             if a is None: continue
             a = a.double(); b = b.double()
             errs.append(float((a - b).abs().max() / (a.abs().max() + 1e-9)))
-        print(shp, "rel max err (y, stats, dx, dx_acc):", ["%.2e" % e for e in errs])
+        print(shp, "rel max err (y, stats, dx, dx_acc, dw):", ["%.2e" % e for e in errs])
 HM = MODES[0]
 for (B, H, cin, cout, g) in [(32, 400, 64, 32, 1), (32, 400, 32, 64, 1), (32, 200, 32, 64, 1), (32, 200, 64, 128, 2), (32, 200, 32, 32, 1), (32, 100, 64, 64, 1)]:
     x = Act(torch.randn(B, H, H, cin, device=dev).bfloat16(), B, H, H, cin)
@@ -61,4 +62,9 @@ for (B, H, cin, cout, g) in [(32, 400, 64, 32, 1), (32, 400, 32, 64, 1), (32, 20
         ms = timeit(lambda: ops.conv_fwd(x, spec, out=y, want_stats=True))
         res.append(ms)
     byts = 2.0 * B * H * H * (cin + cout)
-    print(f"B{B} {H}x{H} {cin}->{cout} g{g}: generic {res[0]*1e3:7.1f} us  halo {res[1]*1e3:7.1f} us  ({byts/res[1]/1e6:.0f} GB/s min-traffic)")
+    resw = []
+    for en in (0, 1):
+        lib.octave_conv_halo_config(en, HM)
+        resw.append(timeit(lambda: ops.conv_wgrad(x, y, spec)))
+    print(f"B{B} {H}x{H} {cin}->{cout} g{g}: fwd generic {res[0]*1e3:7.1f} us  halo {res[1]*1e3:7.1f} us  ({byts/res[1]/1e6:.0f} GB/s) | "
+          f"wgrad generic {resw[0]*1e3:7.1f} us  halo {resw[1]*1e3:7.1f} us")
