@@ -408,15 +408,32 @@ __global__ void __launch_bounds__(kHwThreads, 1) conv3x3_halo_wgrad_kernel(const
       const uint64_t dY = tc::umma_smem_desc(sy, ROWY, 0);
       const uint64_t dX = tc::umma_smem_desc(sx, ROWX, 0);
       if (leader) {
+        if (p.x_is_n) {
+          // x is the N operand (32 channels per pixel row, one 64-byte MN run): the three taps of a filter row are three
+          // MN runs ONE pixel row (64 B) apart — leading-dimension byte offset = ROWX — so one 128 x 96 x 16 MMA covers
+          // dw = 0, 1, 2 at once: 24 MMAs per patch instead of 72 (a small-N tcgen05.mma costs ~64 cycles regardless of N)
+          constexpr uint32_t idesc3 = tc::umma_idesc_bf16(128, 96, 1, 1);
+          const uint64_t dX3 = tc::umma_smem_desc(sx, ROWX, ROWX);
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t xoff = (uint32_t)(((tap / 3) * kHwTWp + (tap % 3)) * ROWX) >> 4;
+          for (int dh = 0; dh < 3; ++dh) {
+            const uint32_t xoff = (uint32_t)(dh * kHwTWp * ROWX) >> 4;
 #pragma unroll
-          for (int k = 0; k < Y_ROWS / 16; ++k) {
-            const uint64_t ay = dY + (uint32_t)(k * ROWY);            // 16 pixel rows further
-            const uint64_t ax = dX + xoff + (uint32_t)(k * ROWX);
-            if (p.x_is_n) tc::umma_bf16(tmem_base + tap * 32, ay, ax, idesc, (it | k) != 0);
-            else          tc::umma_bf16(tmem_base + tap * 32, ax, ay, idesc, (it | k) != 0);
+            for (int k = 0; k < Y_ROWS / 16; ++k)
+              tc::umma_bf16(tmem_base + dh * 96, dY + (uint32_t)(k * ROWY), dX3 + xoff + (uint32_t)(k * ROWX), idesc3, (it | k) != 0);
+          }
+        } else {
+          // x is the M operand (64 channels = one 128-byte MN run per pixel row; M = 128 takes two runs): two taps per MMA,
+          // the second run being the first one shifted by the tap distance (leading-dimension byte offset).  Groups:
+          // (dh,0)+(dh,1) for dh = 0..2 [one row apart], (0,2)+(1,2) [one patch row apart], (2,2) alone [aliased].
+#pragma unroll
+          for (int gi = 0; gi < 5; ++gi) {
+            const int first = gi < 3 ? gi * 3 : (gi == 3 ? 2 : 8);
+            const uint32_t lbo = gi < 3 ? (uint32_t)ROWX : (gi == 3 ? (uint32_t)(kHwTWp * ROWX) : 0u);
+            const uint64_t dXg = tc::umma_smem_desc(sx, ROWX, lbo);
+            const uint32_t xoff = (uint32_t)(((first / 3) * kHwTWp + (first % 3)) * ROWX) >> 4;
+#pragma unroll
+            for (int k = 0; k < Y_ROWS / 16; ++k)
+              tc::umma_bf16(tmem_base + gi * 32, dXg + xoff + (uint32_t)(k * ROWX), dY + (uint32_t)(k * ROWY), idesc, (it | k) != 0);
           }
         }
         tc::umma_commit(tc::smem_u32(&empty_bar[s]));
@@ -431,21 +448,45 @@ __global__ void __launch_bounds__(kHwThreads, 1) conv3x3_halo_wgrad_kernel(const
     tc::mbar_wait(tc::smem_u32(&acc_bar), 0);
     tc::fence_after_sync();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (p.x_is_n) {
+      // accumulator column = tap * 32 + ci (dh * 96 + dw * 32 + ci); row = output channel
 #pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
+      for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        uint32_t v[16];
-        tc::tmem_ld16(taddr + tap * 32 + c0, v);
-        tc::tmem_ld_wait();
-        if (r < m_ch) {
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tc::tmem_ld16(taddr + tap * 32 + c0, v);
+          tc::tmem_ld_wait();
+          if (r < m_ch) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = c0 + i;
-            const int co = g * p.cout_g + (p.x_is_n ? r : n);
-            const int ci = g * p.cin_g + (p.x_is_n ? n : r);
-            if (ci / p.real_cin_g == co / p.real_cout_g)
-              atomicAdd(p.dw + ((long long)co * p.real_cin_g + (ci % p.real_cin_g)) * 9 + tap, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) {
+              const int co = g * p.cout_g + r, ci = g * p.cin_g + c0 + i;
+              if (ci / p.real_cin_g == co / p.real_cout_g)
+                atomicAdd(p.dw + ((long long)co * p.real_cin_g + (ci % p.real_cin_g)) * 9 + tap, __uint_as_float(v[i]));
+            }
+          }
+        }
+      }
+    } else {
+      // five tap groups of 32 columns (output channels); rows 0..63 = first tap of the group, 64..127 = second tap
+#pragma unroll 1
+      for (int gi = 0; gi < 5; ++gi) {
+        const int first = gi < 3 ? gi * 3 : (gi == 3 ? 2 : 8);
+        const int second = gi < 3 ? first + 1 : (gi == 3 ? 5 : -1);
+        const int tap = r < 64 ? first : second;
+        const int ci = g * p.cin_g + (r & 63);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t v[16];
+          tc::tmem_ld16(taddr + gi * 32 + c0, v);
+          tc::tmem_ld_wait();
+          if (tap >= 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int co = g * p.cout_g + c0 + i;
+              if (ci / p.real_cin_g == co / p.real_cout_g)
+                atomicAdd(p.dw + ((long long)co * p.real_cin_g + (ci % p.real_cin_g)) * 9 + tap, __uint_as_float(v[i]));
+            }
           }
         }
       }
@@ -631,14 +672,14 @@ extern "C" int octave_conv_halo_wgrad_supported(const OctaveConvDesc* d) {
     g_halo_enabled = (e && atoi(e) == 0) ? 0 : 1;
   }
   if (!g_halo_enabled || !d) return 0;
-  // Opt-in (OCTAVE_HALO_WGRAD=1).  Measured on B200 (tools/probe_halo.py, B=32): it cuts the L2->SM traffic ~5x but not
-  // the time (400^2 64->32: 774 vs 751 us generic; 400^2 32->64: 786 vs 916 us; 200^2: 3-10 % slower): both kernels issue
-  // the same 72 tcgen05.mma (128x32x16) per 128-pixel patch and such small-N MMAs cost ~64 cycles each whatever the
-  // operand source, which puts the floor at ~2x the HBM time of these layers.
+  // Measured on B200 (tools/probe_halo.py, B=32).  With nine separate taps this kernel cut the L2->SM traffic ~5x but
+  // not the time (774 vs 751 us on 400^2 64->32): a small-N tcgen05.mma costs ~64 cycles whatever its operands, and both
+  // kernels issued 72 of them per 128-pixel patch.  Pairing taps inside one MMA (24 / 40 MMAs per patch) is what pays:
+  // 400^2 32->64 790 -> 329 us, 200^2 32->64 208 -> 108 us, 200^2 64->128 g2 401 -> 171 us.  OCTAVE_HALO_WGRAD=0 disables.
   static int wg_on = -1;
   if (wg_on < 0) {
     const char* e = getenv("OCTAVE_HALO_WGRAD");
-    wg_on = (e && atoi(e) != 0) ? 1 : 0;
+    wg_on = e ? atoi(e) : 1;       // 0: always the generic weight-gradient kernel
   }
   if (!wg_on) return 0;
   if (d->ksize != 3 || d->mode != OCT_CONV_MODE_CONV || d->accumulate) return 0;
