@@ -206,6 +206,15 @@ int octave_splat_bwd_reduce(const OctaveAct* dout, const OctaveAct* mask, const 
 int octave_splat_bwd_du(const OctaveAct* dout, const OctaveAct* mask, const float* att, const float* dgap,
                         float gap_scale, const OctaveAct* dU, void* stream);
 
+/* Backward of SplAtConv2d's combine + bn0 + ReLU in two passes over z (resnest.py:101-105,133-135): the gradient of U,
+ *   dU[p][r*C+c] = att[b][r*C+c] * dout[p][c] * (omask[p][c] > 0) + dgap[b][c] * gap_scale,
+ * is rebuilt on the fly from dout instead of being written and re-read.  z: bn0 input [B,H,W,2C]; ab / mean_invstd: the
+ * [2*2C] scale-shift and statistics octave_bn_prepare produced in the forward pass (the ReLU mask is z*a+b > 0).
+ * Outputs: dz (gradient w.r.t. z), dgamma / dbeta [2C], sums2 (fp64 [2*2C] scratch, overwritten). */
+int octave_splat_bn_bwd(const OctaveAct* dout, const OctaveAct* omask, const float* att, const float* dgap, float gap_scale,
+                        const OctaveAct* z, const float* ab, const float* mean_invstd, const float* gamma, int32_t training,
+                        double* sums2, const OctaveAct* dz, float* dgamma, float* dbeta, void* stream);
+
 /* K6 pools (NHWC).  kind 0: MaxPool2d; 1: AvgPool2d.  Exact torch semantics incl. ceil_mode and
  * count_include_pad (resnest.py:340 maxpool 3/2/1; :189 avd AvgPool 3/s/1; :383 shortcut AvgPool s/s ceil, no pad count). */
 typedef struct OctavePoolDesc {

@@ -534,6 +534,145 @@ __global__ void __launch_bounds__(256) splat_bwd_du_kernel(const OctaveAct dout,
   }
 }
 
+// ---- split-attention backward fused with the backward of its BatchNorm (bn0) -----------------------------------------
+// dU[p][r*C+c] = att[b][r*C+c] * dout[p][c] * (omask > 0) + dgap[b][c] * gap_scale   (splat_bwd_du) is never written:
+// both BatchNorm-backward passes rebuild it from dout (C channels) while they stream z (2C channels), so the backward of
+// SplAtConv2d.bn0 + relu (resnest.py:101-105) costs z twice + dz once instead of seven passes over 2C-wide tensors.
+// blockIdx.y = image, blockIdx.z = radix half r.  The ReLU mask of bn0 is recomputed from z (y = z*a + b > 0).
+constexpr int U_SBR = 4;   // reduce pass: loads per thread and tensor in flight
+constexpr int U_SBA = 3;   // apply pass
+template <typename T, bool HAS_OMASK>
+__global__ void __launch_bounds__(256, 2) splat_bn_bwd_reduce_kernel(const OctaveAct dout, const OctaveAct omask, int Gb,
+                                                                     const float* att, const float* dgap, float gap_scale,
+                                                                     const OctaveAct z, const float* ab, const float* mi,
+                                                                     double* sums2) {
+  extern __shared__ float sm[];
+  const int C = dout.C, C2 = 2 * C, r = blockIdx.z;
+  Tix t = make_tix<U_SBR>(dout, Gb);
+  t.cg = threadIdx.x % Gb;                   // blockIdx.z is the radix half here, not a channel slab
+  const int c0 = r * C + t.cg * 8;           // first of this thread's 8 channels in the 2C-wide tensors
+  float mean[8], v[16], aa[8], bb[8], at8[8], gg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean[i] = mi[c0 + i];
+    aa[i] = ab[c0 + i];
+    bb[i] = ab[C2 + c0 + i];
+    at8[i] = att[(long long)blockIdx.y * C2 + c0 + i];
+    gg[i] = dgap ? dgap[(long long)blockIdx.y * C + t.cg * 8 + i] * gap_scale : 0.f;
+    v[i] = v[8 + i] = 0.f;
+  }
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> rd[U_SBR], rz[U_SBR], rm[HAS_OMASK ? U_SBR : 1];
+#pragma unroll
+    for (int u = 0; u < U_SBR; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        rd[u].ld(at<T>(dout, t.base + q, t.cg * 8));
+        rz[u].ld(at<T>(z, t.base + q, c0));
+        if (HAS_OMASK) rm[u].ld(at<T>(omask, t.base + q, t.cg * 8));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U_SBR; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float d[8], f[8];
+        rd[u].get(d);
+        rz[u].get(f);
+        if (HAS_OMASK) {
+          float m[8];
+          rm[u].get(m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // dU rounded to storage precision like the unfused path stored it, then gated by bn0's own ReLU
+          float du = to_f(from_f<T>(at8[i] * d[i] + gg[i]));
+          du = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? du : 0.f;
+          v[i] += du;
+          v[8 + i] += du * (f[i] - mean[i]);
+        }
+      }
+    }
+  }
+  fold_lanes<16>(v, sm, Gb);
+  if (threadIdx.x < Gb) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(sums2 + c0 + i, (double)v[i]);
+      atomicAdd(sums2 + C2 + c0 + i, (double)v[8 + i] * (double)mi[C2 + c0 + i]);
+    }
+  }
+}
+
+template <typename T, bool HAS_OMASK>
+__global__ void __launch_bounds__(256, 2) splat_bn_bwd_apply_kernel(const OctaveAct dout, const OctaveAct omask, int Gb,
+                                                                    const float* att, const float* dgap, float gap_scale,
+                                                                    const OctaveAct z, const float* ab, const float* mi,
+                                                                    const float* gamma, const double* sums2, int training,
+                                                                    const OctaveAct dz, float* dgamma, float* dbeta) {
+  const int C = dout.C, C2 = 2 * C, r = blockIdx.z;
+  Tix t = make_tix<U_SBA>(dout, Gb);
+  t.cg = threadIdx.x % Gb;                   // blockIdx.z is the radix half here, not a channel slab
+  const int c0 = r * C + t.cg * 8;
+  const float inv_n = 1.f / ((float)z.B * (float)z.H * (float)z.W);
+  float P[8], Q[8], R[8], aa[8], bb[8], at8[8], gg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    const float mean = mi[c], inv = mi[C2 + c];
+    aa[i] = ab[c];
+    bb[i] = ab[C2 + c];
+    at8[i] = att[(long long)blockIdx.y * C2 + c];
+    gg[i] = dgap ? dgap[(long long)blockIdx.y * C + t.cg * 8 + i] * gap_scale : 0.f;
+    const float sd = (float)sums2[c], sdx = (float)sums2[C2 + c];
+    const float k1 = training ? sd * inv_n : 0.f;
+    const float k2 = training ? sdx * inv_n : 0.f;
+    P[i] = (gamma ? gamma[c] : 1.f) * inv;
+    Q[i] = -P[i] * inv * k2;
+    R[i] = -P[i] * k1 - Q[i] * mean;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && t.lane == 0) {
+      if (dgamma) dgamma[c] = sdx;
+      if (dbeta) dbeta[c] = sd;
+    }
+  }
+  for (long long p = t.first; p < t.n; p += t.stride) {
+    Raw8<T> rd[U_SBA], rz[U_SBA], rm[HAS_OMASK ? U_SBA : 1];
+#pragma unroll
+    for (int u = 0; u < U_SBA; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        rd[u].ld(at<T>(dout, t.base + q, t.cg * 8));
+        rz[u].ld(at<T>(z, t.base + q, c0));
+        if (HAS_OMASK) rm[u].ld(at<T>(omask, t.base + q, t.cg * 8));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U_SBA; ++u) {
+      const long long q = p + (long long)u * t.ppb;
+      if (q < t.n) {
+        float d[8], f[8];
+        rd[u].get(d);
+        rz[u].get(f);
+        if (HAS_OMASK) {
+          float m[8];
+          rm[u].get(m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float du = to_f(from_f<T>(at8[i] * d[i] + gg[i]));
+          du = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? du : 0.f;
+          d[i] = P[i] * du + (Q[i] * f[i] + R[i]);
+        }
+        VecIO<T, 8>::st(at<T>(dz, t.base + q, c0), d);
+      }
+    }
+  }
+}
+
 #define DISPATCH_T(dtype, ...)                         \
   do {                                                 \
     if ((dtype) == OCT_DTYPE_F32) { using T = float; __VA_ARGS__; } \
@@ -762,6 +901,45 @@ extern "C" int octave_splat_bwd_du(const OctaveAct* dout, const OctaveAct* mask,
       fn<<<g.grid, g.bs, 0, (cudaStream_t)stream>>>(*dout, m, g.Gb, att, dgap, gap_scale, *dU);
     }
   });
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_splat_bn_bwd(const OctaveAct* dout, const OctaveAct* omask, const float* att, const float* dgap,
+                                   float gap_scale, const OctaveAct* z, const float* ab, const float* mean_invstd,
+                                   const float* gamma, int32_t training, double* sums2, const OctaveAct* dz, float* dgamma,
+                                   float* dbeta, void* stream) {
+  if (!view_ok(dout) || !view_ok(z) || !view_ok(dz) || !att || !ab || !mean_invstd || !sums2) return OCT_ERR_INVALID;
+  if (z->C != 2 * dout->C || z->B != dout->B || z->H != dout->H || z->W != dout->W || z->dtype != dout->dtype) return OCT_ERR_INVALID;
+  if (!same_shape(z, dz)) return OCT_ERR_INVALID;
+  if (omask && (!view_ok(omask) || !same_shape(omask, dout))) return OCT_ERR_INVALID;
+  if (dout->C / 8 > 256) return OCT_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * z->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  OctaveAct m = omask ? *omask : *dout;
+  Geo g;
+  DISPATCH_T(dout->dtype, {
+    if (omask) {
+      auto fr = splat_bn_bwd_reduce_kernel<T, true>;
+      auto fa = splat_bn_bwd_apply_kernel<T, true>;
+      if (!make_geo(dout, &g, U_SBR, true, ONE_WAVE(fr, 256, 16 * 256 * sizeof(float)) / 2, 4)) return OCT_ERR_UNSUPPORTED;
+      g.grid.z = 2;
+      fr<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*dout, m, g.Gb, att, dgap, gap_scale, *z, ab, mean_invstd, sums2);
+      if (!make_geo(dout, &g, U_SBA, true, ONE_WAVE(fa, 256, 0) / 2)) return OCT_ERR_UNSUPPORTED;
+      g.grid.z = 2;
+      fa<<<g.grid, g.bs, 0, s>>>(*dout, m, g.Gb, att, dgap, gap_scale, *z, ab, mean_invstd, gamma, sums2, training, *dz, dgamma, dbeta);
+    } else {
+      auto fr = splat_bn_bwd_reduce_kernel<T, false>;
+      auto fa = splat_bn_bwd_apply_kernel<T, false>;
+      if (!make_geo(dout, &g, U_SBR, true, ONE_WAVE(fr, 256, 16 * 256 * sizeof(float)) / 2, 4)) return OCT_ERR_UNSUPPORTED;
+      g.grid.z = 2;
+      fr<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*dout, m, g.Gb, att, dgap, gap_scale, *z, ab, mean_invstd, sums2);
+      if (!make_geo(dout, &g, U_SBA, true, ONE_WAVE(fa, 256, 0) / 2)) return OCT_ERR_UNSUPPORTED;
+      g.grid.z = 2;
+      fa<<<g.grid, g.bs, 0, s>>>(*dout, m, g.Gb, att, dgap, gap_scale, *z, ab, mean_invstd, gamma, sums2, training, *dz, dgamma, dbeta);
+    }
+  });
+  ++g_octave_launches;    // two kernels: the macro below counts one
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

@@ -143,8 +143,14 @@ class SplAtConv2d(nn.Module):
         w1 = self.fc1.weight.detach().reshape(self.fc1.out_channels, -1)
         dgap, dw1, db1 = ops.glinear_bwd(dh1, gap, w1, card, 1.0 / hw)
         _acc(grads, self.fc1.weight, dw1); _acc(grads, self.fc1.bias, db1)
-        dU = ops.splat_bwd_du(dout, mask, att, dgap, 1.0)
-        dz = bn_bwd(bn0ctx, dU, U, grads, out=dU)
+        bn0, z0, mi0, ab0, tr0, _relu_self, _u = bn0ctx
+        if dout.C // 8 <= 256:
+            # dU is never materialised: both BatchNorm-backward passes rebuild it from dout while streaming z
+            dz, dg0, db0 = ops.splat_bn_bwd(dout, mask, att, dgap, 1.0, z0, ab0, mi0, bn0.weight.detach(), tr0)
+            _acc(grads, bn0.weight, dg0); _acc(grads, bn0.bias, db0)
+        else:
+            dU = ops.splat_bwd_du(dout, mask, att, dgap, 1.0)
+            dz = bn_bwd(bn0ctx, dU, U, grads, out=dU)
         return conv_bwd(self.conv, x, dz, grads, need_dx, zero_bias_grad=tr)
 
 

@@ -116,6 +116,7 @@ _sigs = {
     "octave_splat_combine": [_A, _vp, C.c_int32, _A, _vp],
     "octave_splat_bwd_reduce": [_A, _A, _A, _vp, _vp],
     "octave_splat_bwd_du": [_A, _A, _vp, _vp, C.c_float, _A, _vp],
+    "octave_splat_bn_bwd": [_A, _A, _vp, _vp, C.c_float, _A, _vp, _vp, _vp, C.c_int32, _vp, _A, _vp, _vp, _vp],
     "octave_pool_out_size": [C.POINTER(PoolDesc), C.c_int32],
     "octave_pool_fwd": [C.POINTER(PoolDesc), _A, _A, _vp, _vp],
     "octave_pool_bwd": [C.POINTER(PoolDesc), _A, _vp, _A, _vp],
@@ -224,6 +225,19 @@ def splat_bwd_du(dout: Act, mask: Optional[Act], att: torch.Tensor, dgap: Option
     dU = dout.like(2 * dout.C)
     _chk("octave_splat_bwd_du", lib.octave_splat_bwd_du(_ref(dout), _ref(mask), att.data_ptr(), _p(dgap), gap_scale, _ref(dU), stream_ptr()))
     return dU
+
+
+def splat_bn_bwd(dout: Act, omask: Optional[Act], att: torch.Tensor, dgap: Optional[torch.Tensor], gap_scale: float, z: Act,
+                 ab: torch.Tensor, mi: torch.Tensor, gamma: torch.Tensor, training: bool):
+    """Fused backward of the split-attention combine + bn0 + ReLU -> dz [B,H,W,2C], dgamma, dbeta (see the C header)."""
+    dz = z.like()
+    sums2 = torch.empty(2 * z.C, dtype=torch.float64, device=z.device)
+    dg = torch.empty(z.C, dtype=torch.float32, device=z.device)
+    db = torch.empty(z.C, dtype=torch.float32, device=z.device)
+    _chk("octave_splat_bn_bwd", lib.octave_splat_bn_bwd(_ref(dout), _ref(omask), att.data_ptr(), _p(dgap), gap_scale, _ref(z), ab.data_ptr(),
+                                                        mi.data_ptr(), _p(gamma), int(training), sums2.data_ptr(), _ref(dz), dg.data_ptr(),
+                                                        db.data_ptr(), stream_ptr()))
+    return dz, dg, db
 
 
 def glinear_fwd(inp: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], groups: int, in_scale: float) -> torch.Tensor:
