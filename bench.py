@@ -237,18 +237,26 @@ def run_gpu(args):
     # one CUDA graph per step on a single GPU; data-parallel runs launch eagerly (capturing the bucketed NCCL
     # all-reduces together with the autograd backward hung at N=2 in this round: not enabled)
     use_graph = not args.no_graph and world == 1
+    from octave_b200.train import HostPrefetcher
+    pre = HostPrefetcher(dev)
 
     def one_step(i, e2e: bool, dev_batches=None):
         if e2e:
             x, ys, real = host[i % nb]          # pinned host buffers: the H2D copies are part of the step
             if not use_graph:
-                x = x.to(dev, non_blocking=True); ys = ys.to(dev, non_blocking=True)
-                real = [r.to(dev, non_blocking=True) for r in real]
+                got = pre.get()                 # uploaded by the copy stream while the previous step computed
+                if got is None:
+                    pre.put(x, ys, real)
+                    got = pre.get()
+                x, ys, real = got
         else:
             x, ys, real = dev_batches[i % nb]
         res = ts.step_graphed(x, ys, real) if use_graph else ts.step(x, ys, real)
-        if e2e and use_graph:
-            ts.prefetch(*host[(i + 1) % nb])      # input pipelining: next batch's H2D overlaps this step's compute
+        if e2e:                                 # input pipelining: next batch's H2D overlaps this step's compute
+            if use_graph:
+                ts.prefetch(*host[(i + 1) % nb])
+            else:
+                pre.put(*host[(i + 1) % nb])
         if e2e:
             return float(res['total'].item())     # device -> host read of the step's loss
         return res['total']

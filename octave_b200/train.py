@@ -100,6 +100,32 @@ class GradAllReducer:
         self._pending = []
 
 
+class HostPrefetcher:
+    """Input pipelining for the eager step: `put(x, ys, real)` (pinned host tensors) starts their upload on a copy stream
+    while the current step computes; `get()` hands the device tensors to the compute stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._batch = None
+
+    def put(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> None:
+        with torch.cuda.stream(self.stream):
+            self._batch = (x.to(self.device, non_blocking=True), ys.to(self.device, non_blocking=True),
+                           [r.to(self.device, non_blocking=True) for r in real])
+
+    def get(self):
+        if self._batch is None:
+            return None
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.stream)
+        x, ys, real = self._batch
+        for t in (x, ys, *real):
+            t.record_stream(cur)           # allocated on the copy stream, consumed on the compute stream
+        self._batch = None
+        return x, ys, real
+
+
 class _null:
     def __enter__(self):
         return self
