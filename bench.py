@@ -215,8 +215,12 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # control plane (barriers, max over ranks of the timings) on gloo: the NCCL communicator only ever carries the
+        # gradient all-reduces, which in graph mode are replayed from the captured step
+        ctl = dist.new_group(backend="gloo")
     B, H, W = CONFIGS[args.config]
     if args.batch:
         B = args.batch
@@ -234,9 +238,8 @@ def run_gpu(args):
         host.append((x.pin_memory(), ys.pin_memory(), [r.pin_memory() for r in real]))
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4 + sum(r.numel() * 4 for r in host[0][2])
 
-    # one CUDA graph per step on a single GPU; data-parallel runs launch eagerly (capturing the bucketed NCCL
-    # all-reduces together with the autograd backward hung at N=2 in this round: not enabled)
-    use_graph = not args.no_graph and world == 1
+    # one CUDA graph per step, also data-parallel: the bucketed NCCL all-reduces are captured with the backward pass
+    use_graph = not args.no_graph
     from octave_b200.train import HostPrefetcher
     pre = HostPrefetcher(dev)
 
@@ -269,7 +272,7 @@ def run_gpu(args):
             one_step(i, e2e, dev_batches)
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=ctl)
         torch.cuda.synchronize()
         l0 = _lib.lib.octave_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,11 +282,11 @@ def run_gpu(args):
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=ctl)
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1)])
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=ctl)
         n_launch = _lib.lib.octave_launch_count() - l0
         if use_graph and getattr(ts, "_graph", None) is not None:
             n_launch = steps * ts.graph_kernel_nodes      # replayed kernel nodes of this library (host-side counter sees none)
@@ -330,6 +333,10 @@ def run_gpu(args):
                 line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
+        sys.stdout.flush()
+        dist.barrier(group=ctl)
+        if use_graph:
+            os._exit(0)          # a communicator whose collectives live in a captured graph is not torn down here
         dist.destroy_process_group()
 
 

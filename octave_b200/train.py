@@ -257,8 +257,6 @@ class TrainStep:
         try:
             if not self.has_d or not net.discriminator._use_tc():
                 raise RuntimeError("graph mode needs the bf16 tensor-core critic path")
-            if self.reducer is not None:
-                raise RuntimeError("graph mode is single-GPU: the bucketed NCCL all-reduce is launched eagerly")
             self._sx = x.to(dev).clone()
             self._sys = ys.to(dev).clone()
             self._sreal = [r.to(dev).clone() for r in real]
