@@ -198,15 +198,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
       tc::mbar_wait(tc::smem_u32(&acc_full[buf]), (it >> 1) & 1u);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
+      // all TMEM loads in flight, one wait, accumulator handed back before the bias / activation / packing work
+      uint32_t v[NCHUNK_W][16];
+#pragma unroll
+      for (int c = 0; c < NCHUNK_W; ++c) tc::tmem_ld16(taddr + c * 16, v[c]);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
 #pragma unroll
       for (int c = 0; c < NCHUNK_W; ++c) {
-        uint32_t v[16];
-        tc::tmem_ld16(taddr + c * 16, v);
-        tc::tmem_ld_wait();
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          f[i] = __uint_as_float(v[i]);
+          f[i] = __uint_as_float(v[c][i]);
           if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
         }
         if (p.act) {
@@ -225,9 +230,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
         *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
         *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
       }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+      __syncwarp();   // staged rows are read by other lanes below
       if (p.stats) tile_col_stats<COLS_W, PITCH>(stage, lane, sacc);
       constexpr int LPR = (COLS_W * 2) / 16;   // lanes per row (16 B each): 2 or 4
       constexpr int RPI = 32 / LPR;

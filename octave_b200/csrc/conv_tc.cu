@@ -231,15 +231,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       tc::fence_after_sync();
       if (works) {
         const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
+        // all TMEM loads of this warp's columns in flight, ONE wait, and the accumulator goes back to the MMA warp
+        // before the bias / activation / packing work starts
+        uint32_t v[NCHUNK_W][16];
+#pragma unroll
+        for (int c = 0; c < NCHUNK_W; ++c) tc::tmem_ld16(taddr + c * 16, v[c]);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
 #pragma unroll
         for (int c = 0; c < NCHUNK_W; ++c) {
-          uint32_t v[16];
-          tc::tmem_ld16(taddr + c * 16, v);
-          tc::tmem_ld_wait();
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            f[i] = __uint_as_float(v[i]);
+            f[i] = __uint_as_float(v[c][i]);
             if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
           }
           if (p.act) {
@@ -258,11 +264,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
           *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
           *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
         }
+        __syncwarp();   // staged rows are read by other lanes below
+      } else {
+        // idle column half (BN < 32): still hand the accumulator back
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
       }
-      // this accumulator may be overwritten by the MMA of the tile after next
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
       if (works) {
         // per-channel sum / sum of squares of the staged (bf16-rounded) values
         if (p.stats) tile_col_stats<COLS_W, PITCH>(stage, lane, sacc);
