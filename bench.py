@@ -113,6 +113,57 @@ def cpu_step_fn(H: int, W: int, batch: int, seed: int = 0):
     return step
 
 
+def run_torch_gpu(H, W, batch, steps, warmup, autocast: bool):
+    """On-box comparator: the SAME reference arithmetic (oracle port of the reference modules, stock
+    torch ops: cuDNN convolutions, ATen BatchNorm / softmax) on the GPU.  Baseline leg only — never the product path."""
+    from octave_b200 import synth
+    from oracle import octave_oracle as O
+    from octave_b200.model import OctaScribbleNet
+    dev = torch.device("cuda")
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    net = OctaScribbleNet(torch.Size((batch, 3, H, W)), torch.Size((batch, 2, H, W)), True, False, instance_noise=False, label_noise=False)
+    sd = {k: v.detach().clone().to(dev) for k, v in net.state_dict().items()}
+    del net
+    seg = {k[len("segmentor."):]: (v.requires_grad_() if v.is_floating_point() and "running" not in k else v)
+           for k, v in sd.items() if k.startswith("segmentor.")}
+    dis = {k[len("discriminator."):]: (v.requires_grad_() if v.is_floating_point() and not k.endswith(("_u", "_v")) else v)
+           for k, v in sd.items() if k.startswith("discriminator.")}
+    x, ys, _ = synth.octa_batch(batch, H, W, seed=0, n_ridges=8)
+    real = [r.to(dev) for r in synth.mask_pyramid(batch, H, W, n_ridges=8)]
+    x, ys = x.to(dev).contiguous(memory_format=torch.channels_last), ys.to(dev)
+    seg_p = [v for k, v in seg.items() if v.requires_grad and not k.startswith("linear_head_")]
+    dis_p = [v for v in dis.values() if v.requires_grad]
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            att, agg, _ = O.segmentor_forward(seg, x, training=True)
+        att = [a.float() for a in att]
+        lg = O.weighted_partial_ce(torch.softmax(agg.float(), 1), ys, 2) + 0.1 * O.interlayer_divergence(att) + \
+            0.1 * O.ls_generator_loss(O.discriminator_forward(dis, att, depth=4, training=True))
+        gs = torch.autograd.grad(lg, seg_p, allow_unused=True)
+        ld = O.ls_discriminator_loss(O.discriminator_forward(dis, real, depth=4, training=True),
+                                     O.discriminator_forward(dis, [a.detach() for a in att], depth=4, training=True))
+        gd = torch.autograd.grad(ld, dis_p, allow_unused=True)
+        with torch.no_grad():
+            torch._foreach_add_([p for p, g in zip(seg_p, gs) if g is not None], [g for g in gs if g is not None], alpha=-1e-3)
+            torch._foreach_add_([p for p, g in zip(dis_p, gd) if g is not None], [g for g in gd if g is not None], alpha=-1e-3)
+        return lg
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": batch / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "batch": batch,
+            "what": "oracle port of the reference modules on stock torch CUDA ops (cuDNN), " + ("bf16 autocast" if autocast else "fp32 (TF32 off)")
+                    + ", same G+D step; comparator only"}
+
+
 def run_cpu(H, W, sample_batch, steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -331,6 +382,15 @@ def run_gpu(args):
                 line["cpu_baseline"] = run_cpu(H, W, 2, 3, 1)
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(e)}
+        if world == 1 and args.comparator:
+            del ts, net
+            torch.cuda.empty_cache()
+            for name, ac in (("torch_gpu_bf16_autocast", True), ("torch_gpu_fp32", False)):
+                try:
+                    line[name] = run_torch_gpu(H, W, B, 3, 2, ac)
+                except Exception as e:  # pragma: no cover
+                    line[name] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
         print(json.dumps(line))
     if world > 1:
         sys.stdout.flush()
@@ -366,6 +426,7 @@ if __name__ == "__main__":
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--comparator", action="store_true", help="also time the reference arithmetic on stock torch CUDA ops (cuDNN) on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~1100 kernels of a step eagerly instead of replaying one CUDA graph")
     a = ap.parse_args()
     if a.impl == "reference":
