@@ -48,6 +48,8 @@ unsigned long long octave_launch_count(void);
 #define OCT_LOSS_FROM_LOGITS (1 << 5) /* yhat holds logits; softmax(dim=1) is fused (compose.py:191-192) */
 #define OCT_LOSS_WPCE_FULL   (1 << 6) /* kwargs['full']: do not mask yhat by ys (losses.py:31-32) */
 #define OCT_LOSS_KLD_STOPGRAD (1 << 7) /* stop_gradient=True: basis gets no gradient (losses.py:114) */
+#define OCT_LOSS_JSD         (1 << 8) /* with OCT_LOSS_KLD: divergence='JSD' (losses.py:154-169): mean_q = mean_k(w_k*up(att_k)),
+                                         M = (b + mean_q)/2, 0.5*KL(b||M) + 0.5*KL(mean_q||M); generic (fp32) kernel */
 
 #define OCT_LOSS_MAX_CLASSES 8
 #define OCT_LOSS_MAX_ATT 5
@@ -64,6 +66,7 @@ typedef struct OctaveLossDesc {
   float wpce_scale;         /* 1/(B*H*W) for reduction='mean', 1 for 'sum' (losses.py:55) */
   float dice_eps;           /* DiceLoss.eps (losses.py:66) */
   int32_t n_real, n_fake;   /* number of discriminator logits in d_real / d_fake */
+  float jsd_eps;            /* InterlayerDivergence.eps inside log(M + eps) of the JSD branch (losses.py:159) */
 } OctaveLossDesc;
 
 /* out[] slots written by octave_loss_fwd */

@@ -71,6 +71,7 @@ class LossDesc(C.Structure):
         ("wpce_scale", C.c_float),
         ("dice_eps", C.c_float),
         ("n_real", C.c_int32), ("n_fake", C.c_int32),
+        ("jsd_eps", C.c_float),
     ]
 
 
@@ -82,6 +83,7 @@ LOSS_LSD = 1 << 4
 LOSS_FROM_LOGITS = 1 << 5
 LOSS_WPCE_FULL = 1 << 6
 LOSS_KLD_STOPGRAD = 1 << 7
+LOSS_JSD = 1 << 8
 LOSS_OUT_SLOTS = 8
 
 _vp = C.c_void_p

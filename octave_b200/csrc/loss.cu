@@ -50,7 +50,7 @@ struct LossArgs {
   int B, C, H, W, flags, n_att;
   int ah[OCT_LOSS_MAX_ATT], aw[OCT_LOSS_MAX_ATT];
   float aw8[OCT_LOSS_MAX_ATT - 1];
-  float inv_sumw, wpce_scale, dice_eps;
+  float inv_sumw, wpce_scale, dice_eps, jsd_eps;
   int n_real, n_fake;
 };
 
@@ -648,15 +648,32 @@ __device__ __forceinline__ void generic_load(const LossArgs& a, int b, int y, in
   if (a.flags & OCT_LOSS_KLD) {
     const float* a0 = reinterpret_cast<const float*>(a.att[0]);
     for (int c = 0; c < C; ++c) { px.bs[c] = a0[off + c * plane]; px.m[c] = 0.f; }
+    int used = 0;
     for (int k = 1; k < a.n_att; ++k) {
       const float w = a.aw8[k - 1];
       if (w == 0.f) continue;
+      ++used;
       const int sy = nearest_src(y, a.ah[k], a.H), sx = nearest_src(x, a.aw[k], a.W);
       const size_t pl = (size_t)a.ah[k] * a.aw[k];
       const float* q = reinterpret_cast<const float*>(a.att[k]) + (size_t)b * C * pl + (size_t)sy * a.aw[k] + sx;
-      for (int c = 0; c < C; ++c) px.m[c] += __logf(w * q[c * pl] + kEps);
+      if (a.flags & OCT_LOSS_JSD) {
+        for (int c = 0; c < C; ++c) px.m[c] += w * q[c * pl];               // sum of the weighted posteriors (losses.py:126)
+      } else {
+        for (int c = 0; c < C; ++c) px.m[c] += __logf(w * q[c * pl] + kEps);
+      }
+    }
+    if (a.flags & OCT_LOSS_JSD) {
+      const float inv = used > 0 ? 1.f / (float)used : 0.f;                  // mean over the levels (losses.py:156-157)
+      for (int c = 0; c < C; ++c) px.m[c] *= inv;
     }
   }
+}
+
+// number of posterior levels that take part (non-zero weight)
+__device__ __forceinline__ int used_levels(const LossArgs& a) {
+  int used = 0;
+  for (int k = 1; k < a.n_att; ++k) used += a.aw8[k - 1] != 0.f;
+  return used;
 }
 
 __global__ void __launch_bounds__(256) loss_generic_fwd_kernel(const LossArgs a) {
@@ -685,8 +702,15 @@ __global__ void __launch_bounds__(256) loss_generic_fwd_kernel(const LossArgs a)
           acc[17] += px.p[c] * px.t[c];
           acc[18] += px.p[c] + px.t[c];
         }
-        if (a.flags & OCT_LOSS_KLD)
-          acc[16] += px.bs[c] * (__logf(px.bs[c] + kEps) - px.m[c] * a.inv_sumw);
+        if (a.flags & OCT_LOSS_KLD) {
+          if (a.flags & OCT_LOSS_JSD) {
+            // 0.5 * b * (log b - log M) + 0.5 * mq * (log mq - log M),  M = (b + mq) / 2   (losses.py:158-168)
+            const float lm = logf(0.5f * (px.bs[c] + px.m[c]) + a.jsd_eps);
+            acc[16] += 0.5f * px.bs[c] * (logf(px.bs[c] + kEps) - lm) + 0.5f * px.m[c] * (logf(px.m[c] + kEps) - lm);
+          } else {
+            acc[16] += px.bs[c] * (__logf(px.bs[c] + kEps) - px.m[c] * a.inv_sumw);
+          }
+        }
       }
     }
   }
@@ -754,12 +778,27 @@ __global__ void __launch_bounds__(256) loss_generic_bwd_kernel(const LossArgs a)
     if (a.flags & OCT_LOSS_KLD) {
       const float gk = a.gscale[OCT_LOSS_OUT_KLD] / ((float)a.B * (float)hw);
       const bool stop = a.flags & OCT_LOSS_KLD_STOPGRAD;
+      const bool jsd = a.flags & OCT_LOSS_JSD;
       float* g0 = reinterpret_cast<float*>(a.g_att[0]);
+      float gq[OCT_LOSS_MAX_CLASSES];   // JSD: gradient w.r.t. mean_q
 #pragma unroll
-      for (int c = 0; c < OCT_LOSS_MAX_CLASSES; ++c)
-        if (c < C)
-          g0[off + c * plane] =
-              stop ? 0.f : gk * (__logf(px.bs[c] + kEps) - px.m[c] * a.inv_sumw + px.bs[c] / (px.bs[c] + kEps));
+      for (int c = 0; c < OCT_LOSS_MAX_CLASSES; ++c) {
+        gq[c] = 0.f;
+        if (c < C) {
+          if (jsd) {
+            const float bsum = px.bs[c] + px.m[c];
+            const float mix = 0.5f * bsum + a.jsd_eps;
+            const float lm = logf(mix), common = 0.25f * bsum / mix;
+            const float gb = 0.5f * (logf(px.bs[c] + kEps) - lm + px.bs[c] / (px.bs[c] + kEps)) - common;
+            gq[c] = gk * (0.5f * (logf(px.m[c] + kEps) - lm + px.m[c] / (px.m[c] + kEps)) - common);
+            g0[off + c * plane] = stop ? 0.f : gk * gb;
+          } else {
+            g0[off + c * plane] =
+                stop ? 0.f : gk * (__logf(px.bs[c] + kEps) - px.m[c] * a.inv_sumw + px.bs[c] / (px.bs[c] + kEps));
+          }
+        }
+      }
+      const int used = jsd ? used_levels(a) : 0;
       for (int k = 1; k < a.n_att; ++k) {
         const float w = a.aw8[k - 1];
         if (w == 0.f) continue;
@@ -768,8 +807,10 @@ __global__ void __launch_bounds__(256) loss_generic_bwd_kernel(const LossArgs a)
         const size_t qo = (size_t)b * C * pl + (size_t)sy * a.aw[k] + sx;
         const float* q = reinterpret_cast<const float*>(a.att[k]) + qo;
         float* g = reinterpret_cast<float*>(a.g_att[k]) + qo;
-        for (int c = 0; c < C; ++c)
-          atomicAdd(g + c * pl, -gk * a.inv_sumw * w / (w * q[c * pl] + kEps) * px.bs[c]);
+        for (int c = 0; c < C; ++c) {
+          if (jsd) atomicAdd(g + c * pl, gq[c] * w / (float)used);
+          else atomicAdd(g + c * pl, -gk * a.inv_sumw * w / (w * q[c * pl] + kEps) * px.bs[c]);
+        }
       }
     }
   }
@@ -778,6 +819,7 @@ __global__ void __launch_bounds__(256) loss_generic_bwd_kernel(const LossArgs a)
 bool fast_ok(const OctaveLossDesc* d) {
   const bool maps = d->flags & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD);
   if (!maps) return true;  // LS-only launches take the fast kernel with a 1x1 grid
+  if (d->flags & OCT_LOSS_JSD) return false;   // Jensen-Shannon variant: generic kernel
   if (d->C != 2 || (d->H & 15) || (d->W & 15)) return false;
   if (d->flags & OCT_LOSS_KLD) {
     if (d->n_att < 2 || d->n_att > OCT_LOSS_MAX_ATT) return false;
@@ -841,7 +883,7 @@ void fill_args(LossArgs& a, const OctaveLossDesc* d, const void* yhat, const voi
   }
   for (int k = 0; k < OCT_LOSS_MAX_ATT - 1; ++k) a.aw8[k] = (k + 1 < a.n_att) ? d->att_weight[k] : 0.f;
   a.inv_sumw = d->sum_weights != 0.f ? 1.f / d->sum_weights : 0.f;
-  a.wpce_scale = d->wpce_scale; a.dice_eps = d->dice_eps;
+  a.wpce_scale = d->wpce_scale; a.dice_eps = d->dice_eps; a.jsd_eps = d->jsd_eps;
   a.n_real = d->n_real; a.n_fake = d->n_fake;
   a.out = nullptr; a.gscale = nullptr; a.g_yhat = nullptr; a.g_real = nullptr; a.g_fake = nullptr;
 }

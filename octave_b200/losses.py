@@ -44,12 +44,13 @@ class _LossCfg:
     """Static (non-tensor) configuration of one fused-loss evaluation."""
 
     def __init__(self, flags: int, wpce_scale_mode: str = "mean", dice_eps: float = 1e-12,
-                 att_weights: Sequence[float] = (), sum_weights: float = 1.0):
+                 att_weights: Sequence[float] = (), sum_weights: float = 1.0, jsd_eps: float = 1e-12):
         self.flags = flags
         self.wpce_scale_mode = wpce_scale_mode
         self.dice_eps = dice_eps
         self.att_weights = list(att_weights)
         self.sum_weights = sum_weights
+        self.jsd_eps = jsd_eps
 
 
 def _build_desc(cfg: _LossCfg, yhat: Optional[Tensor], att: Sequence[Tensor], d_real: Optional[Tensor],
@@ -72,6 +73,7 @@ def _build_desc(cfg: _LossCfg, yhat: Optional[Tensor], att: Sequence[Tensor], d_
     npix = max(d.B * d.H * d.W, 1)
     d.wpce_scale = 1.0 / npix if cfg.wpce_scale_mode == "mean" else 1.0
     d.dice_eps = float(cfg.dice_eps)
+    d.jsd_eps = float(cfg.jsd_eps)
     d.n_real = 0 if d_real is None else d_real.numel()
     d.n_fake = 0 if d_fake is None else d_fake.numel()
     return d
@@ -225,15 +227,19 @@ class InterlayerDivergence(nn.Module):
             if self.mode == 'sum':
                 raise NotImplementedError('Not implemented yet.')
         elif self.divergence == 'JSD':
-            raise NotImplementedError('octave_b200: JSD branch (reference losses.py:154-169) is not ported yet')
+            pass                                   # Jensen-Shannon branch (losses.py:154-169): generic fp32 kernel
         else:
             raise NotImplementedError(f'Invalid divergence type / Not implemented: {self.divergence}')
         used = [float(w) for _, w in zip(attentions[1:], weights)]
         if len(attentions) > 5:
             raise NotImplementedError('octave_b200: at most 5 attention maps are supported')
         flags = _lib.LOSS_KLD | (_lib.LOSS_KLD_STOPGRAD if self.stop_gradient else 0)
-        cfg = _LossCfg(flags, att_weights=used, sum_weights=float(sum(weights)))
-        out = fused_loss(cfg, att=list(attentions[:1 + len(used)]))
+        atts = list(attentions[:1 + len(used)])
+        if self.divergence == 'JSD':
+            flags |= _lib.LOSS_JSD
+            atts = [a.float() for a in atts]       # the generic kernel computes on fp32 maps
+        cfg = _LossCfg(flags, att_weights=used, sum_weights=float(sum(weights)), jsd_eps=float(self.eps))
+        out = fused_loss(cfg, att=atts)
         if config.nan_check and bool(out[_OUT_NAN].item()):
             _log_error(f'Divergence: {out[_OUT_KLD]}')
             raise Exception('Divergence is NaN')

@@ -82,6 +82,29 @@ def interlayer_divergence(attentions: Sequence[Tensor], weights: Optional[list] 
     return divergence
 
 
+def interlayer_divergence_jsd(attentions: Sequence[Tensor], weights: Optional[list] = None,
+                              stop_gradient: bool = False, eps: float = 1e-12) -> Tensor:
+    """architectures/segmentor/losses.py:111-126,154-169 (divergence='JSD', mode='mean')."""
+    basis = attentions[0].detach() if stop_gradient else attentions[0]           # :114
+    C = basis.shape[1]
+    flat = lambda t: t.permute(0, 2, 3, 1).reshape(-1, C)
+    log_basis = torch.log(flat(basis) + 1e-12)                                   # :115
+    height, width = basis.shape[2], basis.shape[3]
+    if weights is None:
+        weights = [1 for _ in range(len(attentions[1:]))]
+    elif len(weights) != len(attentions[1:]):
+        weights = weights[:len(attentions)]
+    posterior = [nearest_resize(att, (height, width)) * weight
+                 for att, weight in zip(attentions[1:], weights) if weight != 0]  # :124-126
+    mean_q = torch.stack(posterior, dim=0).mean(dim=0)                           # :156-157
+    mixture = 0.5 * (basis + mean_q)                                             # :158
+    log_mixture = torch.log(flat(mixture) + eps)                                 # :159
+    log_mean_q = flat(torch.log(mean_q + 1e-12))                                 # :160 (the 'mean' reduce has no reduced axis)
+    kld_p = (0.5 * flat(basis) * (log_basis - log_mixture)).sum(dim=1).mean()    # :162-164
+    kld_q = (0.5 * flat(mean_q) * (log_mean_q - log_mixture)).sum(dim=1).mean()  # :166-168
+    return kld_p + kld_q
+
+
 def ls_discriminator_loss(y_real: Tensor, y_fake: Tensor) -> Tensor:
     """architectures/discriminator/losses.py:11-14."""
     return 0.5 * torch.mean((y_real - 1) ** 2) + 0.5 * torch.mean((y_fake + 1) ** 2)

@@ -166,6 +166,34 @@ def test_generic_path_vs_oracle():
         grad_close(a, b, 1e-4, f"grad[{i}]")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("weights,stop", [(None, False), ([1, 0.5, 2], False), ([1, 0, 2], True)])
+def test_interlayer_divergence_jsd_vs_oracle(weights, stop, dtype):
+    """divergence='JSD' (reference losses.py:154-169) on the generic kernel: value, gradients, stop_gradient, weights."""
+    m = L()
+    g = torch.Generator().manual_seed(11)
+    B, C = 2, 2
+    sizes = [(48, 64), (24, 32), (12, 16), (6, 8)]
+    att = [torch.softmax(torch.randn(B, C, h, w, generator=g), 1).to(dtype).float() for h, w in sizes]
+    ao = [a.double().requires_grad_() for a in att]
+    lo = O.interlayer_divergence_jsd(ao, weights, stop_gradient=stop)
+    go = torch.autograd.grad(lo, ao, allow_unused=True)
+    ac = [a.to(DEV).to(dtype).requires_grad_() for a in att]
+    lc = m.InterlayerDivergence(divergence='JSD', stop_gradient=stop)(ac, weights)
+    close(lc, lo, rtol=1e-4)
+    gc = torch.autograd.grad(lc, ac, allow_unused=True)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    for i, (a, b) in enumerate(zip(gc, go)):
+        if b is None or float(b.abs().max()) == 0.0:
+            assert a is None or float(a.float().abs().max()) == 0.0, f"grad[{i}] should be zero"
+        else:
+            grad_close(a.float(), b, tol, f"grad[{i}]")
+    # known answer (SURVEY.md 8c)
+    b0 = torch.zeros(1, 2, 4, 4); b0[:, 0] = .8; b0[:, 1] = .2
+    q1 = torch.full((1, 2, 2, 2), .5); q2 = torch.zeros(1, 2, 1, 1); q2[:, 0] = .25; q2[:, 1] = .75
+    assert abs(m.InterlayerDivergence(divergence='JSD')([b0.to(DEV), q1.to(DEV), q2.to(DEV)]).item() - 0.0967728) < 1e-5
+
+
 def test_full_size_properties():
     """BASELINE config sizes (c5: B=8, 1024^2): size-independent properties instead of a CPU oracle run."""
     m = L()

@@ -42,3 +42,10 @@ def test_oracle_losses_match_golden(cases, name):
     torch.testing.assert_close(l, c["kld_w"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(O.ls_generator_loss(c["d_fake"]), c["lsg"])
     torch.testing.assert_close(O.ls_discriminator_loss(c["d_real"], c["d_fake"]), c["lsd"])
+
+
+def test_oracle_jsd_known_answer():
+    """SURVEY.md 8c closed-form answer confirmed against the imported reference (JSD branch, losses.py:154-169)."""
+    b = torch.zeros(1, 2, 4, 4); b[:, 0] = .8; b[:, 1] = .2
+    q1 = torch.full((1, 2, 2, 2), .5); q2 = torch.zeros(1, 2, 1, 1); q2[:, 0] = .25; q2[:, 1] = .75
+    assert abs(O.interlayer_divergence_jsd([b, q1, q2]).item() - 0.0967728) < 1e-6

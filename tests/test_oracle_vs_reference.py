@@ -31,6 +31,8 @@ def test_known_answers_reference_and_oracle(ref):
     assert abs(O.interlayer_divergence([b, q1, q2]).item() - 0.4294572) < 1e-6
     assert abs(ref.InterlayerDivergence()([b, q1, q2], weights=[2, 0]).item() + 0.5004024) < 1e-6
     assert abs(O.interlayer_divergence([b, q1, q2], weights=[2, 0]).item() + 0.5004024) < 1e-6
+    assert abs(ref.InterlayerDivergence(divergence='JSD')([b, q1, q2]).item() - 0.0967728) < 1e-6
+    assert abs(O.interlayer_divergence_jsd([b, q1, q2]).item() - 0.0967728) < 1e-6
     r = torch.tensor([[.5], [1.5]]); f = torch.tensor([[-.5], [0.]])
     assert abs(ref.LSDiscriminatorialLoss()(r, f).item() - 0.4375) < 1e-7
     assert abs(O.ls_discriminator_loss(r, f).item() - 0.4375) < 1e-7
@@ -55,6 +57,18 @@ def test_losses_match_reference(ref, shape):
     for w in (None, [1, 2, 0], [0.5, 1, 1, 3]):
         torch.testing.assert_close(ref.InterlayerDivergence()(atts, weights=w), O.interlayer_divergence(atts, weights=w),
                                    rtol=1e-5, atol=1e-6)
+    # Jensen-Shannon branch (losses.py:154-169), values and gradients, with and without stop_gradient
+    for w in (None, [1, 2, 0]):
+        for sg in (False, True):
+            ar = [a.clone().requires_grad_() for a in atts]; ao = [a.clone().requires_grad_() for a in atts]
+            lr = ref.InterlayerDivergence(divergence='JSD', stop_gradient=sg)(ar, weights=w)
+            lo = O.interlayer_divergence_jsd(ao, weights=w, stop_gradient=sg)
+            torch.testing.assert_close(lr, lo, rtol=1e-5, atol=1e-7)
+            gr = torch.autograd.grad(lr, ar, allow_unused=True); go = torch.autograd.grad(lo, ao, allow_unused=True)
+            for x, y in zip(gr, go):
+                assert (x is None) == (y is None)
+                if x is not None:
+                    torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-8)
 
 
 def test_segmentor_and_discriminator_match_reference(ref):
