@@ -19,6 +19,7 @@
 // the pixel index, so both operands are MN-major views of the very same TMA boxes; partial sums over
 // pixel-tile slices are reduced with fp32 red.global.add.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -196,7 +197,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
     const int r = q * 32 + lane;
     const int th = r / p.TW, tw = r - th * p.TW;
     uint8_t* const stage = smem_gen + STAGES * STAGE_BYTES + (warp - 2) * (32 * PITCH);
-    float sacc[4] = {0.f, 0.f, 0.f, 0.f};   // statistics of this lane's column pair (tile_col_stats)
+    constexpr int NS = COLS_W > 64 ? COLS_W / 64 : 1;   // 64-column statistic slabs per warp
+    constexpr int SW = COLS_W > 64 ? 64 : COLS_W;       // columns per slab
+    float sacc[NS][4];                                  // statistics of this lane's column pair(s) (tile_col_stats)
+#pragma unroll
+    for (int h2 = 0; h2 < NS; ++h2) sacc[h2][0] = sacc[h2][1] = sacc[h2][2] = sacc[h2][3] = 0.f;
     int stat_col0 = -1;  // global channel of this warp's column 0 (fixed across the CTA's tiles when stats are on)
     uint32_t li = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
@@ -231,38 +236,45 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       tc::fence_after_sync();
       if (works) {
         const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
-        // all TMEM loads of this warp's columns in flight, ONE wait, and the accumulator goes back to the MMA warp
-        // before the bias / activation / packing work starts
-        uint32_t v[NCHUNK_W][16];
+        // TMEM loads of up to 64 columns in flight before ONE wait; the accumulator goes back to the MMA warp as soon as
+        // the last load has landed, before the bias / activation / packing work of that slab
+        constexpr int LDG = NCHUNK_W > 4 ? 4 : NCHUNK_W;
 #pragma unroll
-        for (int c = 0; c < NCHUNK_W; ++c) tc::tmem_ld16(taddr + c * 16, v[c]);
-        tc::tmem_ld_wait();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+        for (int c0 = 0; c0 < NCHUNK_W; c0 += LDG) {
+          uint32_t v[LDG][16];
 #pragma unroll
-        for (int c = 0; c < NCHUNK_W; ++c) {
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            f[i] = __uint_as_float(v[c][i]);
-            if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
+          for (int c = 0; c < LDG; ++c) tc::tmem_ld16(taddr + (c0 + c) * 16, v[c]);
+          tc::tmem_ld_wait();
+          if (c0 + LDG >= NCHUNK_W) {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
           }
-          if (p.act) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
-          }
-          if (!valid) {   // rows outside the image stage zeros: they are not stored and must not enter the statistics
+          for (int cc = 0; cc < LDG; ++cc) {
+            const int c = c0 + cc;
+            float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = 0.f;
+            for (int i = 0; i < 16; ++i) {
+              f[i] = __uint_as_float(v[cc][i]);
+              if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
+            }
+            if (p.act) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
+            }
+            if (!valid) {   // rows outside the image stage zeros: they are not stored and must not enter the statistics
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = 0.f;
+            }
+            uint4 u0, u1;
+            u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
+            u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
+            u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
+            u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
+            *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
+            *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
           }
-          uint4 u0, u1;
-          u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
-          u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
-          u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
-          u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
-          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
-          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
         }
         __syncwarp();   // staged rows are read by other lanes below
       } else {
@@ -272,36 +284,43 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       }
       if (works) {
         // per-channel sum / sum of squares of the staged (bf16-rounded) values
-        if (p.stats) tile_col_stats<COLS_W, PITCH>(stage, lane, sacc);
+        if (p.stats) {
+#pragma unroll
+          for (int h2 = 0; h2 < NS; ++h2) tile_col_stats<SW, PITCH>(stage + h2 * 128, lane, sacc[h2]);
+        }
         // coalesced write-out of the warp's 32 staged rows: LPR lanes cover one row (16 B each)
         constexpr int LPR = (COLS_W * 2) / 16;   // lanes per row: 8 (64 cols), 4, 2
         constexpr int RPI = 32 / LPR;            // rows per instruction
         constexpr int NIT = 32 / RPI;            // store instructions per lane
         const int sub = lane % LPR, rsel = lane / LPR;
         if (p.accumulate) {
-          // y += result: fetch all the old values first (NIT independent 16-byte loads in flight), then add and store
-          uint4 old[NIT];
-          long long offs[NIT];
+          // y += result: fetch the old values first (up to 8 independent 16-byte loads in flight), then add and store
+          constexpr int NB = NIT > 8 ? 8 : NIT;
+#pragma unroll 1
+          for (int i0 = 0; i0 < NIT; i0 += NB) {
+            uint4 old[NB];
+            long long offs[NB];
 #pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            const int row = i * RPI + rsel;
-            long long off = __shfl_sync(0xffffffffu, row_off, row);
-            if (sub * 8 >= nvalid) off = -1;
-            offs[i] = off;
-            if (off >= 0) old[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.out) + off + sub * 8);
-          }
+            for (int i = 0; i < NB; ++i) {
+              const int row = (i0 + i) * RPI + rsel;
+              long long off = __shfl_sync(0xffffffffu, row_off, row);
+              if (sub * 8 >= nvalid) off = -1;
+              offs[i] = off;
+              if (off >= 0) old[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.out) + off + sub * 8);
+            }
 #pragma unroll
-          for (int i = 0; i < NIT; ++i) {
-            if (offs[i] >= 0) {
-              const int row = i * RPI + rsel;
-              uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
-              const uint4 e = old[i];
-              float x0, x1, y0, y1;
-              bf16x2_unpack(val.x, x0, x1); bf16x2_unpack(e.x, y0, y1); val.x = bf16x2_pack(x0 + y0, x1 + y1);
-              bf16x2_unpack(val.y, x0, x1); bf16x2_unpack(e.y, y0, y1); val.y = bf16x2_pack(x0 + y0, x1 + y1);
-              bf16x2_unpack(val.z, x0, x1); bf16x2_unpack(e.z, y0, y1); val.z = bf16x2_pack(x0 + y0, x1 + y1);
-              bf16x2_unpack(val.w, x0, x1); bf16x2_unpack(e.w, y0, y1); val.w = bf16x2_pack(x0 + y0, x1 + y1);
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + sub * 8) = val;
+            for (int i = 0; i < NB; ++i) {
+              if (offs[i] >= 0) {
+                const int row = (i0 + i) * RPI + rsel;
+                uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
+                const uint4 e = old[i];
+                float x0, x1, y0, y1;
+                bf16x2_unpack(val.x, x0, x1); bf16x2_unpack(e.x, y0, y1); val.x = bf16x2_pack(x0 + y0, x1 + y1);
+                bf16x2_unpack(val.y, x0, x1); bf16x2_unpack(e.y, y0, y1); val.y = bf16x2_pack(x0 + y0, x1 + y1);
+                bf16x2_unpack(val.z, x0, x1); bf16x2_unpack(e.z, y0, y1); val.z = bf16x2_pack(x0 + y0, x1 + y1);
+                bf16x2_unpack(val.w, x0, x1); bf16x2_unpack(e.w, y0, y1); val.w = bf16x2_pack(x0 + y0, x1 + y1);
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + sub * 8) = val;
+              }
             }
           }
         } else {
@@ -318,16 +337,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
         __syncwarp();  // staging rows are rewritten by the next tile
       }
     }
-    if (p.stats && works && stat_col0 >= 0 && lane < COLS_W / 2) {
+    if (p.stats && works && stat_col0 >= 0 && lane < SW / 2) {
       const int nvalid_cols = p.cout_g - (stat_col0 % p.cout_g);
-      const int col = 2 * lane;
-      if (col < nvalid_cols) {
-        atomicAdd(p.stats + stat_col0 + col, (double)sacc[0]);
-        atomicAdd(p.stats + p.stats_stride + stat_col0 + col, (double)sacc[2]);
-      }
-      if (col + 1 < nvalid_cols) {
-        atomicAdd(p.stats + stat_col0 + col + 1, (double)sacc[1]);
-        atomicAdd(p.stats + p.stats_stride + stat_col0 + col + 1, (double)sacc[3]);
+#pragma unroll
+      for (int h2 = 0; h2 < NS; ++h2) {
+        const int col = h2 * 64 + 2 * lane;
+        if (col < nvalid_cols) {
+          atomicAdd(p.stats + stat_col0 + col, (double)sacc[h2][0]);
+          atomicAdd(p.stats + p.stats_stride + stat_col0 + col, (double)sacc[h2][2]);
+        }
+        if (col + 1 < nvalid_cols) {
+          atomicAdd(p.stats + stat_col0 + col + 1, (double)sacc[h2][1]);
+          atomicAdd(p.stats + p.stats_stride + stat_col0 + col + 1, (double)sacc[h2][3]);
+        }
       }
     }
   }
@@ -688,6 +710,18 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
   p.bias = bias; p.act = d->relu; p.out_f32 = d->out_dtype == OCT_DTYPE_F32; p.accumulate = d->accumulate;
   int BN = 128;
   if (n_cols_g % 128) BN = (n_cols_g % 64 == 0) ? 64 : ((n_cols_g % 32 == 0) ? 32 : 16);
+  {
+    // 256-column tiles for the long-K, many-tile convolutions (the fat decoder layers): the A tile is fetched once per
+    // 256 output channels, which takes a quarter of the L2->SM traffic off the layers that sit on that limit
+    static int bn256 = -1;
+    if (bn256 < 0) { const char* e = getenv("OCTAVE_BN256"); bn256 = e ? atoi(e) : 1; }
+    int sms0 = octave_sm_count();
+    if (sms0 <= 0) sms0 = 148;
+    const long long tiles256 = (long long)p.tiles_w * p.tiles_h * B * (n_cols_g / 256) * d->groups;
+    if (bn256 && BK == 64 && n_cols_g % 256 == 0 && !convt && !s2d && !d->accumulate && p.taps * p.kchunks >= 16 &&
+        tiles256 >= 4LL * sms0)
+      BN = 256;
+  }
   if (convt && d->cout % BN) BN = (d->cout % 64 == 0) ? 64 : 32;  // a column tile must stay inside one tap
   if (convt && d->cout % BN) return OCT_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmB;
@@ -716,6 +750,7 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
     switch (BN) {
       // pipeline depth sized to ~160-190 KB in flight per SM: the persistent CTA is alone on its SM, so the ring must
       // cover the HBM bandwidth-delay product by itself, also for the small stages of narrow layers
+      case 256: return launch_fwd<256, 64, 3>(tmA, tmB, p, (int)grid, s);
       case 128: return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
       case 64: return launch_fwd<64, 64, 7>(tmA, tmB, p, (int)grid, s);
       case 32: return launch_fwd<32, 64, 9>(tmA, tmB, p, (int)grid, s);
