@@ -382,12 +382,14 @@ struct WgradParams {
 constexpr int kWgProducers = 4;
 constexpr int kWgThreads = (6 + kWgProducers - 1) * 32;  // warp 0 + warps 6.. producers, warp 1 MMA, warps 2..5 epilogue
 
-template <int BN, int CWA, int CWB, int NA, int STAGES>
+template <int BN, int CWA, int CWB, int NA, int STAGES, int ROWS>
 __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
                                                                 const __grid_constant__ CUtensorMap tmX,
                                                                 const WgradParams p) {
   constexpr int PITCH_A = CWA * 2, PITCH_B = CWB * 2;   // bytes per pixel row of one box
-  constexpr int CHUNK_A = 128 * PITCH_A, CHUNK_B = 128 * PITCH_B;
+  // ROWS = pixel rows of one box region (>= 16 * ksteps): 128, or fewer rows per stage and a deeper ring where the
+  // stage is so large that two of them cannot hide the L2 latency (BN = 256)
+  constexpr int CHUNK_A = ROWS * PITCH_A, CHUNK_B = ROWS * PITCH_B;
   // NA = A chunks that really exist (cout_g <= NA*CWA): only they get shared memory; the 128-row UMMA still strides
   // over 128/CWA chunks, the missing ones alias whatever follows (their accumulator rows are never stored)
   constexpr int NCH_A = NA, NCH_B = (BN + CWB - 1) / CWB;
@@ -598,16 +600,17 @@ bool make_w_map(CUtensorMap* m, const void* base, int K, int rows, int taps, int
   return r == CUDA_SUCCESS;
 }
 
-// Pick the spatial patch TW x TH (<= 128 pixels, TW,TH <= 256) that wastes the fewest UMMA rows.
-void pick_patch(int H, int W, int* TW, int* TH) {
+// Pick the spatial patch TW x TH (<= max_px pixels, TW,TH <= 256) that wastes the fewest UMMA rows.  quantum = the row
+// granularity the kernel pays for: the whole 128-row M tile (forward), or one 16-pixel K step (weight gradient).
+void pick_patch(int H, int W, int* TW, int* TH, int max_px = 128, int quantum = 128) {
   double best = -1.0;
   int bw = 1, bh = 1;
-  for (int tw = 1; tw <= (W < 128 ? W : 128); ++tw) {
-    int th = 128 / tw;
+  for (int tw = 1; tw <= (W < max_px ? W : max_px); ++tw) {
+    int th = max_px / tw;
     if (th > H) th = H;
     if (th > 256) th = 256;
     long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
-    double eff = (double)H * W / ((double)tiles * 128.0);
+    double eff = (double)H * W / ((double)tiles * (double)((tw * th + quantum - 1) / quantum * quantum));
     if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
       best = eff; bw = tw; bh = th;
     }
@@ -630,21 +633,21 @@ int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParam
   return OCT_OK;
 }
 
-template <int BN, int CWA, int CWB, int NA>
-constexpr int wgrad_stage_bytes() { return NA * 128 * CWA * 2 + ((BN + CWB - 1) / CWB) * 128 * CWB * 2; }
+template <int BN, int CWA, int CWB, int NA, int ROWS>
+constexpr int wgrad_stage_bytes() { return NA * ROWS * CWA * 2 + ((BN + CWB - 1) / CWB) * ROWS * CWB * 2; }
 
-template <int BN, int CWA, int CWB, int NA, int STAGES>
+template <int BN, int CWA, int CWB, int NA, int STAGES, int ROWS = 128>
 int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradParams& p, dim3 grid, cudaStream_t s) {
   // +32 KB slack: the chunks a 128-row UMMA strides over beyond NA must stay inside the allocation
-  constexpr int smem = STAGES * wgrad_stage_bytes<BN, CWA, CWB, NA>() + (128 / CWA - NA) * 128 * CWA * 2 + 1024;
+  constexpr int smem = STAGES * wgrad_stage_bytes<BN, CWA, CWB, NA, ROWS>() + (128 / CWA - NA) * ROWS * CWA * 2 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return OCT_ERR_LAUNCH;
     attr_done = true;
   }
-  conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES><<<grid, kWgThreads, smem, s>>>(tmDY, tmX, p);
+  conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES, ROWS><<<grid, kWgThreads, smem, s>>>(tmDY, tmX, p);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -798,17 +801,24 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   p.convt = convt ? 1 : 0; p.convt_cout = d->cout;
   int H = d->H, W = d->W, B = d->B;
   if (d->ksize == 1) { W = d->B * d->H * d->W; H = 1; B = 1; }
-  pick_patch(H, W, &p.TW, &p.TH);
-  p.tiles_w = (W + p.TW - 1) / p.TW;
-  p.tiles_h = (H + p.TH - 1) / p.TH;
-  p.B = B;
-  p.total_tiles = B * p.tiles_w * p.tiles_h;
   const int CWA = (cout_g % 64 == 0) ? 64 : 32;
   const int CWB = (cin_g % 64 == 0) ? 64 : 32;
   int BN;
   if (CWB == 32) BN = 32;
   else if (CWA == 32) BN = 64;
   else BN = (cin_g % 256 == 0) ? 256 : ((cin_g % 128 == 0) ? 128 : 64);
+  // 128 x 256 tiles: a 128-pixel stage is 96 KB, and a ring of two cannot cover the L2 latency (ncu: tensor pipe 56 %
+  // busy at 13 TB/s of L2->SM traffic, far below what L2 delivers).  Four 64-pixel stages do, even though the smaller
+  // patches waste more K rows (measured 1.15 -> 1.25-1.35 PFLOP/s; 96 x 3 is between, 48 x 6 and 32 x 9 are slower:
+  // the TMA boxes get too small).  OCTAVE_WGRAD_ROWS=128 restores the two-stage ring.
+  static const int rows_env = [] { const char* e = getenv("OCTAVE_WGRAD_ROWS"); return e ? atoi(e) : 64; }();
+  int stage_rows = 128;
+  if (BN == 256 && cout_g > CWA && rows_env == 64) stage_rows = 64;
+  pick_patch(H, W, &p.TW, &p.TH, stage_rows, 16);
+  p.tiles_w = (W + p.TW - 1) / p.TW;
+  p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.B = B;
+  p.total_tiles = B * p.tiles_w * p.tiles_h;
   p.n_ci_tiles = (cin_g + BN - 1) / BN;
   const int n_co_tiles = (cout_g + 127) / 128;
   const int out_tiles = n_co_tiles * p.n_ci_tiles * p.taps * d->groups;
@@ -833,7 +843,10 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   const bool one_a = cout_g <= CWA;   // a single A box per pixel tile
   if (CWA == 64 && CWB == 64) {
     switch (BN) {
-      case 256: return one_a ? launch_wgrad<256, 64, 64, 1, 2>(tmDY, tmX, p, grid, s) : launch_wgrad<256, 64, 64, 2, 2>(tmDY, tmX, p, grid, s);
+      case 256:
+        if (one_a) return launch_wgrad<256, 64, 64, 1, 2>(tmDY, tmX, p, grid, s);
+        if (stage_rows == 64) return launch_wgrad<256, 64, 64, 2, 4, 64>(tmDY, tmX, p, grid, s);
+        return launch_wgrad<256, 64, 64, 2, 2>(tmDY, tmX, p, grid, s);
       case 128: return one_a ? launch_wgrad<128, 64, 64, 1, 4>(tmDY, tmX, p, grid, s) : launch_wgrad<128, 64, 64, 2, 3>(tmDY, tmX, p, grid, s);
       default: return one_a ? launch_wgrad<64, 64, 64, 1, 6>(tmDY, tmX, p, grid, s) : launch_wgrad<64, 64, 64, 2, 4>(tmDY, tmX, p, grid, s);
     }
