@@ -810,10 +810,12 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   // 128 x 256 tiles: a 128-pixel stage is 96 KB, and a ring of two cannot cover the L2 latency (ncu: tensor pipe 56 %
   // busy at 13 TB/s of L2->SM traffic, far below what L2 delivers).  Four 64-pixel stages do, even though the smaller
   // patches waste more K rows (measured 1.15 -> 1.25-1.35 PFLOP/s; 96 x 3 is between, 48 x 6 and 32 x 9 are slower:
-  // the TMA boxes get too small).  OCTAVE_WGRAD_ROWS=128 restores the two-stage ring.
+  // the TMA boxes get too small).  Only for dense 3x3 layers: in the step's launch list the 1x1 and grouped layers at
+  // 25x25 with few split-K slices lost 20-50 % with the short stages.  OCTAVE_WGRAD_ROWS=128 restores the two-stage
+  // ring everywhere, OCTAVE_WGRAD_ROWS=-64 forces the short stages on every 128 x 256 tile.
   static const int rows_env = [] { const char* e = getenv("OCTAVE_WGRAD_ROWS"); return e ? atoi(e) : 64; }();
   int stage_rows = 128;
-  if (BN == 256 && cout_g > CWA && rows_env == 64) stage_rows = 64;
+  if (BN == 256 && cout_g > CWA && ((rows_env == 64 && d->ksize == 3 && d->groups == 1) || rows_env == -64)) stage_rows = 64;
   pick_patch(H, W, &p.TW, &p.TH, stage_rows, 16);
   p.tiles_w = (W + p.TW - 1) / p.TW;
   p.tiles_h = (H + p.TH - 1) / p.TH;
