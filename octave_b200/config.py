@@ -8,6 +8,11 @@ nan_check = True
 compute_dtype = "bf16"
 
 
+# Inference (eval mode under torch.no_grad()): fold every BatchNorm that directly follows a convolution into that
+# convolution's weights / epilogue.  False keeps the separate BN pass (same results to rounding).
+fold_bn_inference = True
+
+
 def set_compute_dtype(name: str) -> None:
     global compute_dtype
     if name not in ("bf16", "fp32"):

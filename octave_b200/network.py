@@ -81,6 +81,42 @@ def bn_bwd(ctx, dy: Act, mask: Optional[Act], grads: Grads, out: Optional[Act] =
     return dz
 
 
+# ---------------------------------------------------------------------------------------------------
+# Inference: conv -> BatchNorm2d(eval) [-> ReLU] as ONE convolution (reference: ResnestUNet.predict, compose.py:189-199)
+# ---------------------------------------------------------------------------------------------------
+_fold_active = False     # set by ResnestUNet.forward for an eval-mode pass that records no tape
+
+
+def _folded_spec(conv: Conv2d, bn: BatchNorm2d) -> ConvSpec:
+    """ConvSpec of  W' = W * g/sqrt(var+eps) (per output channel),  b' = beta + (b - mean) * g/sqrt(var+eps):
+    eval-mode BN(conv(x)) == conv'(x).  Cached until a parameter or running statistic changes."""
+    key = (conv.weight._version, conv.weight.data_ptr(), bn.weight._version, bn.bias._version, bn.running_mean._version,
+           bn.running_var._version, None if conv.bias is None else conv.bias._version)
+    hit = getattr(conv, "_oct_fold", None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    with torch.no_grad():
+        a = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+        b = bn.bias.detach().float() - bn.running_mean.float() * a
+        if conv.bias is not None:
+            b = b + conv.bias.detach().float() * a
+        w = (conv.weight.detach().float() * a.view(-1, 1, 1, 1)).contiguous()
+    spec = ConvSpec(w, b.contiguous(), conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0],
+                    conv.padding[0], conv.groups)
+    conv._oct_fold = (key, spec)
+    return spec
+
+
+def conv_bn_fwd(conv: Conv2d, bn: BatchNorm2d, x: Act, training: bool, relu: bool, out: Optional[Act] = None):
+    """y = act(BN(conv(x))) -> (y, bn ctx).  Under `_fold_active` (eval, no tape) the BN scale lives in the weights and
+    the shift + ReLU in the conv epilogue: one kernel and no pre-activation tensor; ctx is None."""
+    if _fold_active and not training:
+        return ops.conv_fwd(x, _folded_spec(conv, bn), out=out, act=1 if relu else 0), None
+    z, s = ops.conv_fwd(x, _spec(conv), want_stats=training)
+    y, c, _ = bn_fwd(bn, z, training, relu, out=out, sums=s)
+    return y, c
+
+
 def conv_bwd(conv: nn.Module, x: Act, dz: Act, grads: Grads, need_dx: bool = True, dx_out: Optional[Act] = None,
              accumulate: bool = False, zero_bias_grad: bool = False) -> Optional[Act]:
     """zero_bias_grad: the conv feeds a training-mode BatchNorm, whose input gradient sums to zero over every channel,
@@ -181,8 +217,7 @@ class Bottleneck(nn.Module):
 
     def fwd(self, x: Act, out: Optional[Act] = None):
         tr = self.training
-        z1, s1 = ops.conv_fwd(x, _spec(self.conv1), want_stats=tr)
-        y1, c1, _ = bn_fwd(self.bn1, z1, tr, True, sums=s1)
+        y1, c1 = conv_bn_fwd(self.conv1, self.bn1, x, tr, True)
         s, c2 = self.conv2.fwd(y1, relu_out=False)
         if self.avd:
             sp, _ = ops.pool_fwd(self._avd_pd, s)
@@ -196,8 +231,7 @@ class Bottleneck(nn.Module):
             r = x
             if pool.kernel_size != 1:
                 r, _ = ops.pool_fwd(pd, x)
-            zr, sr = ops.conv_fwd(r, _spec(convd), want_stats=tr)
-            res, cbd, _ = bn_fwd(bnd, zr, tr, False, sums=sr)
+            res, cbd = conv_bn_fwd(convd, bnd, r, tr, False)
             cd = (pd, r, cbd)
         else:
             res = x
@@ -325,8 +359,7 @@ class ResNestDecoder(nn.Module):
     def fwd(self, x: Act, out: Optional[Act] = None):
         tr = self.training
         zr, sr = ops.conv_fwd(x, _spec(self.downsample[0]), want_stats=tr)
-        z0, s0 = ops.conv_fwd(x, _spec(self.conv[0]), want_stats=tr)
-        y0, c0, _ = bn_fwd(self.conv[1], z0, tr, True, sums=s0)
+        y0, c0 = conv_bn_fwd(self.conv[0], self.conv[1], x, tr, True)
         s, cs = self.conv[3].fwd(y0, relu_out=True)
         y, cr, _ = bn_fwd(self.downsample[1], zr, tr, True, res=s, out=out, sums=sr)   # relu(BN(shortcut) + relu(splat))
         return y, (x, y0, c0, cs, s, cr, y)
@@ -478,10 +511,8 @@ class ResnestUNet(nn.Module):
                                       H // 2, W // 2, 0, stats=s0)
             x = xs
         y0, c0, _ = bn_fwd(seq[1], z0, tr, True, sums=s0)
-        z1, s1 = ops.conv_fwd(y0, _spec(seq[3]), want_stats=tr)
-        y1, c1, _ = bn_fwd(seq[4], z1, tr, True, sums=s1)
-        z2, s2 = ops.conv_fwd(y1, _spec(seq[6]), want_stats=tr)
-        y2, c2, _ = bn_fwd(bn1, z2, tr, True, out=out, sums=s2)
+        y1, c1 = conv_bn_fwd(seq[3], seq[4], y0, tr, True)
+        y2, c2 = conv_bn_fwd(seq[6], bn1, y1, tr, True, out=out)
         return y2, (x, y0, c0, y1, c1, c2, y2)
 
     def _stem_bwd(self, ctx, dy: Act, grads: Grads) -> None:
@@ -660,8 +691,16 @@ class ResnestUNet(nn.Module):
 
     # ---- public interface ----------------------------------------------------------------------------
     def forward(self, x):
-        params = self._hot_params()
-        outs = _SegmentorFn.apply(self, x, *params)
+        global _fold_active
+        if not self.training and not torch.is_grad_enabled() and config.fold_bn_inference:
+            # inference: no tape is kept, conv+BN pairs run as one convolution
+            _fold_active = True
+            try:
+                outs, _ = self._fwd(x)
+            finally:
+                _fold_active = False
+        else:
+            outs = _SegmentorFn.apply(self, x, *self._hot_params())
         n = len(outs) - 2
         return tuple(outs[:n]), outs[n], outs[n + 1]
 

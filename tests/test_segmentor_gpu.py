@@ -178,3 +178,46 @@ def test_segmentor_eval_and_predict():
         net(torch.zeros(1, 3, 40, 40, device="cuda"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+def test_inference_bn_folding_matches_separate_bn(mode, tol):
+    """Inference pass (eval mode under no_grad): conv+BatchNorm pairs folded into one convolution (network.conv_bn_fwd,
+    SURVEY §8f.2) against the same pass with the separate BN kernels and against the oracle's eval forward
+    (compose.py:100-187 with every BatchNorm in eval mode)."""
+    from octave_b200 import config, network
+    net, _ = _build(mode, seed=4)
+    _randomize_bn(net, seed=11)
+    sd = {k: v.detach().clone().cpu() for k, v in net.state_dict().items()}
+    net.eval()
+    x, _, _ = synth.octa_batch(2, 80, 96, seed=12)
+    with torch.no_grad():
+        att1, agg1, x41 = net(x.cuda())
+        folded = [m for m in net.modules() if hasattr(m, "_oct_fold")]
+        config.fold_bn_inference = False
+        try:
+            att0, agg0, x40 = net(x.cuda())
+        finally:
+            config.fold_bn_inference = True
+        _, pred = net.predict(x.cuda(), method='one-hot')
+    # 3 stem convs - 1 (space-to-depth conv keeps its BN) + 16 bottleneck conv1 + 4 downsample + 5 decoder conv.0
+    assert len(folded) == 2 + 16 + 4 + 5
+    assert l2err(agg1, agg0) < tol and l2err(x41, x40) < tol
+    for a1, a0 in zip(att1, att0):
+        assert l2err(a1, a0) < tol
+    _, agg_o, x4_o = O.segmentor_forward(sd, x, training=False)
+    assert l2err(agg1, agg_o) < (1e-4 if mode == "fp32" else 3e-2)
+    assert l2err(x41, x4_o) < (1e-4 if mode == "fp32" else 3e-2)
+    if mode == "fp32":
+        assert torch.equal(pred.cpu().argmax(1), agg_o.argmax(1))      # bit-exact masks
+    # a parameter update invalidates the folded operands
+    with torch.no_grad():
+        net.decoder_0.conv[1].weight.mul_(2.0)
+        _, agg2, _ = net(x.cuda())
+        config.fold_bn_inference = False
+        try:
+            _, agg3, _ = net(x.cuda())
+        finally:
+            config.fold_bn_inference = True
+    e_fold, e_update = l2err(agg2, agg3), l2err(agg2, agg1)
+    assert e_fold < tol and e_update > 5 * max(e_fold, 1e-6), (e_fold, e_update)
