@@ -264,6 +264,55 @@ def segmentor_forward(sd: Mapping[str, Tensor], x: Tensor, training: bool = True
     return tuple(attentions), agg_map, x_4
 
 
+def parallel_head_forward(sd: Mapping[str, Tensor], x: Tensor, training: bool = True,
+                          gating_level: Optional[int] = None, st: Optional[BNState] = None, p: str = ""):
+    """ResnestUnetParallelHead.forward (segmentor/compose.py:291-350) when gating_level is None, else
+    ResnestUnetParallelHeadAttentionGate.forward (:432-515; constructor default gating_leveL=3, level 4 gated only
+    when gating_level > 3).  A second decoder pair (`*_c`) hangs off the encoder's x_1 and shares the x_0_0 skip.
+    -> agg [2,B,C,H,W]   or   ((attentions), (attentions_c)), agg   with both tuples full-res first."""
+    gated = gating_level is not None
+    gl = gating_level if gated else -1
+    x_0_0 = stem(sd, p + "encoder_0_1_2.", x, training, st)
+    x_0_1 = F.max_pool2d(x_0_0, 3, 2, 1)
+    x_1 = resnest_layer(sd, p + "encoder_1.", x_0_1, 3, 1, False, training, st)
+    x_2 = resnest_layer(sd, p + "encoder_2.", x_1, 4, 2, True, training, st)
+    x_3 = resnest_layer(sd, p + "encoder_3.", x_2, 6, 2, True, training, st)
+    down_padding = right_padding = False
+    if x_3.shape[2] % 2 == 1:
+        x_3 = F.pad(x_3, (0, 0, 0, 1)); down_padding = True
+    if x_3.shape[3] % 2 == 1:
+        x_3 = F.pad(x_3, (0, 1, 0, 0)); right_padding = True
+    x_4 = resnest_layer(sd, p + "encoder_4.", x_3, 3, 2, True, training, st)
+    attentions, attentions_c = [], []
+
+    def level(name: str, inp: Tensor, on: bool, sink: list) -> Tensor:
+        d = decoder_block(sd, p + "decoder_" + name + ".", inp, training, st)
+        if on:
+            d, y = attention_gate(sd, p + "aag_" + name + ".", d)
+            sink.append(y)
+        return d
+
+    d_4 = torch.cat((x_3, upsampling(sd, p + "upsampling_4.", x_4)), dim=1)
+    if down_padding:
+        d_4 = d_4[:, :, :-1, :]
+    if right_padding:
+        d_4 = d_4[:, :, :, :-1]
+    d_4 = level("4", d_4, gated and gl > 3, attentions)
+    d_3 = level("3", torch.cat((x_2, upsampling(sd, p + "upsampling_3.", d_4)), dim=1), gated and gl >= 3, attentions)
+    d_2 = level("2", torch.cat((x_1, upsampling(sd, p + "upsampling_2.", d_3)), dim=1), gated and gl >= 2, attentions)
+    d_1 = level("1", torch.cat((x_0_0, upsampling(sd, p + "upsampling_1.", d_2)), dim=1), gated and gl >= 1, attentions)
+    d_0 = level("0", upsampling(sd, p + "upsampling_0.", d_1), gated and gl >= 0, attentions)
+    # parallel branch: from the layer1 features, not from d_2
+    d_1_c = level("1_c", torch.cat((x_0_0, upsampling(sd, p + "upsampling_1_c.", x_1)), dim=1), gated and gl >= 1, attentions_c)
+    d_0_c = level("0_c", upsampling(sd, p + "upsampling_0_c.", d_1_c), gated and gl >= 0, attentions_c)
+    agg = torch.stack([F.conv2d(d_0, sd[p + "fc.weight"], sd[p + "fc.bias"]),
+                       F.conv2d(d_0_c, sd[p + "fc_c.weight"], sd[p + "fc_c.bias"])])
+    if not gated:
+        return agg
+    attentions.reverse(); attentions_c.reverse()
+    return (tuple(attentions), tuple(attentions_c)), agg
+
+
 # =================================================================================================
 # Discriminator
 # =================================================================================================

@@ -58,3 +58,32 @@ def test_no_discriminator_attribute_when_depth_is_zero():
     from architectures.models.octa import OctaScribbleNet
     m = OctaScribbleNet(torch.Size((2, 3, 64, 64)), torch.Size((2, 2, 64, 64)), True, False, discriminator_depth=0)
     assert not hasattr(m, "discriminator")   # models/octa.py:46
+
+
+@pytest.mark.parametrize("gated", [False, True])
+def test_parallel_head_siblings_match_reference(gated):
+    """ResnestUnetParallelHead / ...AttentionGate (compose.py:233-527): same keys, shapes, seeded init, RNG consumption
+    and constructor signature as the reference."""
+    ref = refload.load()
+    from architectures.segmentor import compose
+    name = "ResnestUnetParallelHeadAttentionGate" if gated else "ResnestUnetParallelHead"
+    rc, mc = getattr(ref.compose, name), getattr(compose, name)
+    torch.manual_seed(0)
+    r = rc(2, False)
+    ra = torch.rand(4)
+    torch.manual_seed(0)
+    m = mc(2, False)
+    rb = torch.rand(4)
+    a, b = r.state_dict(), m.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    assert torch.equal(ra, rb)
+    m.load_state_dict(r.state_dict())
+    r.load_state_dict(m.state_dict())
+    pa, pb = inspect.signature(rc.__init__).parameters, inspect.signature(mc.__init__).parameters
+    assert list(pa) == list(pb)
+    for k in pa:
+        assert pa[k].default == pb[k].default or pa[k].default is inspect._empty
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 64, 64))

@@ -105,3 +105,36 @@ def test_segmentor_and_discriminator_match_reference(ref):
     att_r, agg_r, _ = net.segmentor(x)
     att_o, agg_o, _ = O.segmentor_forward({k: v for k, v in net.segmentor.state_dict().items()}, x, training=False)
     torch.testing.assert_close(agg_o, agg_r, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("gating_level", [None, 3, 4])
+def test_parallel_head_oracle_matches_reference(ref, gating_level):
+    """O.parallel_head_forward vs ResnestUnetParallelHead / ...AttentionGate (compose.py:233-527), train mode incl. the
+    BatchNorm running statistics, then eval mode.  80x64: H/16 = 5 is odd (pad/crop path)."""
+    torch.manual_seed(1)
+    if gating_level is None:
+        net = ref.compose.ResnestUnetParallelHead(2, False)
+    else:
+        net = ref.compose.ResnestUnetParallelHeadAttentionGate(2, False, None, gating_level)
+    x, _, _ = synth.octa_batch(2, 80, 64, seed=6)
+    for training in (True, False):
+        net.train(training)
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        st = O.BNState()
+        out_o = O.parallel_head_forward(sd, x, training, gating_level, st)
+        with torch.no_grad():
+            out_r = net(x)
+        if gating_level is None:
+            assert out_r.shape == (2, 2, 2, 80, 64)
+            torch.testing.assert_close(out_o, out_r, rtol=1e-4, atol=1e-5)
+        else:
+            (a_o, c_o), g_o = out_o
+            (a_r, c_r), g_r = out_r
+            assert len(a_o) == len(a_r) == (5 if gating_level > 3 else 4) and len(c_o) == len(c_r) == 2
+            torch.testing.assert_close(g_o, g_r, rtol=1e-4, atol=1e-5)
+            for u, v in zip(a_o + c_o, a_r + c_r):
+                torch.testing.assert_close(u, v, rtol=1e-4, atol=1e-6)
+        if training:
+            new_sd = net.state_dict()
+            for k, v in st.updated.items():
+                torch.testing.assert_close(v, new_sd[k], rtol=1e-4, atol=1e-6, msg=k)
