@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — generate tests/golden/*.pt by running the REAL reference (imported from
 /root/reference, CPU fp32).  Run here (the reference cannot travel to the GPU box); the fixtures are
-committed.  Usage:  python -m oracle.make_golden [losses|segmentor|discriminator|all]
+committed.  Usage:  python -m oracle.make_golden [losses|networks|all]
 """
 from __future__ import annotations
 
@@ -60,6 +60,51 @@ def make_losses(ref):
     print("losses.pt", {k: float(v["wpce"]) for k, v in cases.items()})
 
 
+NET_SEED, NET_B, NET_H, NET_W = 123, 4, 64, 80          # 80/16 = 5 is odd: the pad/crop path of compose.py:125-147
+BN_KEYS = ("encoder_0_1_2.1.running_mean", "encoder_2.0.conv2.bn0.running_var", "decoder_0.conv.1.running_mean",
+           "decoder_3.downsample.1.running_var", "encoder_4.2.bn3.running_mean")
+
+
+def make_networks(ref):
+    """Seeded reference networks on one synthetic batch.  Only the seed travels: the host mirror's seeded construction
+    is identical to the reference's (tests/test_host_mirror.py), so the consumer rebuilds the weights from NET_SEED."""
+    out = {"seed": NET_SEED, "B": NET_B, "H": NET_H, "W": NET_W, "batch_seed": 21}
+    x, ys, _ = synth.octa_batch(NET_B, NET_H, NET_W, seed=21)
+    shape = (torch.Size((NET_B, 3, NET_H, NET_W)), torch.Size((NET_B, 2, NET_H, NET_W)))
+    torch.manual_seed(NET_SEED)
+    net = ref.OctaScribbleNet(*shape, True, False, instance_noise=False, label_noise=False)
+    net.train()
+    with torch.no_grad():
+        att, agg, x4 = net.segmentor(x)
+        sd = net.segmentor.state_dict()
+        out["segmentor_train"] = {"att": [a.clone() for a in att], "agg": agg.clone(), "x4": x4.clone(),
+                                  "bn": {k: sd[k].clone() for k in BN_KEYS}}
+        pyr = synth.mask_pyramid(NET_B, NET_H, NET_W)
+        logit = net.discriminator(pyr)
+        dsd = net.discriminator.state_dict()
+        out["discriminator_train"] = {"logit": logit.clone(),
+                                      "u": {k: v.clone() for k, v in dsd.items() if k.endswith("weight_u")}}
+        net.eval()
+        att, agg, x4 = net.segmentor(x)
+        out["segmentor_eval"] = {"att": [a.clone() for a in att], "agg": agg.clone(), "x4": x4.clone()}
+    for name, gl in (("parallel_head", None), ("parallel_head_ag3", 3)):
+        torch.manual_seed(NET_SEED)
+        if gl is None:
+            pn = ref.compose.ResnestUnetParallelHead(2, False)
+        else:
+            pn = ref.compose.ResnestUnetParallelHeadAttentionGate(2, False, None, gl)
+        pn.train()
+        with torch.no_grad():
+            o = pn(x)
+        if gl is None:
+            out[name] = {"agg": o.clone()}
+        else:
+            (a, c), agg = o
+            out[name] = {"agg": agg.clone(), "att": [t.clone() for t in a], "att_c": [t.clone() for t in c]}
+    torch.save(out, os.path.join(GOLD, "networks.pt"))
+    print("networks.pt", float(out["segmentor_train"]["agg"].abs().mean()), float(out["parallel_head"]["agg"].abs().mean()))
+
+
 def main(which: str):
     ref = refload.load()
     if ref is None:
@@ -68,10 +113,8 @@ def main(which: str):
     torch.set_num_threads(os.cpu_count() or 1)
     if which in ("losses", "all"):
         make_losses(ref)
-    if which in ("segmentor", "all") and "make_segmentor" in globals():
-        make_segmentor(ref)  # noqa: F821
-    if which in ("discriminator", "all") and "make_discriminator" in globals():
-        make_discriminator(ref)  # noqa: F821
+    if which in ("networks", "all"):
+        make_networks(ref)
 
 
 if __name__ == "__main__":

@@ -49,3 +49,69 @@ def test_oracle_jsd_known_answer():
     b = torch.zeros(1, 2, 4, 4); b[:, 0] = .8; b[:, 1] = .2
     q1 = torch.full((1, 2, 2, 2), .5); q2 = torch.zeros(1, 2, 1, 1); q2[:, 0] = .25; q2[:, 1] = .75
     assert abs(O.interlayer_divergence_jsd([b, q1, q2]).item() - 0.0967728) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole networks: outputs of the REAL reference (oracle/make_golden.py make_networks) for seeded weights.  Only the seed
+# is stored: the host mirror's seeded construction equals the reference's (tests/test_host_mirror.py).
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def nets():
+    return torch.load(os.path.join(GOLD, "networks.pt"))
+
+
+def _close(a, b, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+def test_oracle_segmentor_and_discriminator_match_reference_golden(nets):
+    from architectures.models.octa import OctaScribbleNet
+    from tests import synth
+    B, H, W = nets["B"], nets["H"], nets["W"]
+    x, _, _ = synth.octa_batch(B, H, W, seed=nets["batch_seed"])
+    torch.manual_seed(nets["seed"])
+    m = OctaScribbleNet(torch.Size((B, 3, H, W)), torch.Size((B, 2, H, W)), True, False, instance_noise=False, label_noise=False)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    seg = {k[len("segmentor."):]: v for k, v in sd.items() if k.startswith("segmentor.")}
+    st = O.BNState()
+    att, agg, x4 = O.segmentor_forward(seg, x, training=True, st=st)
+    g = nets["segmentor_train"]
+    _close(agg, g["agg"]); _close(x4, g["x4"])
+    assert torch.equal(agg.argmax(1), g["agg"].argmax(1))
+    assert len(att) == len(g["att"]) == 5
+    for a, b in zip(att, g["att"]):
+        _close(a, b, atol=1e-6)
+    for k, v in g["bn"].items():
+        _close(st.updated[k], v, atol=1e-6)
+    dis = {k[len("discriminator."):]: v for k, v in sd.items() if k.startswith("discriminator.")}
+    upd = {}
+    logit = O.discriminator_forward(dis, synth.mask_pyramid(B, H, W), depth=4, training=True, updated=upd)
+    _close(logit, nets["discriminator_train"]["logit"], atol=1e-6)
+    for k, v in nets["discriminator_train"]["u"].items():
+        _close(upd[k], v, rtol=1e-5, atol=1e-7)
+    seg_eval = dict(seg); seg_eval.update(st.updated)
+    att, agg, x4 = O.segmentor_forward(seg_eval, x, training=False)
+    g = nets["segmentor_eval"]
+    _close(agg, g["agg"]); _close(x4, g["x4"])
+    for a, b in zip(att, g["att"]):
+        _close(a, b, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,gating_level", [("parallel_head", None), ("parallel_head_ag3", 3)])
+def test_oracle_parallel_heads_match_reference_golden(nets, name, gating_level):
+    from architectures.segmentor import compose
+    from tests import synth
+    x, _, _ = synth.octa_batch(nets["B"], nets["H"], nets["W"], seed=nets["batch_seed"])
+    torch.manual_seed(nets["seed"])
+    m = compose.ResnestUnetParallelHead(2, False) if gating_level is None else \
+        compose.ResnestUnetParallelHeadAttentionGate(2, False, None, gating_level)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    out = O.parallel_head_forward(sd, x, True, gating_level, O.BNState())
+    g = nets[name]
+    if gating_level is None:
+        _close(out, g["agg"])
+    else:
+        (a, c), agg = out
+        _close(agg, g["agg"])
+        for u, v in zip(list(a) + list(c), g["att"] + g["att_c"]):
+            _close(u, v, atol=1e-6)

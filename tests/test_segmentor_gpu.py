@@ -221,3 +221,48 @@ def test_inference_bn_folding_matches_separate_bn(mode, tol):
             config.fold_bn_inference = True
     e_fold, e_update = l2err(agg2, agg3), l2err(agg2, agg1)
     assert e_fold < tol and e_update > 5 * max(e_fold, 1e-6), (e_fold, e_update)
+
+
+def test_cuda_path_matches_reference_golden_vectors():
+    """fp32 CUDA path against outputs of the REAL reference for seeded weights (tests/golden/networks.pt, written by
+    oracle/make_golden.py from /root/reference): ResnestUNet train-mode forward + BatchNorm buffers, folded eval-mode
+    inference, and the two parallel-head siblings.  No oracle in the loop."""
+    import os
+    from octave_b200 import config, network, network_parallel
+    nets = torch.load(os.path.join(os.path.dirname(__file__), "golden", "networks.pt"))
+    config.set_compute_dtype("fp32")
+    H, W = nets["H"], nets["W"]
+    x, _, _ = synth.octa_batch(nets["B"], H, W, seed=nets["batch_seed"])
+    torch.manual_seed(nets["seed"])
+    net = network.ResnestUNet(2, False).cuda().train()       # OctaScribbleNet builds its segmentor first with these arguments
+    g = nets["segmentor_train"]
+    with torch.no_grad():
+        att, agg, x4 = net(x.cuda())
+    assert l2err(agg, g["agg"]) < 1e-4 and l2err(x4, g["x4"]) < 2e-3, (l2err(agg, g["agg"]), l2err(x4, g["x4"]))
+    assert torch.equal(agg.argmax(1).cpu(), g["agg"].argmax(1))
+    for a, b in zip(att, g["att"]):
+        assert a.shape == b.shape and l2err(a, b) < 1e-4
+    new = net.state_dict()
+    for k, v in g["bn"].items():
+        assert l2err(new[k], v) < 1e-4, k
+    net.eval()
+    g = nets["segmentor_eval"]
+    with torch.no_grad():
+        att, agg, x4 = net(x.cuda())                          # conv+BN folded inference path
+    assert l2err(agg, g["agg"]) < 1e-4 and l2err(x4, g["x4"]) < 1e-4, (l2err(agg, g["agg"]), l2err(x4, g["x4"]))
+    assert torch.equal(agg.argmax(1).cpu(), g["agg"].argmax(1))
+    for name, gl in (("parallel_head", None), ("parallel_head_ag3", 3)):
+        torch.manual_seed(nets["seed"])
+        pn = network_parallel.ResnestUnetParallelHead(2, False) if gl is None else \
+            network_parallel.ResnestUnetParallelHeadAttentionGate(2, False, None, gl)
+        pn = pn.cuda().train()
+        with torch.no_grad():
+            out = pn(x.cuda())
+        g = nets[name]
+        if gl is None:
+            assert l2err(out, g["agg"]) < 1e-4
+        else:
+            (a, c), agg = out
+            assert l2err(agg, g["agg"]) < 1e-4
+            for u, v in zip(list(a) + list(c), g["att"] + g["att_c"]):
+                assert u.shape == v.shape and l2err(u, v) < 1e-4
