@@ -753,7 +753,11 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
     switch (BN) {
       // pipeline depth sized to ~160-190 KB in flight per SM: the persistent CTA is alone on its SM, so the ring must
       // cover the HBM bandwidth-delay product by itself, also for the small stages of narrow layers
-      case 256: return launch_fwd<256, 64, 3>(tmA, tmB, p, (int)grid, s);
+      case 256: {
+        static const int st2 = [] { const char* e = getenv("OCTAVE_FWD_STAGES"); return e ? atoi(e) : 3; }();
+        if (st2 == 2) return launch_fwd<256, 64, 2>(tmA, tmB, p, (int)grid, s);   // ring-depth probe
+        return launch_fwd<256, 64, 3>(tmA, tmB, p, (int)grid, s);
+      }
       case 128: return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
       case 64: return launch_fwd<64, 64, 7>(tmA, tmB, p, (int)grid, s);
       case 32: return launch_fwd<32, 64, 9>(tmA, tmB, p, (int)grid, s);
@@ -847,7 +851,13 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
     switch (BN) {
       case 256:
         if (one_a) return launch_wgrad<256, 64, 64, 1, 2>(tmDY, tmX, p, grid, s);
-        if (stage_rows == 64) return launch_wgrad<256, 64, 64, 2, 4, 64>(tmDY, tmX, p, grid, s);
+        if (stage_rows == 64) {
+          // several waves of CTAs and no split-K: two co-resident CTAs per SM (2 x 2 stages, 2 x 256 TMEM columns) hide
+          // each other's prologue and reduction epilogue: 780 -> 697 us on decoder_4.conv.0 (OCTAVE_WGRAD_2CTA=0: off)
+          static const int two = [] { const char* e = getenv("OCTAVE_WGRAD_2CTA"); return e ? atoi(e) : 1; }();
+          if (two && split == 1 && out_tiles >= 2 * sms) return launch_wgrad<256, 64, 64, 2, 2, 64>(tmDY, tmX, p, grid, s);
+          return launch_wgrad<256, 64, 64, 2, 4, 64>(tmDY, tmX, p, grid, s);
+        }
         return launch_wgrad<256, 64, 64, 2, 2>(tmDY, tmX, p, grid, s);
       case 128: return one_a ? launch_wgrad<128, 64, 64, 1, 4>(tmDY, tmX, p, grid, s) : launch_wgrad<128, 64, 64, 2, 3>(tmDY, tmX, p, grid, s);
       default: return one_a ? launch_wgrad<64, 64, 64, 1, 6>(tmDY, tmX, p, grid, s) : launch_wgrad<64, 64, 64, 2, 4>(tmDY, tmX, p, grid, s);

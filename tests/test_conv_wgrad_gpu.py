@@ -13,6 +13,7 @@ SHAPES = [  # B, H, W, cin, cout, k
     (1, 37, 41, 256, 192, 3),     # ragged extents, a half-filled second Cout tile
     (2, 20, 20, 256, 256, 1),     # 1x1: pixels flattened to one row
     (1, 100, 100, 256, 128, 3),   # 20x4 patches fill the stage exactly
+    (1, 16, 16, 1280, 1024, 3),   # 360 output tiles, no split-K: two co-resident CTAs per SM
 ]
 
 
