@@ -209,7 +209,7 @@ def kernel_rooflines(peaks, B, H, W):
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=32, 400^2 from one `ncu --set full` capture
     # (profiles/ncu_conv_fat_512x256_bn256_r01.txt: 330.4 MB + 137.7 MB; algorithmic minimum x + y + w = 494 MB)
     traffic = 468.1e6 if (B, H, W) == (32, 400, 400) else None
-    out["roofline"] = {"kernel": "conv_tc_kernel<256,64,3> (decoder_2.conv.0 fwd 3x3 512->256)", "bound": "tensor",
+    out["roofline"] = {"kernel": "conv_tc_kernel<256,64,4> (decoder_2.conv.0 fwd 3x3 512->256)", "bound": "tensor",
                        "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                        "traffic": traffic, "algorithmic_flop": flops,
                        "peak_source": peaks["source"] + " burst (kernel timed alone)", "ms_per_launch": ms}

@@ -86,7 +86,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   constexpr int COLS_W = BN >= 32 ? BN / 2 : BN;   // columns handled by one epilogue warp
   constexpr int NCHUNK_W = COLS_W / 16;
-  constexpr int PITCH = COLS_W * 2 + 16;           // bytes per staged row (+16 spreads the banks)
+  // SLAB (256-column tiles with a 4-deep ring): the epilogue staging shrinks from 32 x 272 B to 32 x 128 B per warp - one
+  // 64-column slab at a time, 16-byte units XOR-swizzled by the row instead of padded - which frees the 34 KB the fourth
+  // 48 KB stage needs.
+  constexpr bool SLAB = (BN == 256 && STAGES >= 4);
+  constexpr int PITCH = SLAB ? 128 : COLS_W * 2 + 16;   // bytes per staged row (+16 spreads the banks)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -234,6 +238,75 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       const int nvalid = min(COLS_W, p.cout_g - n0);
       tc::mbar_wait(tc::smem_u32(&acc_full[buf]), (li >> 1) & 1u);
       tc::fence_after_sync();
+      if constexpr (SLAB) {
+        // two 64-column slabs per warp: TMEM -> registers -> swizzled staging -> statistics -> coalesced stores
+        const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
+        const int rx = lane & 7;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t v[4][16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tc::tmem_ld16(taddr + (h2 * 4 + c) * 16, v[c]);
+          tc::tmem_ld_wait();
+          if (h2 == 1) {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              f[i] = __uint_as_float(v[cc][i]);
+              if (p.bias) f[i] += __ldg(p.bias + cbase + (h2 * 4 + cc) * 16 + i);
+            }
+            if (p.act) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
+            }
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = 0.f;
+            }
+            uint4 u0, u1;
+            u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
+            u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
+            u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
+            u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
+            *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc) ^ rx) << 4)) = u0;
+            *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc + 1) ^ rx) << 4)) = u1;
+          }
+          __syncwarp();
+          if (p.stats) {
+            // lane owns the column pair `lane` of this slab (unit lane/4, word lane%4) over the 32 rows
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int row = 0; row < 32; ++row) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stage + row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + (lane & 3) * 4);
+              float a, b;
+              bf16x2_unpack(u, a, b);
+              s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+            }
+            sacc[h2][0] += s0; sacc[h2][1] += s1; sacc[h2][2] += q0; sacc[h2][3] += q1;
+          }
+          {
+            // 8 lanes cover one 128-byte row, 4 rows per instruction
+            const int sub = lane & 7, rsel = lane >> 3;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 4) {
+              const int row = r0 + rsel;
+              const long long off = __shfl_sync(0xffffffffu, row_off, row);
+              if (off >= 0 && h2 * 64 + sub * 8 < nvalid) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((sub ^ (row & 7)) << 4));
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + h2 * 64 + sub * 8) = val;
+              }
+            }
+          }
+          __syncwarp();   // the staging rows are rewritten by the next slab / tile
+        }
+        continue;
+      }
       if (works) {
         const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
         // TMEM loads of up to 64 columns in flight before ONE wait; the accumulator goes back to the MMA warp as soon as
@@ -620,8 +693,9 @@ void pick_patch(int H, int W, int* TW, int* TH, int max_px = 128, int quantum = 
 
 template <int BN, int BK, int STAGES>
 int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int grid, cudaStream_t s) {
-  constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + 8 * 32 * ((BN >= 32 ? BN / 2 : BN) * 2 + 16) + 1024;
-  static_assert(smem <= 227 * 1024, "shared memory budget");
+  constexpr int pitch = (BN == 256 && STAGES >= 4) ? 128 : (BN >= 32 ? BN / 2 : BN) * 2 + 16;   // see SLAB in the kernel
+  constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + 8 * 32 * pitch + 1024;
+  static_assert(smem <= 226 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -754,9 +828,12 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
       // pipeline depth sized to ~160-190 KB in flight per SM: the persistent CTA is alone on its SM, so the ring must
       // cover the HBM bandwidth-delay product by itself, also for the small stages of narrow layers
       case 256: {
-        static const int st2 = [] { const char* e = getenv("OCTAVE_FWD_STAGES"); return e ? atoi(e) : 3; }();
-        if (st2 == 2) return launch_fwd<256, 64, 2>(tmA, tmB, p, (int)grid, s);   // ring-depth probe
-        return launch_fwd<256, 64, 3>(tmA, tmB, p, (int)grid, s);
+        // four 48 KB stages with the slab epilogue (see SLAB): bit-exact with the 3-stage kernel and 2.6-3.8 % faster
+        // (profiles/slab_epilogue_ab_r01.log); OCTAVE_FWD_STAGES=3 / 2 select the padded-staging kernel / the ring probe
+        static const int st2 = [] { const char* e = getenv("OCTAVE_FWD_STAGES"); return e ? atoi(e) : 4; }();
+        if (st2 == 2) return launch_fwd<256, 64, 2>(tmA, tmB, p, (int)grid, s);
+        if (st2 == 3) return launch_fwd<256, 64, 3>(tmA, tmB, p, (int)grid, s);
+        return launch_fwd<256, 64, 4>(tmA, tmB, p, (int)grid, s);
       }
       case 128: return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
       case 64: return launch_fwd<64, 64, 7>(tmA, tmB, p, (int)grid, s);
