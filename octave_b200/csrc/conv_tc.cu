@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
   // SLAB (256-column tiles with a 4-deep ring): the epilogue staging shrinks from 32 x 272 B to 32 x 128 B per warp - one
   // 64-column slab at a time, 16-byte units XOR-swizzled by the row instead of padded - which frees the 34 KB the fourth
   // 48 KB stage needs.
-  constexpr bool SLAB = (BN == 256 && STAGES >= 4);
+  // The same trade for the 128-column kernel (6 x 32 KB stages, one slab per warp) is compiled but opt-in
+  // (OCTAVE_FWD128_STAGES=6): it has not been A/B-ed on the GPU yet.
+  constexpr bool SLAB = (BN == 256 && STAGES >= 4) || (BN == 128 && STAGES >= 6);
+  constexpr int NSLAB = COLS_W >= 64 ? COLS_W / 64 : 1;   // 64-column slabs per epilogue warp
   constexpr int PITCH = SLAB ? 128 : COLS_W * 2 + 16;   // bytes per staged row (+16 spreads the banks)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -239,16 +242,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       tc::mbar_wait(tc::smem_u32(&acc_full[buf]), (li >> 1) & 1u);
       tc::fence_after_sync();
       if constexpr (SLAB) {
-        // two 64-column slabs per warp: TMEM -> registers -> swizzled staging -> statistics -> coalesced stores
+        // 64-column slabs (two per warp for BN = 256): TMEM -> registers -> swizzled staging -> statistics -> stores
         const uint32_t taddr = tmem_base + buf * ACC_COLS + hsel * COLS_W + ((uint32_t)(q * 32) << 16);
         const int rx = lane & 7;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
+        for (int h2 = 0; h2 < NSLAB; ++h2) {
           uint32_t v[4][16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) tc::tmem_ld16(taddr + (h2 * 4 + c) * 16, v[c]);
           tc::tmem_ld_wait();
-          if (h2 == 1) {
+          if (h2 == NSLAB - 1) {
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
@@ -693,7 +696,8 @@ void pick_patch(int H, int W, int* TW, int* TH, int max_px = 128, int quantum = 
 
 template <int BN, int BK, int STAGES>
 int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int grid, cudaStream_t s) {
-  constexpr int pitch = (BN == 256 && STAGES >= 4) ? 128 : (BN >= 32 ? BN / 2 : BN) * 2 + 16;   // see SLAB in the kernel
+  constexpr int pitch = ((BN == 256 && STAGES >= 4) || (BN == 128 && STAGES >= 6)) ? 128
+                                                                                    : (BN >= 32 ? BN / 2 : BN) * 2 + 16;   // see SLAB
   constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + 8 * 32 * pitch + 1024;
   static_assert(smem <= 226 * 1024, "shared memory budget");
   static bool attr_done = false;
@@ -835,7 +839,12 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
         if (st2 == 3) return launch_fwd<256, 64, 3>(tmA, tmB, p, (int)grid, s);
         return launch_fwd<256, 64, 4>(tmA, tmB, p, (int)grid, s);
       }
-      case 128: return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
+      case 128: {
+        // opt-in, not yet measured: six stages with the slab epilogue (plain stores only)
+        static const int st1 = [] { const char* e = getenv("OCTAVE_FWD128_STAGES"); return e ? atoi(e) : 5; }();
+        if (st1 == 6 && !p.accumulate) return launch_fwd<128, 64, 6>(tmA, tmB, p, (int)grid, s);
+        return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
+      }
       case 64: return launch_fwd<64, 64, 7>(tmA, tmB, p, (int)grid, s);
       case 32: return launch_fwd<32, 64, 9>(tmA, tmB, p, (int)grid, s);
       default: return launch_fwd<16, 64, 10>(tmA, tmB, p, (int)grid, s);
