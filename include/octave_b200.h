@@ -4,7 +4,7 @@
  * The reference (IoBT-VISTEC/OCTAve, /root/reference) has no FFI of its own: its boundary is the
  * Python class surface.  This header is the C-ABI that sits directly beneath that
  * surface; each entry point names the reference function whose arithmetic it replaces.  The Python
- * host (octave_b200/*.py, mirroring architectures/*.py of the reference) binds these symbols with
+ * host (the octave_b200 Python package, mirroring the reference's architectures package) binds these symbols with
  * ctypes.
  *
  * Conventions

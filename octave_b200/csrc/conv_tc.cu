@@ -27,8 +27,6 @@
 
 namespace {
 
-constexpr int kThreads = 192;
-
 struct ConvTcParams {
   int taps;
   int tap_dh[9], tap_dw[9];
