@@ -31,6 +31,11 @@ int octave_abi_version(void);
 int octave_sm_count(void);
 /* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
 unsigned long long octave_launch_count(void);
+/* Deterministic mode (process-wide, default off): reductions that are normally split across CTAs and merged with fp32
+ * atomics (split-K weight gradients, K-split linears, head parameter gradients) run with ONE writer per output element,
+ * so two runs on the same inputs give bit-identical results.  Slower for the small layers; off for benchmarks. */
+void octave_set_deterministic(int on);
+int octave_get_deterministic(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K9 — fused loss kernel (forward statistics pass + gradient pass).
@@ -94,6 +99,20 @@ int octave_loss_bwd(const OctaveLossDesc* d, const void* yhat, const void* ys,
                     const void* const* att, const float* d_real, const float* d_fake,
                     const void* stats, const float* gscale, void* g_yhat, void* const* g_att,
                     float* g_real, float* g_fake, void* stream);
+
+/* Fused single pass of the G-step (training loop): loss VALUES and GRADIENTS from one sweep over the maps.
+ * total = lambdas[0]*WPCE + lambdas[1]*KLD + lambdas[2]*LSG (host float[3]); the gradients of `total` w.r.t. yhat,
+ * att[k] and d_fake are written in the same pass (a labels-only pre-pass supplies the class counts of losses.py:34-38),
+ * out[0..5] as octave_loss_fwd, out[6] = total.  Supported: C == 2 pyramids (octave_loss_fused_supported), flags within
+ * WPCE | KLD | LSG | FROM_LOGITS | WPCE_FULL.  Reductions are in a fixed order (bit-reproducible).
+ * octave_loss_scale_grads multiplies the written gradients by *g_total (device) and is a no-op when it is 1. */
+int octave_loss_fused_supported(const OctaveLossDesc* d);
+size_t octave_loss_fused_stats_bytes(const OctaveLossDesc* d);
+int octave_loss_fused(const OctaveLossDesc* d, const void* yhat, const void* ys, const void* const* att,
+                      const float* d_fake, const float* lambdas /* host [3] */, void* stats, float* out,
+                      void* g_yhat, void* const* g_att, float* g_fake, void* stream);
+int octave_loss_scale_grads(const OctaveLossDesc* d, const float* g_total /* device */, void* g_yhat,
+                            void* const* g_att, float* g_fake, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1/K2/K3 — convolutions.  Activations NHWC; a tensor argument is a *channel view*: base pointer,
@@ -179,10 +198,13 @@ int octave_chan_stats(const OctaveAct* x, double* sums /* [2C]: sum, sum of squa
 int octave_bn_prepare(int32_t C, double count, const double* sums, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, int64_t* num_batches_tracked, float eps, float momentum,
                       int32_t training, float* ab /* [2C] scale, shift */, float* mean_invstd /* [2C] */, void* stream);
-/* y = act(x*a[c] + b[c] + res); ab NULL => identity; gap (nullable, fp32 [B][C/2], pre-zeroed by the callee):
- * gap[b][c % (C/2)] += sum_pixels y  — the radix-sum + global-average-pool of resnest.py:106-116. */
+/* y = act(x*a[c] + b[c] + res); ab NULL => identity; gap (nullable, fp32 [B][C/2], overwritten):
+ * gap[b][c % (C/2)] = sum_pixels y  — the radix-sum + global-average-pool of resnest.py:106-116, reduced in a fixed
+ * order (bit-reproducible, no floating-point atomics) through gap_ws: octave_affine_gap_ws_bytes(x) bytes whose first
+ * 65536 32-bit words (one counter per image) are zero before the first launch (the kernel leaves them zero). */
+size_t octave_affine_gap_ws_bytes(const OctaveAct* x);
 int octave_affine_act(const OctaveAct* x, const float* ab, const OctaveAct* res, int32_t relu, const OctaveAct* y,
-                      float* gap, void* stream);
+                      float* gap, void* gap_ws, void* stream);
 /* dz = dy * (mask > 0) (mask nullable); or, with mask NULL and relu_ab != NULL (the [2C] scale/shift of this very BN),
  * the ReLU mask is recomputed from x as (x*a+b > 0) instead of being read.  sums2[c] = sum dz, sums2[C+c] = sum dz * xhat. */
 int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,

@@ -84,6 +84,7 @@ LOSS_FROM_LOGITS = 1 << 5
 LOSS_WPCE_FULL = 1 << 6
 LOSS_KLD_STOPGRAD = 1 << 7
 LOSS_JSD = 1 << 8
+LOSS_OUT_TOTAL = 6
 LOSS_OUT_SLOTS = 8
 
 _vp = C.c_void_p
@@ -100,6 +101,15 @@ lib.octave_loss_fwd.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _
 lib.octave_loss_bwd.restype = C.c_int
 lib.octave_loss_bwd.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
                                 C.POINTER(_vp), _vp, _vp, _vp]
+lib.octave_loss_fused_supported.restype = C.c_int
+lib.octave_loss_fused_supported.argtypes = [C.POINTER(LossDesc)]
+lib.octave_loss_fused_stats_bytes.restype = C.c_size_t
+lib.octave_loss_fused_stats_bytes.argtypes = [C.POINTER(LossDesc)]
+lib.octave_loss_fused.restype = C.c_int
+lib.octave_loss_fused.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, C.POINTER(C.c_float), _vp, _vp, _vp,
+                                  C.POINTER(_vp), _vp, _vp]
+lib.octave_loss_scale_grads.restype = C.c_int
+lib.octave_loss_scale_grads.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, _vp]
 
 
 class ConvDesc(C.Structure):

@@ -18,3 +18,12 @@ def set_compute_dtype(name: str) -> None:
     if name not in ("bf16", "fp32"):
         raise ValueError("compute dtype must be 'bf16' or 'fp32'")
     compute_dtype = name
+
+
+def set_deterministic(on: bool) -> None:
+    """Bit-reproducible mode: reductions that are normally split across CTAs and merged with fp32 atomics (split-K weight
+    gradients, K-split linears) run with one writer per output element (include/octave_b200.h: octave_set_deterministic).
+    The forward pass (BatchNorm statistics in fp64, fixed-order global average pool, single-pass loss) is reproducible in
+    either mode."""
+    from . import _lib
+    _lib.lib.octave_set_deterministic(1 if on else 0)

@@ -839,7 +839,7 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
       }
       case 128: {
         // opt-in, not yet measured: six stages with the slab epilogue (plain stores only)
-        static const int st1 = [] { const char* e = getenv("OCTAVE_FWD128_STAGES"); return e ? atoi(e) : 5; }();
+        static const int st1 = [] { const char* e = getenv("OCTAVE_FWD128_STAGES"); return e ? atoi(e) : 6; }();
         if (st1 == 6 && !p.accumulate) return launch_fwd<128, 64, 6>(tmA, tmB, p, (int)grid, s);
         return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
       }
@@ -916,7 +916,7 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   if (sms <= 0) sms = 148;
   // one wave of CTAs (1 CTA per SM: the TMA ring takes most of the shared memory): no tail wave
   int split = sms / out_tiles;
-  if (split < 1) split = 1;
+  if (split < 1 || g_octave_deterministic) split = 1;   // deterministic mode: no split-K, one CTA owns an output tile
   if (split > p.total_tiles) split = p.total_tiles;
   p.tiles_per_cta = (p.total_tiles + split - 1) / split;
   split = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
@@ -938,7 +938,7 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
         if (stage_rows == 64) {
           // several waves of CTAs and no split-K: two co-resident CTAs per SM (2 x 2 stages, 2 x 256 TMEM columns) hide
           // each other's prologue and reduction epilogue: 780 -> 697 us on decoder_4.conv.0 (OCTAVE_WGRAD_2CTA=0: off)
-          static const int two = [] { const char* e = getenv("OCTAVE_WGRAD_2CTA"); return e ? atoi(e) : 1; }();
+          static const int two = [] { const char* e = getenv("OCTAVE_WGRAD_2CTA"); return e ? atoi(e) : 0; }();
           if (two && split == 1 && out_tiles >= 2 * sms) return launch_wgrad<256, 64, 64, 2, 2, 64>(tmDY, tmX, p, grid, s);
           return launch_wgrad<256, 64, 64, 2, 4, 64>(tmDY, tmX, p, grid, s);
         }

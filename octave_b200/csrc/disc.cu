@@ -89,9 +89,9 @@ __global__ void unpack_wgrad_s2d_kernel(const float* dw3, int cout, int cin, int
 }
 
 template <typename T>
-__global__ void rowdot_fwd_kernel(OctaveAct x, const float* w, float* out) {
-  // grid (chunks, B); x is dense per sample: n = H*W*C elements
-  __shared__ float red[8];
+__global__ void __launch_bounds__(1024) rowdot_fwd_kernel(OctaveAct x, const float* w, const float* bias, float* out) {
+  // grid (1, B); x is dense per sample: n = H*W*C elements
+  __shared__ float red[32];
   const long long n = (long long)x.H * x.W * x.C;
   const T* xp = reinterpret_cast<const T*>(x.data) + (long long)blockIdx.y * n;
   float acc = 0.f;
@@ -103,12 +103,8 @@ __global__ void rowdot_fwd_kernel(OctaveAct x, const float* w, float* out) {
   }
   float v[1] = {acc};
   block_sum<1>(v, red);
-  if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, v[0]);
-}
-
-__global__ void rowdot_init_kernel(float* out, const float* bias, int B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) out[b] = bias ? bias[0] : 0.f;
+  // ONE block per sample (gridDim.x == 1): a single writer, so the critic logit is bit-reproducible
+  if (threadIdx.x == 0) out[blockIdx.y] = v[0] + (bias ? bias[0] : 0.f);
 }
 
 template <typename T>
@@ -198,14 +194,8 @@ extern "C" int octave_unpack_wgrad_s2d(const float* dw3, int32_t cout, int32_t c
 extern "C" int octave_rowdot_fwd(const OctaveAct* x, const float* w, const float* bias, float* out, void* stream) {
   if (!dense(x) || !w || !out) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  rowdot_init_kernel<<<(x->B + 127) / 128, 128, 0, s>>>(out, bias, x->B);
-  OCT_CHECK_LAUNCH();
-  const long long n = (long long)x->H * x->W * x->C;
-  int gx = (int)((n / 8 + 255) / 256);
-  if (gx > 64) gx = 64;
-  if (gx < 1) gx = 1;
-  if (x->dtype == OCT_DTYPE_F32) rowdot_fwd_kernel<float><<<dim3(gx, x->B), 256, 0, s>>>(*x, w, out);
-  else rowdot_fwd_kernel<bf16><<<dim3(gx, x->B), 256, 0, s>>>(*x, w, out);
+  if (x->dtype == OCT_DTYPE_F32) rowdot_fwd_kernel<float><<<dim3(1, x->B), 1024, 0, s>>>(*x, w, bias, out);
+  else rowdot_fwd_kernel<bf16><<<dim3(1, x->B), 1024, 0, s>>>(*x, w, bias, out);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

@@ -176,9 +176,11 @@ __global__ void bn_prepare_kernel(int C, double count, const double* sums, const
 }
 
 constexpr int U_AFF = 4;
+constexpr int kGapMaxBlocks = 64;   // blocks per image of a launch with the fused global average pool
+constexpr int kGapCounterWords = 65536;   // fixed-size counter region (one word per image, B < 65536) ahead of the partial sums
 template <typename T, bool HAS_RES, bool HAS_GAP>
 __global__ void __launch_bounds__(256) affine_act_kernel(const OctaveAct x, int Gb, const float* ab, const OctaveAct res,
-                                                         int relu, const OctaveAct y, float* gap) {
+                                                         int relu, const OctaveAct y, float* gap, unsigned* gap_ws) {
   extern __shared__ float sm[];
   const Tix t = make_tix<U_AFF>(x, Gb);
   float a[8], b[8], acc[8];
@@ -226,12 +228,41 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const OctaveAct x, int 
     }
   }
   if (HAS_GAP) {
+    // Deterministic two-stage reduction (no floating-point atomics): every block stores its per-channel partial sums
+    // (radix halves already added) into the workspace; the LAST block of an image to finish adds the partials in block
+    // order.  gap_ws = [kGapCounterWords counters (zero between launches: the last block resets its own)] [B][gridDim.x][C/2] floats.
+    __shared__ int s_last;
     fold_lanes<8>(acc, sm, Gb);
+    __syncthreads();
     if (threadIdx.x < Gb) {
-      const int half = x.C >> 1;
-      const int c = (t.cg * 8) % half;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(gap + (long long)blockIdx.y * half + c + i, acc[i]);
+      for (int i = 0; i < 8; ++i) sm[threadIdx.x * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    const int half = x.C >> 1, img = blockIdx.y;
+    float* part = reinterpret_cast<float*>(gap_ws + kGapCounterWords) + ((long long)img * gridDim.x + blockIdx.x) * half;
+    for (int c = threadIdx.x; c < half; c += blockDim.x) part[c] = sm[c] + sm[c + half];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(gap_ws + img, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const float* all = reinterpret_cast<const float*>(gap_ws + kGapCounterWords) + (long long)img * gridDim.x * half;
+      for (int c = threadIdx.x; c < half; c += blockDim.x) {
+        float s = 0.f;
+        unsigned bx = 0;
+        for (; bx + 8 <= gridDim.x; bx += 8) {   // 8 independent L2 loads in flight, added in block order
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __ldcg(all + (long long)(bx + i) * half + c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s += v[i];
+        }
+        for (; bx < gridDim.x; ++bx) s += __ldcg(all + (long long)bx * half + c);
+        gap[(long long)img * half + c] = s;
+      }
+      if (threadIdx.x == 0) gap_ws[img] = 0u;
     }
   }
 }
@@ -713,27 +744,34 @@ extern "C" int octave_bn_prepare(int32_t C, double count, const double* sums, co
 
 template <typename T, bool HAS_RES, bool HAS_GAP>
 static int launch_affine(const OctaveAct* x, const float* ab, const OctaveAct* res, int relu, const OctaveAct* y,
-                         float* gap, cudaStream_t s) {
+                         float* gap, unsigned* gap_ws, cudaStream_t s) {
   auto fn = affine_act_kernel<T, HAS_RES, HAS_GAP>;
   const size_t smem = HAS_GAP ? 8 * 256 * sizeof(float) : 0;
   Geo g;
   if (!make_geo(x, &g, U_AFF, HAS_GAP, ONE_WAVE(fn, 256, smem), HAS_GAP ? 4 : 1)) return OCT_ERR_UNSUPPORTED;
+  if (HAS_GAP && (g.grid.z != 1 || (int)g.grid.x > kGapMaxBlocks)) g.grid.x = kGapMaxBlocks;
+  if (HAS_GAP && g.grid.z != 1) return OCT_ERR_UNSUPPORTED;   // C <= 2048: one block covers every channel group
   OctaveAct r = res ? *res : *x;
-  fn<<<g.grid, g.bs, HAS_GAP ? 8 * g.bs * sizeof(float) : 0, s>>>(*x, g.Gb, ab, r, relu, *y, gap);
+  fn<<<g.grid, g.bs, HAS_GAP ? 8 * g.bs * sizeof(float) : 0, s>>>(*x, g.Gb, ab, r, relu, *y, gap, gap_ws);
   return OCT_OK;
 }
 
+extern "C" size_t octave_affine_gap_ws_bytes(const OctaveAct* x) {
+  if (!x || x->B <= 0 || x->C <= 0) return 0;
+  return sizeof(unsigned) * kGapCounterWords + sizeof(float) * (size_t)x->B * kGapMaxBlocks * (x->C / 2);
+}
+
 extern "C" int octave_affine_act(const OctaveAct* x, const float* ab, const OctaveAct* res, int32_t relu,
-                                 const OctaveAct* y, float* gap, void* stream) {
+                                 const OctaveAct* y, float* gap, void* gap_ws, void* stream) {
   if (!view_ok(x) || !view_ok(y) || !same_shape(x, y)) return OCT_ERR_INVALID;
   if (res && (!view_ok(res) || !same_shape(x, res))) return OCT_ERR_INVALID;
-  if (gap && (x->C % 16)) return OCT_ERR_INVALID;
+  if (gap && ((x->C % 16) || !gap_ws)) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  if (gap && cudaMemsetAsync(gap, 0, sizeof(float) * x->B * (x->C / 2), s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  unsigned* ws = reinterpret_cast<unsigned*>(gap_ws);
   int rc = OCT_OK;
   DISPATCH_T(x->dtype, {
-    if (gap) rc = res ? launch_affine<T, true, true>(x, ab, res, relu, y, gap, s) : launch_affine<T, false, true>(x, ab, res, relu, y, gap, s);
-    else rc = res ? launch_affine<T, true, false>(x, ab, res, relu, y, gap, s) : launch_affine<T, false, false>(x, ab, res, relu, y, gap, s);
+    if (gap) rc = res ? launch_affine<T, true, true>(x, ab, res, relu, y, gap, ws, s) : launch_affine<T, false, true>(x, ab, res, relu, y, gap, ws, s);
+    else rc = res ? launch_affine<T, true, false>(x, ab, res, relu, y, gap, ws, s) : launch_affine<T, false, false>(x, ab, res, relu, y, gap, ws, s);
   });
   if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();

@@ -52,6 +52,7 @@ struct LossArgs {
   float aw8[OCT_LOSS_MAX_ATT - 1];
   float inv_sumw, wpce_scale, dice_eps, jsd_eps;
   int n_real, n_fake;
+  float lam_wpce, lam_kld, lam_lsg;   // fused single pass: weights of the terms inside `total` (= upstream gradients)
 };
 
 __device__ __forceinline__ void atomic_add_f64(double* p, float v) { atomicAdd(p, (double)v); }
@@ -446,8 +447,15 @@ __device__ __forceinline__ void ls_backward(const LossArgs& a) {
   }
 }
 
+// upstream gradient of each loss term (device array for the two-pass path, host constants for the fused single pass)
+struct GradScale {
+  float wpce, dice, kld;
+};
+
+// kld_sum != nullptr: also accumulate the cell's divergence terms (the fused single pass needs values and gradients)
 template <typename T, int FL, bool PYR>
-__device__ __forceinline__ void loss_bwd_cell(const LossArgs& a, int b, int cell, int cw, int lane) {
+__device__ __forceinline__ void loss_bwd_cell(const LossArgs& a, int b, int cell, int cw, int lane, const GradScale gs,
+                                              float* kld_sum = nullptr) {
   const int cy = cell / cw, cx = cell - cy * cw;
   const int r = lane >> 1;
   const int y = cy * 16 + r, x0 = cx * 16 + (lane & 1) * 8;
@@ -466,7 +474,7 @@ __device__ __forceinline__ void loss_bwd_cell(const LossArgs& a, int b, int cell
     if (need_p) cell_probs<T, FL>(a, c);
     if ((FLG(a) & OCT_LOSS_WPCE) && need_p) {
       const bool full = FLG(a) & OCT_LOSS_WPCE_FULL;
-      const float k = -a.gscale[OCT_LOSS_OUT_WPCE] * a.wpce_scale;
+      const float k = -gs.wpce * a.wpce_scale;
       const float w0 = k * (float)a.stats[ST_W + 0], w1 = k * (float)a.stats[ST_W + 1];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -483,7 +491,7 @@ __device__ __forceinline__ void loss_bwd_cell(const LossArgs& a, int b, int cell
       // L = mean_b(1 - 2 I/(Card+eps)); dL/dp = (-2 t/(Card+eps) + 2 I/(Card+eps)^2)/B
       const float I = (float)a.stats[ST_DICE + b];
       const float card = (float)a.stats[ST_DICE + a.B + b] + a.dice_eps;
-      const float k = a.gscale[OCT_LOSS_OUT_DICE] / (float)a.B;
+      const float k = gs.dice / (float)a.B;
       const float ka = -2.f * k / card, kb = 2.f * k * I / (card * card);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -505,16 +513,20 @@ __device__ __forceinline__ void loss_bwd_cell(const LossArgs& a, int b, int cell
   }
 
   if (FLG(a) & OCT_LOSS_KLD) {
-    const float gk = a.gscale[OCT_LOSS_OUT_KLD] / ((float)a.B * (float)a.H * (float)a.W);
+    const float gk = gs.kld / ((float)a.B * (float)a.H * (float)a.W);
     {
       float g0[8], g1[8];
       const bool stop = FLG(a) & OCT_LOSS_KLD_STOPGRAD;
+      float ksum = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         // d/db [ b (log(b+eps) - m) ] = log(b+eps) - m + b/(b+eps)
-        g0[j] = stop ? 0.f : gk * (__logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw + __fdividef(c.b0[j], c.b0[j] + kEps));
-        g1[j] = stop ? 0.f : gk * (__logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw + __fdividef(c.b1[j], c.b1[j] + kEps));
+        const float d0 = __logf(c.b0[j] + kEps) - c.m0[j] * a.inv_sumw, d1 = __logf(c.b1[j] + kEps) - c.m1[j] * a.inv_sumw;
+        ksum += c.b0[j] * d0 + c.b1[j] * d1;
+        g0[j] = stop ? 0.f : gk * (d0 + __fdividef(c.b0[j], c.b0[j] + kEps));
+        g1[j] = stop ? 0.f : gk * (d1 + __fdividef(c.b1[j], c.b1[j] + kEps));
       }
+      if (kld_sum) *kld_sum += ksum;
       T* g = reinterpret_cast<T*>(a.g_att[0]);
       VecIO<T, 8>::st(g + off, g0);
       VecIO<T, 8>::st(g + off + plane, g1);
@@ -594,6 +606,7 @@ __global__ void __launch_bounds__(256, 3) loss_fast_bwd_kernel(const LossArgs a)
   const long long total = (long long)cells * a.B;
   if (blockIdx.x == 0) ls_backward(a);
   if (!(FLG(a) & (OCT_LOSS_WPCE | OCT_LOSS_DICE | OCT_LOSS_KLD))) return;
+  const GradScale gs{a.gscale[OCT_LOSS_OUT_WPCE], a.gscale[OCT_LOSS_OUT_DICE], a.gscale[OCT_LOSS_OUT_KLD]};
   for (long long id = (long long)blockIdx.x * 8 + warp; id < total; id += (long long)gridDim.x * 8) {
     const int b = (int)(id / cells), cell = (int)(id - (long long)b * cells);
     {
@@ -604,7 +617,372 @@ __global__ void __launch_bounds__(256, 3) loss_fast_bwd_kernel(const LossArgs a)
         prefetch_cell<T, FL>(a, nb, ncy * 16 + (lane >> 1), ncx * 16 + (lane & 1) * 8);
       }
     }
-    loss_bwd_cell<T, FL, PYR>(a, b, cell, cw, lane);
+    loss_bwd_cell<T, FL, PYR>(a, b, cell, cw, lane, gs);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused single pass (the G-step of the training loop): loss values AND gradients from ONE sweep over the maps.
+//
+// The WPCE gradient needs the class weights w_c = sum(n)/(n_c + eps) (losses.py:34-38), which depend on the labels only:
+// a labels-only pre-pass (loss_label_count_kernel, 2 elements/pixel) counts them, then loss_fused_kernel reads every
+// map once and writes every gradient once: 2 + 6.664 + 4.664 = 13.33 elements/pixel instead of 17.99 for the
+// statistics pass + gradient pass pair.  The upstream gradients are the term weights of  total = lam_wpce * WPCE +
+// lam_kld * KLD + lam_lsg * LSG, known when the forward runs; a different upstream gradient of `total` is applied
+// afterwards by loss_scale_kernel, which exits at once when that gradient is 1 (the `total.backward()` case).
+//
+// WPCE (agg, ys -> g_agg) is purely elementwise and KLD (att pyramid -> g_att) works on 16x16 cells; the two parts
+// share nothing, so a block walks WPCE chunks first and KLD cells afterwards (fewer live registers than one merged
+// body).  Reductions are deterministic: every block stores its partial sums, the last block adds them in block order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedMaxBlocks = 4 * 256;   // >= 4 resident blocks x SM count
+constexpr int kFusedPartials = 4;          // S0 S1 kld pad
+
+template <typename T>
+__global__ void __launch_bounds__(256) loss_label_count_kernel(const T* __restrict__ ys, long long plane8, long long groups,
+                                                              double* stats) {
+  __shared__ float red[2 * 8];
+  float n[2] = {0.f, 0.f};
+  constexpr int U = 4;
+  for (long long g0 = (long long)blockIdx.x * 256 * U + threadIdx.x; g0 < groups; g0 += (long long)gridDim.x * 256 * U) {
+    Raw8<T> r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long g = g0 + (long long)u * 256;
+      if (g < groups) r[u].ld(ys + g * 8); else r[u].zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long g = g0 + (long long)u * 256;
+      float v[8];
+      r[u].get(v);
+      const float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      const int c = (int)((g / plane8) & 1);      // [B][2][plane]: channel of this 8-pixel group
+      n[0] += c ? 0.f : s;
+      n[1] += c ? s : 0.f;
+    }
+  }
+  block_sum<2>(n, red);
+  if (threadIdx.x == 0) {
+    // per-block sums of 0/1 labels are exact integers, and fp64 sums of integers do not depend on the order
+    atomic_add_f64(stats + ST_N + 0, n[0]);
+    atomic_add_f64(stats + ST_N + 1, n[1]);
+  }
+}
+
+// ---- KLD part of the fused pass: the work unit is ONE class plane of one 16x16 cell (the divergence and its gradients are
+// separable per class), so a lane carries 8 pixels of one plane instead of two: half the live registers, twice the units.
+template <typename T>
+struct PlaneRaw {
+  Raw8<T> b;
+  RawN<T, 4> q1;
+  RawN<T, 2> q2;
+  RawN<T, 1> q3, q4;
+  unsigned off[5];               // element offset of this lane's first value in att[k] / g_att[k]
+};
+
+// exact unsigned division by a run-time constant (round-up multiplier; valid for every 32-bit n)
+struct FastDiv {
+  unsigned d, m, s;
+  __host__ void init(unsigned div) {
+    d = div;
+    unsigned l = 0;
+    while ((1ull << l) < div) ++l;
+    m = (unsigned)((((1ull << l) - div) << 32) / div + 1);
+    s = l;
+  }
+  __device__ __forceinline__ unsigned div(unsigned n) const {
+    const unsigned t = __umulhi(m, n);
+    return s == 0 ? n : (t + ((n - t) >> 1)) >> (s - 1);
+  }
+};
+
+struct PlaneGeo {
+  FastDiv cells, cw;             // cells per plane / per row
+  unsigned units;                // B * 2 * cells
+  unsigned W, plane;
+  bool use[4];                   // level k+1 takes part (present and non-zero weight)
+};
+
+template <typename T, bool PYR>
+__device__ __forceinline__ void plane_issue(const LossArgs& a, const PlaneGeo& g, unsigned u, int lane, PlaneRaw<T>& r) {
+  const unsigned pl = g.cells.div(u), cell = u - pl * g.cells.d;
+  const unsigned cy = g.cw.div(cell), cx = cell - cy * g.cw.d;
+  const unsigned y = cy * 16 + (lane >> 1), x0 = cx * 16 + (lane & 1) * 8;
+  r.off[0] = pl * g.plane + y * g.W + x0;
+  r.off[1] = pl * (g.plane >> 2) + (y >> 1) * (g.W >> 1) + (x0 >> 1);
+  r.off[2] = pl * (g.plane >> 4) + (y >> 2) * (g.W >> 2) + (x0 >> 2);
+  r.off[3] = pl * (g.plane >> 6) + (y >> 3) * (g.W >> 3) + (x0 >> 3);
+  r.off[4] = pl * (g.plane >> 8) + (y >> 4) * (g.W >> 4) + (x0 >> 4);
+  r.b.ld(reinterpret_cast<const T*>(a.att[0]) + r.off[0]);
+  if (PYR || g.use[0]) r.q1.ld(reinterpret_cast<const T*>(a.att[1]) + r.off[1]);
+  if (PYR || g.use[1]) r.q2.ld(reinterpret_cast<const T*>(a.att[2]) + r.off[2]);
+  if (PYR || g.use[2]) r.q3.ld(reinterpret_cast<const T*>(a.att[3]) + r.off[3]);
+  if (PYR || g.use[3]) r.q4.ld(reinterpret_cast<const T*>(a.att[4]) + r.off[4]);
+}
+
+// values (sum into ksum) and gradients of one plane unit: the arithmetic of loss_bwd_cell term by term, except that the
+// logarithms stay in base 2 until one multiplication by ln 2 per pixel, and b/(b + 1e-12) is taken as exactly 1 where
+// fp32 rounds b + 1e-12 to b (b > 2e-5; a warp-uniform test keeps the general path for the rest)
+template <typename T, bool PYR>
+__device__ __forceinline__ void plane_finish(const LossArgs& a, const PlaneGeo& g, int lane, const PlaneRaw<T>& r, float gk, float& ksum) {
+  constexpr float kLn2 = 0.6931471805599453f;
+  const int row = lane >> 1;
+  float b[8], m[8], q1[4], q2[2], q3, q4;
+  r.b.get(b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = 0.f;
+  if (PYR || g.use[0]) {
+    const float w = a.aw8[0];
+    r.q1.get(q1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float l = __log2f(w * q1[j] + kEps);
+      m[2 * j] += l; m[2 * j + 1] += l;
+    }
+  }
+  if (PYR || g.use[1]) {
+    const float w = a.aw8[1];
+    r.q2.get(q2);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float l = __log2f(w * q2[j] + kEps);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[4 * j + i] += l;
+    }
+  }
+  if (PYR || g.use[2]) {
+    r.q3.get(&q3);
+    const float l = __log2f(a.aw8[2] * q3 + kEps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] += l;
+  }
+  if (PYR || g.use[3]) {
+    r.q4.get(&q4);
+    const float l = __log2f(a.aw8[3] * q4 + kEps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] += l;
+  }
+  {
+    float gb[8];
+    float ks = 0.f, bmin = b[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) bmin = fminf(bmin, b[j]);
+    const bool unit_ratio = __all_sync(0xffffffffu, bmin > 2e-5f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // d/db [ b (log(b+eps) - m) ] = log(b+eps) - m + b/(b+eps)
+      const float d = kLn2 * (__log2f(b[j] + kEps) - m[j] * a.inv_sumw);
+      ks += b[j] * d;
+      gb[j] = gk * (d + (unit_ratio ? 1.f : __fdividef(b[j], b[j] + kEps)));
+    }
+    ksum += ks;
+    VecIO<T, 8>::st(reinterpret_cast<T*>(a.g_att[0]) + r.off[0], gb);
+  }
+  // box sums of the basis over 2^k x 2^k blocks; d/dq_k = -gk/sum_w * w_k/(w_k q + eps) * boxsum(b)
+  const float kq = -gk * a.inv_sumw;
+  float v1[4], v2[2], v3, v4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v1[j] = b[2 * j] + b[2 * j + 1];
+    v1[j] += __shfl_xor_sync(0xffffffffu, v1[j], 2);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    v2[j] = v1[2 * j] + v1[2 * j + 1];
+    v2[j] += __shfl_xor_sync(0xffffffffu, v2[j], 4);
+  }
+  v3 = v2[0] + v2[1];
+  v3 += __shfl_xor_sync(0xffffffffu, v3, 8);
+  v4 = v3 + __shfl_xor_sync(0xffffffffu, v3, 1);
+  v4 += __shfl_xor_sync(0xffffffffu, v4, 16);
+  if ((PYR || a.n_att > 1) && (row & 1) == 0) {
+    const float w = a.aw8[0];
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = (PYR || g.use[0]) ? __fdividef(kq * w * v1[j], w * q1[j] + kEps) : 0.f;
+    VecIO<T, 4>::st(reinterpret_cast<T*>(a.g_att[1]) + r.off[1], o);
+  }
+  if ((PYR || a.n_att > 2) && (row & 3) == 0) {
+    const float w = a.aw8[1];
+    float o[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) o[j] = (PYR || g.use[1]) ? __fdividef(kq * w * v2[j], w * q2[j] + kEps) : 0.f;
+    VecIO<T, 2>::st(reinterpret_cast<T*>(a.g_att[2]) + r.off[2], o);
+  }
+  if ((PYR || a.n_att > 3) && (row & 7) == 0) {
+    const float w = a.aw8[2];
+    float o = (PYR || g.use[2]) ? __fdividef(kq * w * v3, w * q3 + kEps) : 0.f;
+    VecIO<T, 1>::st(reinterpret_cast<T*>(a.g_att[3]) + r.off[3], &o);
+  }
+  if ((PYR || a.n_att > 4) && lane == 0) {
+    const float w = a.aw8[3];
+    float o = (PYR || g.use[3]) ? __fdividef(kq * w * v4, w * q4 + kEps) : 0.f;
+    VecIO<T, 1>::st(reinterpret_cast<T*>(a.g_att[4]) + r.off[4], &o);
+  }
+}
+
+template <typename T, bool PYR>
+__global__ void __launch_bounds__(256, 4) loss_fused_kernel(const LossArgs a, const PlaneGeo g) {
+  __shared__ float red[3 * 8];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[3] = {0.f, 0.f, 0.f};   // S0 S1 kld
+  const unsigned plane = (unsigned)a.H * (unsigned)a.W;
+
+  if (a.flags & OCT_LOSS_WPCE) {
+    // class weights exactly as finalize() forms them
+    const float n0 = (float)a.stats[ST_N + 0], n1 = (float)a.stats[ST_N + 1];
+    const float ntot = n0 + n1;
+    const float k = -a.lam_wpce * a.wpce_scale;
+    const float w0 = k * (ntot / (n0 + kEps)), w1 = k * (ntot / (n1 + kEps));
+    const bool full = a.flags & OCT_LOSS_WPCE_FULL, logits = a.flags & OCT_LOSS_FROM_LOGITS;
+    const T* yh = reinterpret_cast<const T*>(a.yhat);
+    const T* ys = reinterpret_cast<const T*>(a.ys);
+    T* gy = reinterpret_cast<T*>(a.g_yhat);
+    const unsigned plane8 = plane >> 3, groups = plane8 * (unsigned)a.B;   // 8-pixel groups of one class plane
+    const unsigned stride = gridDim.x * 256u;
+    unsigned g = blockIdx.x * 256u + threadIdx.x;
+    // software pipeline: the four 16-byte loads of the NEXT group are in flight while the current one is processed
+    Raw8<T> nz0, nz1, nt0, nt1;
+    size_t noff = 0;
+    if (g < groups) {
+      const unsigned b = g / plane8;
+      noff = (size_t)b * 2 * plane + (size_t)(g - b * plane8) * 8;
+      nz0.ld(yh + noff); nz1.ld(yh + noff + plane); nt0.ld(ys + noff); nt1.ld(ys + noff + plane);
+    }
+    while (g < groups) {
+      const Raw8<T> rz0 = nz0, rz1 = nz1, rt0 = nt0, rt1 = nt1;
+      const size_t off = noff;
+      g += stride;
+      if (g < groups) {
+        const unsigned b = g / plane8;
+        noff = (size_t)b * 2 * plane + (size_t)(g - b * plane8) * 8;
+        nz0.ld(yh + noff); nz1.ld(yh + noff + plane); nt0.ld(ys + noff); nt1.ld(ys + noff + plane);
+      }
+      float t0[8], t1[8], q0[8], q1[8];
+      rt0.get(t0); rt1.get(t1);
+      float tsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { tsum += fabsf(t0[j]) + fabsf(t1[j]); q0[j] = q1[j] = 0.f; }
+      if (tsum != 0.f) {   // an unlabelled group contributes ys * log(.) = 0 and an all-zero gradient
+        float p0[8], p1[8];
+        rz0.get(p0); rz1.get(p1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (logits) softmax2(p0[j], p1[j]);
+          const float a0 = full ? p0[j] : p0[j] * t0[j], a1 = full ? p1[j] : p1[j] * t1[j];
+          const float m0 = full ? t0[j] : t0[j] * t0[j], m1 = full ? t1[j] : t1[j] * t1[j];
+          acc[0] += t0[j] * __logf(a0 + kEps);
+          acc[1] += t1[j] * __logf(a1 + kEps);
+          float e0 = __fdividef(w0 * m0, a0 + kEps), e1 = __fdividef(w1 * m1, a1 + kEps);
+          if (logits) {
+            const float dot = e0 * p0[j] + e1 * p1[j];
+            e0 = p0[j] * (e0 - dot);
+            e1 = p1[j] * (e1 - dot);
+          }
+          q0[j] = e0; q1[j] = e1;
+        }
+      }
+      VecIO<T, 8>::st(gy + off, q0);
+      VecIO<T, 8>::st(gy + off + plane, q1);
+    }
+  }
+
+  if (a.flags & OCT_LOSS_KLD) {
+    const float gk = a.lam_kld / ((float)a.B * (float)a.H * (float)a.W);
+    const unsigned stride = gridDim.x * 8u;
+    // blocks are walked in reverse here: the ones that drew an extra WPCE round above draw one KLD round less
+    unsigned u = (gridDim.x - 1 - blockIdx.x) * 8u + warp;
+    PlaneRaw<T> nxt;
+    if (u < g.units) plane_issue<T, PYR>(a, g, u, lane, nxt);
+    while (u < g.units) {
+      const PlaneRaw<T> cur = nxt;
+      u += stride;
+      if (u < g.units) plane_issue<T, PYR>(a, g, u, lane, nxt);   // next unit's loads fly while this one is computed
+      plane_finish<T, PYR>(a, g, lane, cur, gk, acc[2]);
+    }
+  }
+
+  float ls[3] = {0.f, 0.f, 0.f};
+  if (blockIdx.x == 0 && (a.flags & OCT_LOSS_LSG)) {
+    // 0.5*mean((f-1)^2) and its gradient: discriminator/losses.py:22-24
+    for (int i = threadIdx.x; i < a.n_fake; i += blockDim.x) {
+      const float f = a.d_fake[i];
+      ls[0] += (f - 1.f) * (f - 1.f);
+      a.g_fake[i] = a.lam_lsg * (f - 1.f) / (float)a.n_fake;
+    }
+  }
+  block_sum<3>(acc, red);
+  if (blockIdx.x == 0) block_sum<3>(ls, red);
+  double* part = a.stats + ST_DICE + 2 * a.B;
+  if (threadIdx.x == 0) {
+    part[blockIdx.x * kFusedPartials + 0] = (double)acc[0];
+    part[blockIdx.x * kFusedPartials + 1] = (double)acc[1];
+    part[blockIdx.x * kFusedPartials + 2] = (double)acc[2];
+    if (blockIdx.x == 0) a.stats[ST_LSG] = (double)ls[0];
+    __threadfence();
+    const unsigned long long prev = atomicAdd(reinterpret_cast<unsigned long long*>(a.stats + ST_COUNTER), 1ULL);
+    s_last = (prev == (unsigned long long)gridDim.x - 1ULL);
+  }
+  __syncthreads();
+  __shared__ double fin[3][256];
+  if (s_last) {
+    // fixed-order (bit-reproducible) sum of the per-block partials by the whole block: thread t adds blocks t, t+256, ...
+    // (independent L2 loads in flight), then a fixed shared-memory tree
+    __threadfence();
+    double s0 = 0.0, s1 = 0.0, kl = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) {
+      s0 += __ldcg(part + i * kFusedPartials + 0);
+      s1 += __ldcg(part + i * kFusedPartials + 1);
+      kl += __ldcg(part + i * kFusedPartials + 2);
+    }
+    fin[0][threadIdx.x] = s0; fin[1][threadIdx.x] = s1; fin[2][threadIdx.x] = kl;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if ((int)threadIdx.x < w) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) fin[q][threadIdx.x] += fin[q][threadIdx.x + w];
+      }
+      __syncthreads();
+    }
+  }
+  if (s_last && threadIdx.x == 0) {
+    volatile double* st = a.stats;
+    st[ST_S + 0] = fin[0][0]; st[ST_S + 1] = fin[1][0]; st[ST_KLD] = fin[2][0];
+    finalize(a);
+    a.out[6] = a.lam_wpce * a.out[OCT_LOSS_OUT_WPCE] + a.lam_kld * a.out[OCT_LOSS_OUT_KLD] + a.lam_lsg * a.out[OCT_LOSS_OUT_LSG];
+  }
+}
+
+// In-place scaling of the gradients written by the fused pass by the upstream gradient of `total`; a gradient of
+// exactly 1 (the usual `total.backward()`) returns at once.
+struct ScaleArgs {
+  void* ptr[8];
+  long long n[8];   // elements, multiples of 8 for the maps
+  int count, dtype;
+  const float* g;
+};
+__global__ void __launch_bounds__(256) loss_scale_kernel(const ScaleArgs sa) {
+  const float g = *sa.g;
+  if (g == 1.f) return;
+  for (int t = 0; t < sa.count; ++t) {
+    const long long n = sa.n[t];
+    if (sa.dtype == OCT_DTYPE_BF16 && t < sa.count - 1) {
+      bf16* p = reinterpret_cast<bf16*>(sa.ptr[t]);
+      for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 8; i + 8 <= n; i += (long long)gridDim.x * 256 * 8) {
+        float v[8];
+        VecIO<bf16, 8>::ld(p + i, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= g;
+        VecIO<bf16, 8>::st(p + i, v);
+      }
+      for (long long i = (n & ~7LL) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        p[i] = __float2bfloat16_rn(__bfloat162float(p[i]) * g);
+    } else {
+      float* p = reinterpret_cast<float*>(sa.ptr[t]);
+      for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) p[i] *= g;
+    }
   }
 }
 
@@ -848,7 +1226,6 @@ constexpr int kGStepFlags = OCT_LOSS_WPCE | OCT_LOSS_KLD | OCT_LOSS_FROM_LOGITS;
 // map flags of the G-step (LS-G rides along: it is handled by block 0 outside the specialised code)
 bool gstep_config(const OctaveLossDesc* d) {
   if ((d->flags & ~(OCT_LOSS_LSG)) != kGStepFlags) return false;
-  if (d->flags & OCT_LOSS_LSG) return false;
   if (d->n_att != OCT_LOSS_MAX_ATT) return false;
   for (int k = 0; k < OCT_LOSS_MAX_ATT - 1; ++k)
     if (d->att_weight[k] == 0.f) return false;
@@ -972,6 +1349,102 @@ extern "C" int octave_loss_bwd(const OctaveLossDesc* d, const void* yhat, const 
     if (gx > 1024) gx = 1024;
     loss_generic_bwd_kernel<<<dim3(gx, d->B), 256, 0, s>>>(a);
   }
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+// ---- fused single pass (G-step) ---------------------------------------------------------------------------------
+extern "C" int octave_loss_fused_supported(const OctaveLossDesc* d) {
+  if (validate(d) != OCT_OK || !fast_ok(d)) return 0;
+  const int allowed = OCT_LOSS_WPCE | OCT_LOSS_KLD | OCT_LOSS_LSG | OCT_LOSS_FROM_LOGITS | OCT_LOSS_WPCE_FULL;
+  if (d->flags & ~allowed) return 0;
+  if (!(d->flags & (OCT_LOSS_WPCE | OCT_LOSS_KLD))) return 0;
+  if (d->C != 2 || (d->H & 15) || (d->W & 15)) return 0;
+  return 1;
+}
+
+extern "C" size_t octave_loss_fused_stats_bytes(const OctaveLossDesc* d) {
+  if (!d) return 0;
+  const int B = d->B > 0 ? d->B : 0;
+  return (size_t)(ST_DICE + 2 * B + kFusedMaxBlocks * kFusedPartials) * sizeof(double);
+}
+
+extern "C" int octave_loss_fused(const OctaveLossDesc* d, const void* yhat, const void* ys, const void* const* att,
+                                 const float* d_fake, const float* lambdas, void* stats, float* out, void* g_yhat,
+                                 void* const* g_att, float* g_fake, void* stream) {
+  if (!octave_loss_fused_supported(d)) return OCT_ERR_UNSUPPORTED;
+  if (!stats || !out || !lambdas) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_WPCE) && (!yhat || !ys || !g_yhat)) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_KLD) && (!att || !g_att)) return OCT_ERR_INVALID;
+  if ((d->flags & OCT_LOSS_LSG) && (!d_fake || !g_fake)) return OCT_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  LossArgs a;
+  fill_args(a, d, yhat, ys, att, nullptr, d_fake, stats);
+  a.out = out; a.g_yhat = g_yhat; a.g_fake = g_fake;
+  a.lam_wpce = lambdas[0]; a.lam_kld = lambdas[1]; a.lam_lsg = lambdas[2];
+  if (d->flags & OCT_LOSS_KLD) {
+    for (int k = 0; k < a.n_att; ++k) {
+      if (!att[k] || !g_att[k]) return OCT_ERR_INVALID;
+      a.g_att[k] = g_att[k];
+    }
+  }
+  if (cudaMemsetAsync(stats, 0, (size_t)(ST_DICE + 2 * d->B) * sizeof(double), s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  int sms = octave_sm_count();
+  if (sms <= 0) sms = 148;
+  const long long plane = (long long)d->H * d->W;
+  if (d->flags & OCT_LOSS_WPCE) {
+    const long long groups = plane / 8 * 2 * d->B;
+    long long gx = (groups + 256 * 4 - 1) / (256 * 4);
+    if (gx > 4LL * sms) gx = 4LL * sms;
+    if (d->dtype == OCT_DTYPE_F32)
+      loss_label_count_kernel<float><<<(int)gx, 256, 0, s>>>(reinterpret_cast<const float*>(ys), plane / 8, groups, a.stats);
+    else
+      loss_label_count_kernel<bf16><<<(int)gx, 256, 0, s>>>(reinterpret_cast<const bf16*>(ys), plane / 8, groups, a.stats);
+    OCT_CHECK_LAUNCH();
+  }
+  long long grid = 4LL * sms;
+  const long long items = (plane * d->B + 2047) / 2048;
+  if (grid > items) grid = items;
+  if (grid > kFusedMaxBlocks) grid = kFusedMaxBlocks;
+  if (grid < 1) grid = 1;
+  PlaneGeo g{};
+  g.cw.init((unsigned)d->W >> 4);
+  g.cells.init(((unsigned)d->W >> 4) * ((unsigned)d->H >> 4));
+  g.units = g.cells.d * 2u * (unsigned)d->B;
+  g.W = (unsigned)d->W; g.plane = (unsigned)plane;
+  bool pyr = (d->flags & OCT_LOSS_KLD) && d->n_att == OCT_LOSS_MAX_ATT;
+  for (int k = 0; k < 4; ++k) {
+    g.use[k] = a.n_att > k + 1 && a.aw8[k] != 0.f;
+    pyr = pyr && g.use[k];
+  }
+  if ((long long)d->B * 2 * plane >= (1LL << 31)) return OCT_ERR_UNSUPPORTED;   // 32-bit element offsets
+  if (d->dtype == OCT_DTYPE_F32) {
+    if (pyr) loss_fused_kernel<float, true><<<(int)grid, 256, 0, s>>>(a, g);
+    else loss_fused_kernel<float, false><<<(int)grid, 256, 0, s>>>(a, g);
+  } else {
+    if (pyr) loss_fused_kernel<bf16, true><<<(int)grid, 256, 0, s>>>(a, g);
+    else loss_fused_kernel<bf16, false><<<(int)grid, 256, 0, s>>>(a, g);
+  }
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_loss_scale_grads(const OctaveLossDesc* d, const float* g_total, void* g_yhat, void* const* g_att,
+                                       float* g_fake, void* stream) {
+  if (!d || !g_total) return OCT_ERR_INVALID;
+  ScaleArgs sa{};
+  sa.g = g_total; sa.dtype = d->dtype;
+  int c = 0;
+  if ((d->flags & OCT_LOSS_WPCE) && g_yhat) { sa.ptr[c] = g_yhat; sa.n[c] = (long long)d->B * d->C * d->H * d->W; ++c; }
+  if ((d->flags & OCT_LOSS_KLD) && g_att)
+    for (int k = 0; k < d->n_att && k < OCT_LOSS_MAX_ATT; ++k)
+      if (g_att[k]) { sa.ptr[c] = g_att[k]; sa.n[c] = (long long)d->B * d->C * d->att_h[k] * d->att_w[k]; ++c; }
+  // the last entry is always the fp32 critic-logit gradient (possibly empty)
+  sa.ptr[c] = g_fake; sa.n[c] = ((d->flags & OCT_LOSS_LSG) && g_fake) ? d->n_fake : 0; ++c;
+  sa.count = c;
+  int sms = octave_sm_count();
+  if (sms <= 0) sms = 148;
+  loss_scale_kernel<<<2 * sms, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sa);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }

@@ -13,3 +13,9 @@ extern "C" int octave_sm_count(void) {
 
 unsigned long long g_octave_launches = 0;
 extern "C" unsigned long long octave_launch_count(void) { return g_octave_launches; }
+
+// Deterministic mode: every reduction that is normally split across CTAs and merged with fp32 atomics (split-K weight
+// gradients, the K-split of the attention-branch linears) runs with a single writer per output element instead.
+int g_octave_deterministic = 0;
+extern "C" void octave_set_deterministic(int on) { g_octave_deterministic = on ? 1 : 0; }
+extern "C" int octave_get_deterministic(void) { return g_octave_deterministic; }

@@ -370,7 +370,7 @@ extern "C" int octave_glinear_bwd_data(const float* dout, const float* w, int32_
     // enough blocks to occupy the machine: split the contraction when there are few 32-input column blocks
     const int Ng = N / groups;
     int split = 1;
-    while (split < 16 && (Kt / 32) * split < 96 && Ng / (split * 2) >= kJC) split *= 2;
+    while (!g_octave_deterministic && split < 16 && (Kt / 32) * split < 96 && Ng / (split * 2) >= kJC) split *= 2;
     if (split > 1 && cudaMemsetAsync(din, 0, sizeof(float) * (size_t)B * Kt, s) != cudaSuccess) return OCT_ERR_LAUNCH;
     glinear_bwd_data_kernel<<<dim3(Kt / 32, (B + 31) / 32, split), 256, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din);
   }
@@ -380,6 +380,7 @@ extern "C" int octave_glinear_bwd_data(const float* dout, const float* w, int32_
     const int Ng = N / groups;
     int split = (Ng + 15) / 16;
     if (split > 128) split = 128;
+    if (g_octave_deterministic) split = 1;   // one writer per din element
     glinear_bwd_data_ref_kernel<<<dim3((Kt + 127) / 128, split, B), 128, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din);
   }
   OCT_CHECK_LAUNCH();

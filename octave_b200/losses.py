@@ -119,6 +119,44 @@ class _FusedLossFn(torch.autograd.Function):
         return (None, g_yhat, None, g_real, g_fake, *(g_att if g_att else [None] * len(att)))
 
 
+class _FusedTotalFn(torch.autograd.Function):
+    """total = l_sup * WPCE + l_kl * KLD + l_g * LSG with values AND gradients from one sweep over the maps
+    (octave_loss_fused: labels-only count pre-pass + one fused pass).  Returns (total, out[8]); `out` is not
+    differentiable.  backward scales the stored gradients by the upstream gradient of `total` on the device
+    (octave_loss_scale_grads, a no-op when it is 1)."""
+
+    @staticmethod
+    def forward(ctx, cfg: _LossCfg, lambdas, yhat, ys, d_fake, *att):
+        desc = _build_desc(cfg, yhat, att, None, d_fake)
+        dev = yhat.device
+        stats = torch.empty(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        out = torch.empty(_lib.LOSS_OUT_SLOTS, dtype=torch.float32, device=dev)
+        g_yhat = torch.empty_like(yhat)
+        g_att = [torch.empty_like(a) for a in att]
+        g_fake = torch.empty_like(d_fake) if d_fake is not None else None
+        lam = (C.c_float * 3)(*[float(v) for v in lambdas])
+        rc = _lib.lib.octave_loss_fused(C.byref(desc), yhat.data_ptr(), ys.data_ptr(), _ptr_array(att), _ptr(d_fake), lam,
+                                        stats.data_ptr(), out.data_ptr(), g_yhat.data_ptr(), _ptr_array(g_att), _ptr(g_fake),
+                                        _stream_ptr())
+        _lib.check("octave_loss_fused", rc)
+        ctx.desc, ctx.n_att, ctx.has_fake = desc, len(att), d_fake is not None
+        ctx.save_for_backward(g_yhat, *g_att, *([g_fake] if g_fake is not None else []))
+        total = out[_lib.LOSS_OUT_TOTAL].clone()
+        ctx.mark_non_differentiable(out)
+        return total, out
+
+    @staticmethod
+    def backward(ctx, g_total, _g_out):
+        saved = list(ctx.saved_tensors)
+        g_yhat, g_att = saved[0], saved[1:1 + ctx.n_att]
+        g_fake = saved[1 + ctx.n_att] if ctx.has_fake else None
+        g = g_total.reshape(1).float().contiguous()
+        rc = _lib.lib.octave_loss_scale_grads(C.byref(ctx.desc), g.data_ptr(), g_yhat.data_ptr(), _ptr_array(g_att), _ptr(g_fake),
+                                              _stream_ptr())
+        _lib.check("octave_loss_scale_grads", rc)
+        return (None, None, g_yhat, None, g_fake, *g_att)
+
+
 def _prep_map(t: Tensor, name: str, dtype: Optional[torch.dtype] = None) -> Tensor:
     _require_cuda(t, name)
     if dtype is None:
@@ -285,6 +323,38 @@ class FusedSegmentorLoss(nn.Module):
         self.from_logits = from_logits
         self.dice_eps = dice_eps
         self.att_weights = att_weights
+
+    def total(self, agg_map: Tensor, ys: Tensor, attentions: Sequence[Tensor], y_fake: Optional[Tensor] = None,
+              lambda_sup: float = 1.0, lambda_kl: float = 1.0, lambda_g: float = 1.0):
+        """The weighted G-step objective  lambda_sup * supervised + lambda_kl * divergence + lambda_g * generator  as ONE
+        differentiable scalar whose gradients were written by the same pass that computed the values (K9 single pass).
+        Returns the same dict as forward() (components detached) plus 'total'.  Falls back to forward() + torch
+        arithmetic for configurations the single pass does not cover (Dice, non-pyramid maps)."""
+        w = list(self.att_weights) if self.att_weights is not None else [1.0] * (len(attentions) - 1)
+        flags = _lib.LOSS_WPCE | _lib.LOSS_KLD | (_lib.LOSS_FROM_LOGITS if self.from_logits else 0) | \
+            (_lib.LOSS_LSG if y_fake is not None else 0)
+        ok = self.weakly_supervise and len(attentions) >= 2
+        if ok:
+            dtype = _common_dtype(agg_map, *attentions)
+            yhat = _prep_map(agg_map, "agg_map", dtype)
+            ysm = _prep_map(ys, "ys", dtype)
+            att = [_prep_map(a, f"attentions[{i}]", dtype) for i, a in enumerate(attentions)]
+            fake = _prep_logits(y_fake, "y_fake") if y_fake is not None else None
+            cfg = _LossCfg(flags, att_weights=w, sum_weights=float(sum(w)))
+            desc = _build_desc(cfg, yhat, att, None, fake)
+            ok = bool(_lib.lib.octave_loss_fused_supported(C.byref(desc)))
+        if not ok:
+            res = self.forward(agg_map, ys, attentions, y_fake)
+            tot = lambda_sup * res['supervised'] + lambda_kl * res['divergence']
+            if y_fake is not None:
+                tot = tot + lambda_g * res['generator']
+            res['total'] = tot
+            return res
+        tot, out = _FusedTotalFn.apply(cfg, (lambda_sup, lambda_kl, lambda_g), yhat, ysm, fake, *att)
+        res = {'total': tot, 'supervised': out[_OUT_WPCE], 'divergence': out[_OUT_KLD], 'nan_flag': out[_OUT_NAN]}
+        if y_fake is not None:
+            res['generator'] = out[_OUT_LSG]
+        return res
 
     def forward(self, agg_map: Tensor, ys: Tensor, attentions: Sequence[Tensor], y_fake: Optional[Tensor] = None):
         flags = (_lib.LOSS_WPCE if self.weakly_supervise else _lib.LOSS_DICE) | _lib.LOSS_KLD

@@ -108,7 +108,7 @@ _sigs = {
     "octave_act_bwd": [_A, _A, C.c_int32, _A, _vp],
     "octave_chan_stats": [_A, _vp, _vp],
     "octave_bn_prepare": [C.c_int32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_int32, _vp, _vp, _vp],
-    "octave_affine_act": [_A, _vp, _A, C.c_int32, _A, _vp, _vp],
+    "octave_affine_act": [_A, _vp, _A, C.c_int32, _A, _vp, _vp, _vp],
     "octave_bn_bwd_reduce": [_A, _A, _vp, _A, _vp, _vp, _vp],
     "octave_bn_bwd_apply": [_A, _A, _vp, _A, _vp, _vp, _vp, C.c_int32, _A, _vp, _vp, _A, _vp],
     "octave_add_inplace": [_A, _A, _vp],
@@ -149,6 +149,8 @@ _sigs = {
 for _n, _a in _sigs.items():
     getattr(lib, _n).restype = C.c_int
     getattr(lib, _n).argtypes = _a
+lib.octave_affine_gap_ws_bytes.restype = C.c_size_t
+lib.octave_affine_gap_ws_bytes.argtypes = [_A]
 lib.octave_pack_job_blocks.restype = C.c_int64
 lib.octave_pack_job_blocks.argtypes = [C.c_int32] * 5
 
@@ -173,9 +175,27 @@ def bn_prepare(C_: int, count: float, sums, gamma, beta, rm, rv, nbt, eps: float
 def affine_act(x: Act, ab: Optional[torch.Tensor], res: Optional[Act], relu: bool, out: Optional[Act] = None,
                want_gap: bool = False):
     y = out if out is not None else x.like()
-    gap = torch.empty((x.B, x.C // 2), dtype=torch.float32, device=x.device) if want_gap else None
-    _chk("octave_affine_act", lib.octave_affine_act(_ref(x), _p(ab), _ref(res), int(relu), _ref(y), _p(gap), stream_ptr()))
+    gap = ws = None
+    if want_gap:
+        gap = torch.empty((x.B, x.C // 2), dtype=torch.float32, device=x.device)
+        ws = _gap_workspace(x)
+    _chk("octave_affine_act", lib.octave_affine_act(_ref(x), _p(ab), _ref(res), int(relu), _ref(y), _p(gap), _p(ws), stream_ptr()))
     return y, gap
+
+
+_gap_ws = {}
+
+
+def _gap_workspace(x: Act) -> torch.Tensor:
+    """Scratch of the fixed-order global-average-pool reduction; one per (device, stream), zeroed once (its counters are
+    left at zero by every launch, and launches on one stream are serialised)."""
+    nbytes = lib.octave_affine_gap_ws_bytes(_ref(x))
+    key = (x.device, stream_ptr())
+    ws = _gap_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 16 << 20), dtype=torch.uint8, device=x.device)
+        _gap_ws[key] = ws
+    return ws
 
 
 def bn_bwd(dy: Act, mask: Optional[Act], x: Act, mi: torch.Tensor, gamma: Optional[torch.Tensor], training: bool,

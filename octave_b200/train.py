@@ -167,10 +167,9 @@ class TrainStep:
         self._set_d_grad(False)
         att, agg, _ = net.segmentor(x)
         y_fake = net.discriminator(att) if self.has_d else None
-        res = self.loss(agg, ys, att, y_fake)
-        total = res['supervised'] + self.lambda_kl * res['divergence']
-        if y_fake is not None:
-            total = total + self.lambda_g * res['generator']
+        # values and gradients of  sup + l_kl * KLD + l_g * LSG  from one sweep over the maps (K9 single pass)
+        res = self.loss.total(agg, ys, att, y_fake, 1.0, self.lambda_kl, self.lambda_g)
+        total = res['total']
         total.backward()
         if self.reducer is not None:
             self.reducer.finish()

@@ -219,3 +219,85 @@ def test_full_size_properties():
     l1 = m.WeightedPartialCE(2, manual=True)(lg, ys, from_logits=True)
     g1, = torch.autograd.grad(l1, lg)
     assert float(g1.sum(dim=1).abs().max()) < 1e-6  # softmax-Jacobian rows sum to zero
+
+
+# ---- single-pass G-step objective (octave_loss_fused): values and gradients against the CPU oracle ------------------------
+def _gstep_inputs(B, H, W, dtype, seed=0, label_frac=0.05):
+    g = torch.Generator().manual_seed(seed)
+    agg = torch.randn(B, 2, H, W, generator=g)
+    lab = torch.rand(B, H, W, generator=g)
+    ys = torch.stack([(lab < label_frac).float(), ((lab >= label_frac) & (lab < 2 * label_frac)).float()], 1)
+    att = [torch.softmax(2.0 * torch.randn(B, 2, H >> k, W >> k, generator=g), 1) for k in range(5)]
+    fake = torch.randn(B, 1, generator=g)
+    rd = lambda t: t.to(dtype).float()          # the oracle sees exactly the values the kernel reads
+    return rd(agg), rd(ys), [rd(a) for a in att], fake
+
+
+def _oracle_total(agg, ys, att, fake, lam):
+    agg = agg.clone().requires_grad_(); att = [a.clone().requires_grad_() for a in att]; fake = fake.clone().requires_grad_()
+    sup = O.weighted_partial_ce(torch.softmax(agg, 1), ys, 2)
+    kld = O.interlayer_divergence(att)
+    gen = O.ls_generator_loss(fake)
+    tot = lam[0] * sup + lam[1] * kld + lam[2] * gen
+    gs = torch.autograd.grad(tot, [agg, fake, *att])
+    return (sup, kld, gen, tot), gs
+
+
+@pytest.mark.parametrize("dtype,B,H,W", [(torch.float32, 2, 304, 304), (torch.float32, 3, 48, 80), (torch.bfloat16, 2, 304, 304),
+                                         (torch.bfloat16, 4, 400, 400)])
+def test_fused_single_pass_matches_oracle(dtype, B, H, W):
+    m = L()
+    lam = (1.0, 0.1, 0.25)
+    agg, ys, att, fake = _gstep_inputs(B, H, W, dtype)
+    (sup, kld, gen, tot), gref = _oracle_total(agg, ys, att, fake, lam)
+    a_d = agg.to(DEV, dtype).requires_grad_(); t_d = [a.to(DEV, dtype).requires_grad_() for a in att]
+    f_d = fake.to(DEV).requires_grad_()
+    res = m.FusedSegmentorLoss().total(a_d, ys.to(DEV, dtype), t_d, f_d, *lam)
+    rt = 1e-4 if dtype == torch.float32 else 1e-2
+    close(res['supervised'], sup, rtol=rt, msg="fused wpce")
+    close(res['divergence'], kld, rtol=rt, msg="fused kld")
+    close(res['generator'], gen, rtol=1e-4, msg="fused lsg")
+    close(res['total'], tot, rtol=rt, msg="fused total")
+    assert float(res['nan_flag']) == 0.0
+    (3.0 * res['total']).backward()             # a non-unit upstream gradient exercises octave_loss_scale_grads
+    got = [a_d.grad, f_d.grad, *[t.grad for t in t_d]]
+    for k, (g, gg) in enumerate(zip(got, gref)):
+        grad_close(g, 3.0 * gg, rt, f"fused gradient {k}")
+
+
+def test_fused_single_pass_equals_two_pass_and_is_deterministic():
+    """Same arithmetic as the statistics pass + gradient pass (fp32: values to 1e-5, gradients to 1e-5 of their maximum),
+    and bit-identical results from two runs (fixed-order reductions)."""
+    m = L()
+    agg, ys, att, fake = _gstep_inputs(4, 160, 208, torch.float32, seed=3)
+    fl = m.FusedSegmentorLoss()
+    outs = []
+    for _ in range(2):
+        a_d = agg.to(DEV).requires_grad_(); t_d = [a.to(DEV).requires_grad_() for a in att]; f_d = fake.to(DEV).requires_grad_()
+        r = fl.total(a_d, ys.to(DEV), t_d, f_d, 1.0, 0.1, 0.1)
+        r['total'].backward()
+        outs.append((r['total'].detach().clone(), a_d.grad.clone(), [t.grad.clone() for t in t_d], f_d.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][3], outs[1][3])
+    for x, y in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(x, y)
+    a_d = agg.to(DEV).requires_grad_(); t_d = [a.to(DEV).requires_grad_() for a in att]; f_d = fake.to(DEV).requires_grad_()
+    r2 = fl(a_d, ys.to(DEV), t_d, f_d)
+    tot2 = r2['supervised'] + 0.1 * r2['divergence'] + 0.1 * r2['generator']
+    tot2.backward()
+    close(outs[0][0], tot2, rtol=1e-5, msg="single pass vs two pass total")
+    grad_close(outs[0][1], a_d.grad, 1e-5, "agg gradient")
+    grad_close(outs[0][3], f_d.grad, 1e-5, "critic-logit gradient")
+    for k, (x, t) in enumerate(zip(outs[0][2], t_d)):
+        grad_close(x, t.grad, 1e-5, f"attention gradient {k}")
+
+
+def test_fused_single_pass_falls_back_for_dice():
+    m = L()
+    agg, ys, att, fake = _gstep_inputs(2, 64, 64, torch.float32, seed=5)
+    full = torch.stack([1 - (att[0][:, 1] > 0.5).float(), (att[0][:, 1] > 0.5).float()], 1)
+    a_d = agg.to(DEV).requires_grad_(); t_d = [a.to(DEV).requires_grad_() for a in att]
+    res = m.FusedSegmentorLoss(weakly_supervise=False).total(a_d, full.to(DEV), t_d, None, 1.0, 0.5, 0.0)
+    exp = O.dice_loss(torch.softmax(agg, 1), full) + 0.5 * O.interlayer_divergence(att)
+    close(res['total'], exp, rtol=1e-4, msg="dice fallback total")
+    res['total'].backward()
+    assert a_d.grad is not None and torch.isfinite(a_d.grad).all()
