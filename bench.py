@@ -77,13 +77,13 @@ class ClockSampler(threading.Thread):
 # CPU arm: the reference algorithm (oracle port: torch fp32 functional restatement, oracle/octave_oracle.py)
 # ----------------------------------------------------------------------------------------------------
 def cpu_step_fn(H: int, W: int, batch: int, seed: int = 0):
+    """One G+D step of the reference algorithm on the host: oracle port (oracle/octave_oracle.py) over a seeded state dict
+    built from the committed shape table (oracle/synth_state.py).  Nothing of octave_b200's CUDA library is imported here
+    (octave_b200.synth is plain torch)."""
     from octave_b200 import synth
     from oracle import octave_oracle as O
-    from octave_b200.model import OctaScribbleNet
-    torch.manual_seed(seed)
-    net = OctaScribbleNet(torch.Size((batch, 3, H, W)), torch.Size((batch, 2, H, W)), True, False, instance_noise=False, label_noise=False)
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    del net
+    from oracle import synth_state
+    sd = synth_state.seeded_state(H, W, seed)
     seg = {k[len("segmentor."):]: (v.requires_grad_() if v.is_floating_point() and "running" not in k else v)
            for k, v in sd.items() if k.startswith("segmentor.")}
     dis = {k[len("discriminator."):]: (v.requires_grad_() if v.is_floating_point() and not k.endswith(("_u", "_v")) else v)
@@ -182,14 +182,85 @@ def run_cpu(H, W, sample_batch, steps, warmup):
 
 
 # ----------------------------------------------------------------------------------------------------
-def kernel_rooflines(peaks, B, H, W):
-    """Times the dominant tensor-core conv and the fused loss kernel in isolation with CUDA events on the launch stream."""
-    import ctypes as C
-    from octave_b200 import _lib, ops, losses
+RIDGE_FLOP_PER_BYTE = 218.0     # sustained bf16 peak / measured HBM bandwidth: above = tensor-bound
+
+
+def family_rooflines(ts, batch, peaks, step_ms):
+    """One extra EAGER step with CUDA events around every C-ABI call (octave_b200.profiler) on the launching stream, grouped
+    into kernel families.  Per family: algorithmic FLOPs or bytes of its launches / their summed duration, against the
+    sustained tensor peak (the kernels run inside a long step) or the measured HBM bandwidth.  Algorithmic units (DESIGN.md
+    §3): a convolution = 2*pixels*Cout*Cin/g*k^2 FLOP and 2 B * pixels * (Cin + Cout) of minimum traffic; an elementwise
+    BatchNorm pass = element size * B*H*W*C per tensor it must read or write."""
+    from octave_b200 import profiler
+    x, ys, real = batch
+
+    def eager():
+        feed = getattr(ts, "_feed", None)      # graph mode installed a host random feed on the critic: fill it as a replay would
+        if feed is not None:
+            feed.draw(); feed.upload()
+        ts.step(x, ys, real)
+
+    profiler.enable()
+    try:
+        eager()
+        profiler.reset()
+        eager()
+        recs = profiler.records()
+    finally:
+        profiler.disable()
+    fam = {}
+
+    def add(name, bound, ms, flop=0.0, byts=0.0):
+        f = fam.setdefault(name, {"bound": bound, "ms": 0.0, "flop": 0.0, "bytes": 0.0, "launches": 0})
+        f["ms"] += ms; f["flop"] += flop; f["bytes"] += byts; f["launches"] += 1
+
+    total_ms = 0.0
+    for key, ms, d in recs:
+        total_ms += ms
+        n = d["name"]
+        if d.get("kind") == "conv":
+            cout = d["cout"] * (4 if d["mode"] == 1 else 1)
+            pix = d["B"] * d["H"] * d["W"]
+            flop = 2.0 * pix * cout * (d["cin"] // d["g"]) * d["k"] ** 2
+            byts = 2.0 * pix * (d["cin"] + cout)
+            tensor = flop / byts >= RIDGE_FLOP_PER_BYTE
+            what = "weight gradient" if n.endswith("wgrad") else "forward / data gradient"
+            add(f"conv {what}, {'tensor' if tensor else 'hbm'}-bound shapes ({'conv_tc_wgrad_kernel / conv3x3_halo_wgrad_kernel' if n.endswith('wgrad') else 'conv_tc_kernel / conv3x3_halo_kernel'})",
+                "tensor" if tensor else "hbm", ms, flop, byts)
+        elif d.get("kind") == "act" and n in ("octave_affine_act", "octave_bn_bwd_reduce", "octave_bn_bwd_apply"):
+            el = d["esize"] * d["B"] * d["H"] * d["W"] * d["C"]
+            pres = d["present"]
+            if n == "octave_affine_act":          # x, res?, y
+                passes = 2 + (1 if 2 in pres else 0)
+            elif n == "octave_bn_bwd_reduce":     # dy, mask?, x
+                passes = 2 + (1 if 1 in pres else 0)
+            else:                                 # dy, mask?, x, dx, dmasked?
+                passes = 3 + (1 if 1 in pres else 0) + (1 if 11 in pres else 0)
+            add({"octave_affine_act": "BatchNorm apply (+residual, +ReLU) (affine_act_kernel)",
+                 "octave_bn_bwd_reduce": "BatchNorm backward, reduction pass (bn_bwd_reduce_kernel)",
+                 "octave_bn_bwd_apply": "BatchNorm backward, apply pass (bn_bwd_apply_kernel)"}[n], "hbm", ms, 0.0, float(passes * el))
+        else:
+            add("other kernels of this library (split-attention, pools, heads, critic plumbing, losses, packing)", "-", ms)
+    out = []
+    for name, f in fam.items():
+        rec = {"family": name, "bound": f["bound"], "launches": f["launches"], "ms_per_step": f["ms"], "share_of_kernel_time": f["ms"] / total_ms}
+        if f["bound"] == "tensor":
+            ach = f["flop"] / (f["ms"] * 1e-3) / 1e12
+            rec.update(achieved=ach, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"],
+                       algorithmic_flop=f["flop"])
+        elif f["bound"] == "hbm":
+            ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+            rec.update(achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"], algorithmic_bytes=f["bytes"])
+        out.append(rec)
+    out.sort(key=lambda r: -r["ms_per_step"])
+    return out, total_ms
+
+
+def best_conv_roofline(peaks, B, H, W):
+    """The fat decoder convolution (decoder_2.conv.0: 3x3 512->256 at H/4, 23.6 GFLOP/img at 400^2) timed alone."""
+    from octave_b200 import ops
     from octave_b200.ops import Act, ConvSpec
     dev = torch.device("cuda")
-    out = {}
-    # (1) decoder_2.conv.0: 3x3 512->256 at H/4 (23.6 GFLOP/img at 400^2 — one of the three fat decoder convs, SURVEY.md §8d)
     h, w = H // 4, W // 4
     x = Act(torch.randn(B, h, w, 512, device=dev).bfloat16(), B, h, w, 512)
     wt = torch.nn.Parameter(torch.randn(256, 512, 3, 3, device=dev) * 0.02)
@@ -206,53 +277,69 @@ def kernel_rooflines(peaks, B, H, W):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     ach = flops / (ms * 1e-3) / 1e12
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=32, 400^2 from one `ncu --set full` capture
+    # traffic of this launch at B=32, 400^2: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
     # (profiles/ncu_conv_fat_512x256_bn256_r01.txt: 330.4 MB + 137.7 MB; algorithmic minimum x + y + w = 494 MB)
     traffic = 468.1e6 if (B, H, W) == (32, 400, 400) else None
-    out["roofline"] = {"kernel": "conv_tc_kernel<256,64,4> (decoder_2.conv.0 fwd 3x3 512->256)", "bound": "tensor",
-                       "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                       "traffic": traffic, "algorithmic_flop": flops,
-                       "peak_source": peaks["source"] + " burst (kernel timed alone)", "ms_per_launch": ms}
-    # (2) fused loss kernel, forward statistics + gradient pass, bf16 maps (36.0 B/pixel algorithmic)
-    g = torch.Generator(device=dev).manual_seed(0)
-    agg = torch.randn(B, 2, H, W, device=dev, generator=g).bfloat16().requires_grad_()
-    ys = (torch.rand(B, 2, H, W, device=dev, generator=g) < 0.03).to(torch.bfloat16)
-    att = [torch.softmax(torch.randn(B, 2, H >> k, W >> k, device=dev, generator=g), 1).bfloat16().requires_grad_() for k in range(5)]
-    fl = losses.FusedSegmentorLoss()
-    def once():
-        r = fl(agg, ys, att)
-        (r['supervised'] + r['divergence']).backward()
-    for _ in range(3):
-        once()
-    torch.cuda.synchronize()
-    # time the two launches themselves through the C-ABI (no autograd / allocator noise)
-    cfg = losses._LossCfg(_lib.LOSS_WPCE | _lib.LOSS_KLD | _lib.LOSS_FROM_LOGITS, att_weights=[1.0] * 4, sum_weights=4.0)
-    attd = [a.detach() for a in att]
-    desc = losses._build_desc(cfg, agg.detach(), attd, None, None)
-    stats = torch.empty(_lib.lib.octave_loss_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
-    outv = torch.empty(8, device=dev)
-    gs = torch.ones(8, device=dev)
-    g_y = torch.empty_like(agg); g_a = [torch.empty_like(a) for a in attd]
-    arr, garr = losses._ptr_array(attd), losses._ptr_array(g_a)
-    sp = torch.cuda.current_stream().cuda_stream
-    def launch():
-        _lib.lib.octave_loss_fwd(C.byref(desc), agg.data_ptr(), ys.data_ptr(), arr, None, None, stats.data_ptr(), outv.data_ptr(), sp)
-        _lib.lib.octave_loss_bwd(C.byref(desc), agg.data_ptr(), ys.data_ptr(), arr, None, None, stats.data_ptr(), gs.data_ptr(),
-                                 g_y.data_ptr(), garr, None, None, sp)
-    for _ in range(3):
-        launch()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    tot = 0.0
-    for _ in range(reps):
-        flush.zero_()          # L2 flush between timed iterations (B200 L2 = 126 MB)
-        torch.cuda.synchronize(); e0.record(); launch(); e1.record(); torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    ms = tot / reps
-    nbytes = 17.99 * 2 * B * H * W
-    gbs = nbytes / (ms * 1e-3) / 1e9
-    out["loss_kernel"] = {"kernel": "loss_fast_fwd_kernel<bf16> + loss_fast_bwd_kernel<bf16>", "bound": "hbm", "achieved": gbs,
-                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
-                          "algorithmic_bytes": nbytes, "ms_fwd_plus_bwd": ms, "peak_source": peaks["source"]}
+    return {"kernel": "conv_tc_kernel<256,64,4> (decoder_2.conv.0 fwd 3x3 512->256), timed alone", "bound": "tensor", "achieved": ach,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic,
+            "algorithmic_flop": flops, "peak_source": peaks["source"] + " burst (kernel timed alone)", "ms_per_launch": ms}
+
+
+def loss_rooflines(peaks, B, H, W):
+    """K9, the G-step loss (WPCE + KLD on logits, 5-level pyramid): single pass = labels pre-pass + fused values-and-
+    gradients kernel, through the C-ABI.  Rotating input sets larger than L2, launches queued back to back between two CUDA
+    events on the launching stream.  Algorithmic bytes: 17.99 elements/pixel (what a statistics pass + a
+    gradient pass must move; the single pass moves 13.33).  Reported for bf16 maps (BASELINE.json's loss-kernel metric) and
+    for the variant TrainStep.g_step launches (fp32 maps as the heads emit them, + LS-G on the critic logits)."""
+    import ctypes as C
+    from octave_b200 import _lib, losses
+    dev = torch.device("cuda")
+    out = {}
+    for tag, dt, with_lsg in (("loss_kernel", torch.bfloat16, False), ("loss_kernel_in_step", torch.float32, True)):
+        es = 2 if dt == torch.bfloat16 else 4
+        npx = B * H * W
+        nsets = max(3, int(400e6 // (13.33 * es * npx)) + 1)
+        sets = []
+        for sd_ in range(nsets):
+            g = torch.Generator(device=dev).manual_seed(sd_)
+            agg = torch.randn(B, 2, H, W, device=dev, generator=g).to(dt)
+            ys = torch.zeros(B, 2, H, W, device=dev, dtype=dt)
+            ys[:, 0, ::37, :] = 1; ys[:, 1, 11::41, :] = 1
+            att = [torch.softmax(torch.randn(B, 2, H >> k, W >> k, device=dev, generator=g), 1).to(dt) for k in range(5)]
+            sets.append((agg, ys, att, torch.empty_like(agg), [torch.empty_like(a) for a in att]))
+        fake = torch.randn(B, 1, device=dev) if with_lsg else None
+        g_fake = torch.empty_like(fake) if with_lsg else None
+        flags = _lib.LOSS_WPCE | _lib.LOSS_KLD | _lib.LOSS_FROM_LOGITS | (_lib.LOSS_LSG if with_lsg else 0)
+        cfg = losses._LossCfg(flags, att_weights=[1.0] * 4, sum_weights=4.0)
+        desc = losses._build_desc(cfg, sets[0][0], sets[0][2], None, fake)
+        stats = torch.empty(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        outv = torch.empty(8, device=dev)
+        lam = (C.c_float * 3)(1.0, 0.1, 0.1)
+        sp = torch.cuda.current_stream().cuda_stream
+        fns = []
+        for agg, ys, att, g_y, g_a in sets:
+            arr, garr = losses._ptr_array(att), losses._ptr_array(g_a)
+            fns.append(lambda agg=agg, ys=ys, arr=arr, g_y=g_y, garr=garr: _lib.lib.octave_loss_fused(
+                C.byref(desc), agg.data_ptr(), ys.data_ptr(), arr, losses._ptr(fake), lam, stats.data_ptr(), outv.data_ptr(), g_y.data_ptr(),
+                garr, losses._ptr(g_fake), sp))
+        for f in fns:
+            assert f() == 0
+        torch.cuda.synchronize()
+        reps = 40
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fns[i % nsets]()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = 17.99 * es * npx
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[tag] = {"kernel": f"loss_label_count_kernel + loss_fused_kernel<{'bf16' if es == 2 else 'float'}> (single pass: values and gradients"
+                              f"{', + LS-G' if with_lsg else ''})", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes": nbytes, "bytes_moved": 13.33 * es * npx, "us_per_evaluation": ms * 1e3,
+                    "traffic": None, "peak_source": peaks["source"], "maps": f"[{B},2,{H},{W}] {'bf16' if es == 2 else 'fp32'}, {nsets} rotating sets"}
+        del sets, fns
+        torch.cuda.empty_cache()
     return out
 
 
@@ -374,7 +461,19 @@ def run_gpu(args):
                                         "frac_of_sustained_peak": flops / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
         if args.dtype == "bf16":
             try:
-                line.update(kernel_rooflines(peaks, min(B, 32), H, W))
+                dev_batch = tuple(t.to(dev) if torch.is_tensor(t) else [r.to(dev) for r in t] for t in host[0])
+                fams, eager_kernel_ms = family_rooflines(ts, dev_batch, peaks, ms_step)
+                line["kernel_families"] = fams
+                line["kernel_time_of_one_eager_step_ms"] = eager_kernel_ms
+                dom = next(f for f in fams if f["bound"] in ("tensor", "hbm"))
+                line["roofline"] = {"kernel": dom["family"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                                    "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
+                                    "share_of_kernel_time": dom["share_of_kernel_time"], "launches_per_step": dom["launches"],
+                                    "how": "largest kernel family of the step by summed duration; CUDA events around each launch of one eager "
+                                           "step on the launching stream; peak = " + ("sustained bf16" if dom["bound"] == "tensor" else "measured HBM copy")
+                                           + " (" + peaks["source"] + ")"}
+                line["best_kernel"] = best_conv_roofline(peaks, min(B, 32), H, W)
+                line.update(loss_rooflines(peaks, min(B, 32), H, W))
             except Exception as e:  # pragma: no cover
                 line["roofline_error"] = repr(e)
         if world == 1 and not args.no_cpu:
@@ -401,16 +500,25 @@ def run_gpu(args):
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path — its modules cannot travel to the GPU box
+    (/root/reference is absent there and the repo has no installer), so the oracle port runs, on all host cores.  Each step
+    is one G+D iteration on a bounded sample (batch 2) of the arm's config; exactly `steps` steps after `warmup` are timed."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     B, H, W = CONFIGS[args.config]
-    cb = run_cpu(H, W, 2, max(1, min(args.steps, 5)), max(1, min(args.warmup, 1)))
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    if args.ref_budget_s > 0:
+        # keep the arm within its time budget on slow hosts: ~1 s per batch-2 step at 400^2 on 16 cores
+        est = 1.0 * (H * W) / 160000.0
+        steps = max(1, min(steps, int(args.ref_budget_s / est) - warmup))
+    cb = run_cpu(H, W, 2, steps, warmup)
     line = {"impl": "reference", "metric": f"train images/s, {H}x{W} synthetic OCTA (adversarial step: G-step + D-step)",
-            "value": cb["value"], "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "value": cb["value"], "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": steps,
+            "warmup": warmup, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: OctaScribbleNet G+D training step, {H}x{W}; each step is a bounded sample of batch 2"},
+            "config": {"workload": f"{args.config}: OctaScribbleNet G+D training step, {H}x{W}; each step is a bounded sample of batch 2 "
+                                   f"(BASELINE.json configs[0] is this step at 304x304, batch 2: --config c1)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -426,6 +534,7 @@ if __name__ == "__main__":
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: cap the number of timed steps so that the run fits this many seconds (0 = no cap)")
     ap.add_argument("--comparator", action="store_true", help="also time the reference arithmetic on stock torch CUDA ops (cuDNN) on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~1100 kernels of a step eagerly instead of replaying one CUDA graph")
     a = ap.parse_args()

@@ -348,6 +348,31 @@ typedef struct OctavePackJob {
 int64_t octave_pack_job_blocks(int32_t mode, int32_t cout, int32_t cin, int32_t dense_groups, int32_t ksize);
 int octave_pack_weight_multi(const OctavePackJob* jobs_device, int32_t n_jobs, int64_t total_blocks, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-tensor optimiser step: every parameter of a module in ONE launch.  The reference ships no
+ * optimiser (README.md:39-47: the training script lives on another branch); the update rules are torch.optim.SGD
+ * (momentum, weight decay; dampening 0, no Nesterov) and torch.optim.AdamW (no amsgrad).  jobs_device: device array
+ * sorted by block_start; job i owns octave_optim_job_blocks(n_i) blocks.  m / v: fp32 state of the same size as w
+ * (v unused by SGD; with first_step != 0 SGD initialises m with the gradient, as torch does).  bias_correction{1,2} =
+ * 1 - beta^t are supplied by the host. */
+#define OCT_OPT_SGD 0
+#define OCT_OPT_ADAMW 1
+typedef struct OctaveOptJob {
+  float* w;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+  int64_t block_start;
+} OctaveOptJob;
+typedef struct OctaveOptHyper {
+  int32_t algo, first_step;
+  float lr, momentum, weight_decay, beta1, beta2, eps, bias_correction1, bias_correction2;
+} OctaveOptHyper;
+int64_t octave_optim_job_blocks(int64_t n);
+int octave_optim_multi(const OctaveOptJob* jobs_device, int32_t n_jobs, int64_t total_blocks, const OctaveOptHyper* hyper,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
     const int th = r / p.TWp, tw = r - th * p.TWp;
     uint8_t* const stage = stage_gen + (warp - 2) * (32 * PITCH);
     float sacc[4] = {0.f, 0.f, 0.f, 0.f};   // statistics of this lane's column pair (tile_col_stats)
+    const bool plain = p.bias == nullptr && p.act == 0;
     int stat_col0 = -1;
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -206,29 +207,43 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+      if (plain && __all_sync(0xffffffffu, valid)) {
+        // common case (conv -> BatchNorm, interior patch): straight pack, no per-element predicated bias loads / selects
 #pragma unroll
-      for (int c = 0; c < NCHUNK_W; ++c) {
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          f[i] = __uint_as_float(v[c][i]);
-          if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
+        for (int c = 0; c < NCHUNK_W; ++c) {
+          uint4 u0, u1;
+          u0.x = bf16x2_pack(__uint_as_float(v[c][0]), __uint_as_float(v[c][1]));   u0.y = bf16x2_pack(__uint_as_float(v[c][2]), __uint_as_float(v[c][3]));
+          u0.z = bf16x2_pack(__uint_as_float(v[c][4]), __uint_as_float(v[c][5]));   u0.w = bf16x2_pack(__uint_as_float(v[c][6]), __uint_as_float(v[c][7]));
+          u1.x = bf16x2_pack(__uint_as_float(v[c][8]), __uint_as_float(v[c][9]));   u1.y = bf16x2_pack(__uint_as_float(v[c][10]), __uint_as_float(v[c][11]));
+          u1.z = bf16x2_pack(__uint_as_float(v[c][12]), __uint_as_float(v[c][13])); u1.w = bf16x2_pack(__uint_as_float(v[c][14]), __uint_as_float(v[c][15]));
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
         }
-        if (p.act) {
+      } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = halo_act(f[i], p.act);
-        }
-        if (!valid) {   // rows that are not stored stage zeros: they must not enter the statistics (and may be NaN junk)
+        for (int c = 0; c < NCHUNK_W; ++c) {
+          float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = 0.f;
+          for (int i = 0; i < 16; ++i) {
+            f[i] = __uint_as_float(v[c][i]);
+            if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
+          }
+          if (p.act) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = halo_act(f[i], p.act);
+          }
+          if (!valid) {   // rows that are not stored stage zeros: they must not enter the statistics (and may be NaN junk)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = 0.f;
+          }
+          uint4 u0, u1;
+          u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
+          u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
+          u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
+          u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
+          *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
         }
-        uint4 u0, u1;
-        u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
-        u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
-        u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
-        u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
-        *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
-        *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
       }
       __syncwarp();   // staged rows are read by other lanes below
       if (p.stats) tile_col_stats<COLS_W, PITCH>(stage, lane, sacc);

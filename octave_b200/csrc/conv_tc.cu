@@ -60,6 +60,15 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   }
 }
 
+
+// 16 fp32 accumulator columns -> two 16-byte vectors of bf16
+__device__ __forceinline__ void pack16(const uint32_t (&v)[16], uint4& u0, uint4& u1) {
+  u0.x = bf16x2_pack(__uint_as_float(v[0]), __uint_as_float(v[1]));   u0.y = bf16x2_pack(__uint_as_float(v[2]), __uint_as_float(v[3]));
+  u0.z = bf16x2_pack(__uint_as_float(v[4]), __uint_as_float(v[5]));   u0.w = bf16x2_pack(__uint_as_float(v[6]), __uint_as_float(v[7]));
+  u1.x = bf16x2_pack(__uint_as_float(v[8]), __uint_as_float(v[9]));   u1.y = bf16x2_pack(__uint_as_float(v[10]), __uint_as_float(v[11]));
+  u1.z = bf16x2_pack(__uint_as_float(v[12]), __uint_as_float(v[13])); u1.w = bf16x2_pack(__uint_as_float(v[14]), __uint_as_float(v[15]));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // forward / dgrad kernel — persistent: one CTA per SM loops over output tiles (N tile fastest, so the CTAs that
 // share an A tile run side by side and hit L2).  Two TMEM accumulators: the epilogue of tile i (TMEM -> registers ->
@@ -208,6 +217,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
     for (int h2 = 0; h2 < NS; ++h2) sacc[h2][0] = sacc[h2][1] = sacc[h2][2] = sacc[h2][3] = 0.f;
     int stat_col0 = -1;  // global channel of this warp's column 0 (fixed across the CTA's tiles when stats are on)
+    const bool plain = p.bias == nullptr && p.act == 0;
     uint32_t li = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++li) {
       const uint32_t buf = li & 1u;
@@ -237,6 +247,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       const long long row_off = valid ? (((long long)img * p.Hout + oh) * p.Wout + ow) * p.ldc + p.c_off + cshift + cbase : -1;
       stat_col0 = cbase;
       const int nvalid = min(COLS_W, p.cout_g - n0);
+      // warp-uniform: nothing to add or clamp and no row of this warp falls outside the image
+      const bool plain_tile = plain && __all_sync(0xffffffffu, valid);
       tc::mbar_wait(tc::smem_u32(&acc_full[buf]), (li >> 1) & 1u);
       tc::fence_after_sync();
       if constexpr (SLAB) {
@@ -254,29 +266,41 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
           }
+          if (plain_tile) {
+            // common case (conv -> BatchNorm: no bias, no activation, every row inside the image): straight pack, no
+            // per-element predicated bias loads / selects
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              f[i] = __uint_as_float(v[cc][i]);
-              if (p.bias) f[i] += __ldg(p.bias + cbase + (h2 * 4 + cc) * 16 + i);
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 u0, u1;
+              pack16(v[cc], u0, u1);
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc) ^ rx) << 4)) = u0;
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc + 1) ^ rx) << 4)) = u1;
             }
-            if (p.act) {
+          } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
-            }
-            if (!valid) {
+            for (int cc = 0; cc < 4; ++cc) {
+              float f[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = 0.f;
+              for (int i = 0; i < 16; ++i) {
+                f[i] = __uint_as_float(v[cc][i]);
+                if (p.bias) f[i] += __ldg(p.bias + cbase + (h2 * 4 + cc) * 16 + i);
+              }
+              if (p.act) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
+              }
+              if (!valid) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = 0.f;
+              }
+              uint4 u0, u1;
+              u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
+              u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
+              u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
+              u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc) ^ rx) << 4)) = u0;
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc + 1) ^ rx) << 4)) = u1;
             }
-            uint4 u0, u1;
-            u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
-            u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
-            u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
-            u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
-            *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc) ^ rx) << 4)) = u0;
-            *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * cc + 1) ^ rx) << 4)) = u1;
           }
           __syncwarp();
           if (p.stats) {
@@ -324,30 +348,41 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
           }
+          if (plain_tile) {
+            // common case (conv -> BatchNorm: no bias, no activation, every row inside the image): straight pack
 #pragma unroll
-          for (int cc = 0; cc < LDG; ++cc) {
-            const int c = c0 + cc;
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              f[i] = __uint_as_float(v[cc][i]);
-              if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
+            for (int cc = 0; cc < LDG; ++cc) {
+              uint4 u0, u1;
+              pack16(v[cc], u0, u1);
+              *reinterpret_cast<uint4*>(stage + lane * PITCH + (c0 + cc) * 32) = u0;
+              *reinterpret_cast<uint4*>(stage + lane * PITCH + (c0 + cc) * 32 + 16) = u1;
             }
-            if (p.act) {
+          } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
-            }
-            if (!valid) {   // rows outside the image stage zeros: they are not stored and must not enter the statistics
+            for (int cc = 0; cc < LDG; ++cc) {
+              const int c = c0 + cc;
+              float f[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = 0.f;
+              for (int i = 0; i < 16; ++i) {
+                f[i] = __uint_as_float(v[cc][i]);
+                if (p.bias) f[i] += __ldg(p.bias + cbase + c * 16 + i);
+              }
+              if (p.act) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = tc_act(f[i], p.act);
+              }
+              if (!valid) {   // rows outside the image stage zeros: they are not stored and must not enter the statistics
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = 0.f;
+              }
+              uint4 u0, u1;
+              u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
+              u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
+              u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
+              u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
+              *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
+              *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
             }
-            uint4 u0, u1;
-            u0.x = bf16x2_pack(f[0], f[1]); u0.y = bf16x2_pack(f[2], f[3]);
-            u0.z = bf16x2_pack(f[4], f[5]); u0.w = bf16x2_pack(f[6], f[7]);
-            u1.x = bf16x2_pack(f[8], f[9]); u1.y = bf16x2_pack(f[10], f[11]);
-            u1.z = bf16x2_pack(f[12], f[13]); u1.w = bf16x2_pack(f[14], f[15]);
-            *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32) = u0;
-            *reinterpret_cast<uint4*>(stage + lane * PITCH + c * 32 + 16) = u1;
           }
         }
         __syncwarp();   // staged rows are read by other lanes below
@@ -398,14 +433,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
             }
           }
         } else {
-#pragma unroll 4
-          for (int r0 = 0; r0 < 32; r0 += RPI) {
-            const int row = r0 + rsel;
-            const long long off = __shfl_sync(0xffffffffu, row_off, row);
-            if (off >= 0 && sub * 8 < nvalid) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stage + row * PITCH + sub * 16);
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + sub * 8) = val;
-            }
+          // the row offsets travel by shuffle first (independent), then the loads from the staging rows, then the stores
+          constexpr int SB = NIT > 8 ? 8 : NIT;
+#pragma unroll 1
+          for (int i0 = 0; i0 < NIT; i0 += SB) {
+            long long offs[SB];
+            uint4 vals[SB];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) offs[i] = __shfl_sync(0xffffffffu, row_off, (i0 + i) * RPI + rsel);
+            const bool col_ok = sub * 8 < nvalid;
+#pragma unroll
+            for (int i = 0; i < SB; ++i) vals[i] = *reinterpret_cast<const uint4*>(stage + ((i0 + i) * RPI + rsel) * PITCH + sub * 16);
+#pragma unroll
+            for (int i = 0; i < SB; ++i)
+              if (offs[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + sub * 8) = vals[i];
           }
         }
         __syncwarp();  // staging rows are rewritten by the next tile

@@ -134,20 +134,31 @@ class _null:
         return False
 
 
+def _momentum_buffers(opt) -> List[Tensor]:
+    """momentum buffers that exist right now (torch.optim.SGD state or octave_b200.optim.FusedSGD.m)"""
+    if hasattr(opt, "momentum_buffers"):
+        return [b for b in opt.momentum_buffers if b is not None]
+    return [st["momentum_buffer"] for st in opt.state.values() if st.get("momentum_buffer") is not None]
+
+
 class TrainStep:
     """Owns the optimisers and runs one adversarial iteration.  `lambda_kl`, `lambda_g` and SGD(momentum) are this
     harness' choice (the mounted branch of the reference specifies none)."""
 
     def __init__(self, net: OctaScribbleNet, lr: float = 1e-3, momentum: float = 0.9, lambda_kl: float = 0.1,
-                 lambda_g: float = 0.1, distributed: bool = False, bucket_bytes: int = 25 << 20):
+                 lambda_g: float = 0.1, distributed: bool = False, bucket_bytes: int = 25 << 20, fused_optimizer: bool = True):
         self.net = net
         self.lambda_kl, self.lambda_g = lambda_kl, lambda_g
         self.seg_params = [p for n, p in net.segmentor.named_parameters() if not n.startswith("linear_head_")]
-        self.opt_g = torch.optim.SGD(self.seg_params, lr=lr, momentum=momentum)
+        # one multi-tensor launch per optimiser step (octave_optim_multi) on the GPU; torch.optim.SGD otherwise (CPU tests)
+        fused = fused_optimizer and all(p.is_cuda for p in self.seg_params)
+        from .optim import FusedSGD
+        make_opt = (lambda ps: FusedSGD(ps, lr=lr, momentum=momentum)) if fused else (lambda ps: torch.optim.SGD(ps, lr=lr, momentum=momentum))
+        self.opt_g = make_opt(self.seg_params)
         self.has_d = hasattr(net, "discriminator")
         if self.has_d:
             self.dis_params = list(net.discriminator.parameters())
-            self.opt_d = torch.optim.SGD(self.dis_params, lr=lr, momentum=momentum)
+            self.opt_d = make_opt(self.dis_params)
         self.loss = FusedSegmentorLoss(weakly_supervise=isinstance(net.supervised_loss, nn.Module)
                                        and net.supervised_loss.__class__.__name__ == "WeightedPartialCE")
         self.lsd = LSDiscriminatorialLoss()
@@ -203,9 +214,15 @@ class TrainStep:
         static device buffers (x / ys / real may live in pinned host memory); the returned tensors are static too and are
         overwritten by the next call.  The critic's per-call CPU randomness is drawn on the host before every replay in
         the eager order (discriminator.HostRandomFeed), so the CPU generator advances exactly as in eager mode.
+        The learning rate, momentum and loss weights are baked into the captured graph (re-capture after changing them:
+        `self._graph = None; self.graph_error = None`); batch shapes are static.
         Falls back to `step` (and says so in `self.graph_error`) when capture is not possible."""
         if getattr(self, "_graph", None) is None and getattr(self, "graph_error", None) is None:
             self._capture(x, ys, real)
+        elif self._graph is not None and (tuple(x.shape) != tuple(self._sx.shape) or tuple(ys.shape) != tuple(self._sys.shape)
+                                          or len(real) != len(self._sreal)):
+            raise ValueError(f"octave_b200: step_graphed was captured for x {tuple(self._sx.shape)} / ys {tuple(self._sys.shape)}; "
+                             f"got {tuple(x.shape)} / {tuple(ys.shape)} (a captured CUDA graph has static shapes)")
         if self._graph is None:
             dev = next(self.net.parameters()).device
             return self.step(x.to(dev, non_blocking=True), ys.to(dev, non_blocking=True), [r.to(dev, non_blocking=True) for r in real])
@@ -224,8 +241,13 @@ class TrainStep:
         if getattr(self, "_copy_stream", None) is not None:
             self._handover.record()          # staging buffers are free again once these copies have run
         if self._feed is not None:
+            # the previous replay's upload nodes read the pinned noise / sign buffers asynchronously: wait until they
+            # have run before the host overwrites them (a host/device race otherwise when the caller does not synchronise)
+            self._replay_done.synchronize()
             self._feed.draw()
         self._graph.replay()
+        if self._feed is not None:
+            self._replay_done.record()
         return self._sout
 
     def prefetch(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> None:
@@ -261,14 +283,32 @@ class TrainStep:
             self._sreal = [r.to(dev).clone() for r in real]
             self._feed = HostRandomFeed(net.discriminator, 3, dev)       # D(fake) in the G-step, D(real) + D(fake) in the D-step
             net.discriminator._rand_feed = self._feed
+            # The warm-up steps (allocator, lazy state) must not train: parameters, BatchNorm / spectral-norm buffers and
+            # the optimiser state are put back afterwards, so the first replay is the first optimiser step on this batch.
+            snap = {k: v.detach().clone() for k, v in net.state_dict().items()}
+            opts = [self.opt_g] + ([self.opt_d] if self.has_d else [])
+            had_mom = [{id(b): b.detach().clone() for b in _momentum_buffers(o)} for o in opts]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):                                        # warm-up on a side stream (allocator, lazy state)
+                for _ in range(2):                                        # warm-up on a side stream
                     self._feed.draw(); self._feed.upload()
                     self.step(self._sx, self._sys, self._sreal)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            with torch.no_grad():
+                cur = net.state_dict()
+                for k, v in snap.items():
+                    cur[k].copy_(v)
+                for o, before in zip(opts, had_mom):
+                    for buf in _momentum_buffers(o):
+                        if id(buf) in before:
+                            buf.copy_(before[id(buf)])
+                        else:
+                            buf.zero_()            # SGD: zeroed momentum + first gradient == a fresh first step
+            del snap, had_mom
+            self._replay_done = torch.cuda.Event()
+            self._replay_done.record()
             from . import _lib
             g = torch.cuda.CUDAGraph()
             l0 = _lib.lib.octave_launch_count()             # (no host draw here: capture executes nothing)

@@ -20,7 +20,7 @@ ts.step(x, ys, real); profiler.reset()
 ts.step(x, ys, real)
 torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
-for k, e0, e1 in profiler._records:
+for k, e0, e1, _d in profiler._records:
     agg[k][0] += 1; agg[k][1] += e0.elapsed_time(e1)
 rows = []
 for k, (n, ms) in agg.items():
