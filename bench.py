@@ -445,7 +445,7 @@ def run_gpu(args):
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"{args.config}: OctaScribbleNet G+D training step, batch {B}/GPU, {H}x{W}, random-init weights",
                    "global_batch": world * B, "parallelism": f"dp{world}", "l2": "working set >> L2 (inputs+activations of one step are GBs)",
-                   "optimizer": "torch SGD(momentum), foreach; the per-step bf16 operand re-pack of all conv weights is one multi-tensor kernel launch (SURVEY.md §8f.1)"},
+                   "optimizer": "SGD(momentum) as ONE multi-tensor launch per module (octave_optim_multi) + ONE launch re-packing the bf16 operands of all conv weights (SURVEY.md §8f.1)"},
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),

@@ -53,34 +53,56 @@ class HostRandomFeed:
     """Static pinned + device buffers for the per-call CPU draws of InstanceNoise / LabelNoise.  With a feed installed
     (`DiscriminatorBlock._rand_feed`) a forward call takes its noise plane and label-flip sign from slot k of these
     buffers instead of drawing: `draw()` makes the very same CPU draws in the same order for all the calls of one step,
-    `upload()` is the (capturable) host-to-device copy.  A captured CUDA graph of the training step therefore sees fresh
+    `upload()` is the stream-ordered host-to-device copy issued before each replay.  A captured CUDA graph of the training step therefore sees fresh
     host randomness at every replay while the CPU generator advances exactly as in eager mode."""
+
+    RING = 2      # pinned staging slots: the host fills slot i+1 while the upload of slot i may still be pending
 
     def __init__(self, disc: "DiscriminatorBlock", n_calls: int, device):
         self.disc, self.n_calls, self.slot = disc, n_calls, 0
         inst = disc._inst
         self.has_noise = inst is not None and inst.is_training
         if self.has_noise:
-            self.noise_pin = [torch.empty(inst.size, dtype=torch.float32).pin_memory() for _ in range(n_calls)]
+            self.noise_pin = [[torch.empty(inst.size, dtype=torch.float32).pin_memory() for _ in range(n_calls)] for _ in range(self.RING)]
             self.noise_dev = [torch.empty(inst.size, dtype=torch.float32, device=device) for _ in range(n_calls)]
-        self.sign_pin = torch.ones(n_calls, dtype=torch.float32).pin_memory()
+        self.sign_pin = [torch.ones(n_calls, dtype=torch.float32).pin_memory() for _ in range(self.RING)]
         self.sign_dev = torch.ones(n_calls, dtype=torch.float32, device=device)
+        self._ring = 0
+        self._uploaded = [None] * self.RING          # event recorded after the upload that reads ring slot r
 
     def draw(self) -> None:
+        """The CPU draws of one step (same generator, same order as the eager modules) into the next pinned ring slot.
+        Blocks only if the upload issued RING steps ago from this slot has not run yet."""
         d = self.disc
+        self._ring = (self._ring + 1) % self.RING
+        ev = self._uploaded[self._ring]
+        if ev is not None:
+            ev.synchronize()
         for k in range(self.n_calls):
             if d._inst is not None:
                 noise = d._inst.draw()
                 if self.has_noise:
-                    self.noise_pin[k].copy_(noise)
+                    self.noise_pin[self._ring][k].copy_(noise)
             if d._label is not None:
-                self.sign_pin[k] = -1.0 if d._label.draw_flip() else 1.0
+                self.sign_pin[self._ring][k] = -1.0 if d._label.draw_flip() else 1.0
 
     def upload(self) -> None:
+        """Asynchronous host-to-device copy of the slot filled by the last draw() (stream-ordered: NOT part of a captured
+        graph, so that the pinned source can rotate)."""
+        r = self._ring
         if self.has_noise:
             for k in range(self.n_calls):
-                self.noise_dev[k].copy_(self.noise_pin[k], non_blocking=True)
-        self.sign_dev.copy_(self.sign_pin, non_blocking=True)
+                self.noise_dev[k].copy_(self.noise_pin[r][k], non_blocking=True)
+        self.sign_dev.copy_(self.sign_pin[r], non_blocking=True)
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("octave_b200: HostRandomFeed.upload() must not be captured")
+        ev = self._uploaded[r] or torch.cuda.Event()
+        ev.record()
+        self._uploaded[r] = ev
+        self.slot = 0
+
+    def rewind(self) -> None:
+        """start of a step whose buffers were uploaded outside (graph replay): calls take slots 0.. again"""
         self.slot = 0
 
     def next(self):

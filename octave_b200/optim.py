@@ -48,6 +48,7 @@ class _MultiTensorOptimizer:
         self._table = None
         self._blocks = 0
         self._n = 0
+        self._ring, self._pin, self._dev, self._ev, self._captured = 0, [None, None], [None, None], [None, None], []
 
     # torch.optim interface ------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = True) -> None:
@@ -85,9 +86,29 @@ class _MultiTensorOptimizer:
             sig.append((p.data_ptr(), g.data_ptr()))
             start += lib.octave_optim_job_blocks(p.numel())
         if sig != self._sig:
+            # (eager mode: gradients are fresh tensors every step, so the table is re-uploaded every step)
             arr = (OptJob * len(jobs))(*[OptJob(*j) for j in jobs])
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
-            self._table = host.to(dev, non_blocking=False)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            if torch.cuda.is_current_stream_capturing():
+                # the upload becomes a node of the graph and runs at every replay: its pinned source is never reused
+                pin = raw.clone().pin_memory()
+                self._captured.append(pin)
+                self._table = torch.empty(raw.numel(), dtype=torch.uint8, device=dev)
+                self._captured.append(self._table)
+            else:
+                r = self._ring = (self._ring + 1) % 2
+                if self._pin[r] is None or self._pin[r].numel() < raw.numel():
+                    self._pin[r] = torch.empty(max(raw.numel(), 1 << 16), dtype=torch.uint8).pin_memory()
+                    self._dev[r] = torch.empty(self._pin[r].numel(), dtype=torch.uint8, device=dev)
+                elif self._ev[r] is not None:
+                    self._ev[r].synchronize()      # the upload issued two steps ago from this slot has run
+                pin = self._pin[r][:raw.numel()]
+                pin.copy_(raw)
+                self._table = self._dev[r][:raw.numel()]
+            self._table.copy_(pin, non_blocking=True)
+            if not torch.cuda.is_current_stream_capturing():
+                self._ev[self._ring] = self._ev[self._ring] or torch.cuda.Event()
+                self._ev[self._ring].record()
             self._sig, self._n, self._blocks = sig, len(jobs), start
         h = self._hyper(self.steps == 0)
         _lib.check("octave_optim_multi", lib.octave_optim_multi(self._table.data_ptr(), self._n, self._blocks, C.byref(h), _stream_ptr()))
@@ -119,7 +140,9 @@ class FusedSGD(_MultiTensorOptimizer):
 
 
 class FusedAdamW(_MultiTensorOptimizer):
-    """torch.optim.AdamW(params, lr, betas, eps, weight_decay) semantics (no amsgrad) in one launch per step."""
+    """torch.optim.AdamW(params, lr, betas, eps, weight_decay) semantics (no amsgrad) in one launch per step.  One step
+    count serves every parameter's bias corrections (torch counts per parameter: the two differ only for a parameter that
+    had no gradient in some step).  The bias corrections are host values: re-capture a CUDA graph that contains step()."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
         super().__init__(params, lr)

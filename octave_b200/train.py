@@ -241,13 +241,11 @@ class TrainStep:
         if getattr(self, "_copy_stream", None) is not None:
             self._handover.record()          # staging buffers are free again once these copies have run
         if self._feed is not None:
-            # the previous replay's upload nodes read the pinned noise / sign buffers asynchronously: wait until they
-            # have run before the host overwrites them (a host/device race otherwise when the caller does not synchronise)
-            self._replay_done.synchronize()
+            # fresh CPU draws for this step: filled into the next pinned ring slot and uploaded on this stream BEFORE the
+            # replay (outside the graph, so the pinned source rotates and the host never overwrites a pending upload)
             self._feed.draw()
+            self._feed.upload()
         self._graph.replay()
-        if self._feed is not None:
-            self._replay_done.record()
         return self._sout
 
     def prefetch(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> None:
@@ -307,13 +305,11 @@ class TrainStep:
                         else:
                             buf.zero_()            # SGD: zeroed momentum + first gradient == a fresh first step
             del snap, had_mom
-            self._replay_done = torch.cuda.Event()
-            self._replay_done.record()
             from . import _lib
             g = torch.cuda.CUDAGraph()
             l0 = _lib.lib.octave_launch_count()             # (no host draw here: capture executes nothing)
             with torch.cuda.graph(g):
-                self._feed.upload()
+                self._feed.rewind()
                 out = self.step(self._sx, self._sys, self._sreal)
             self.graph_kernel_nodes = int(_lib.lib.octave_launch_count() - l0)   # this library's kernels per replay
             out.pop('attentions', None)
