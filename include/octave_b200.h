@@ -100,6 +100,15 @@ int octave_loss_bwd(const OctaveLossDesc* d, const void* yhat, const void* ys,
                     const void* stats, const float* gscale, void* g_yhat, void* const* g_att,
                     float* g_real, float* g_fake, void* stream);
 
+/* The two branches of WeightedPartialCE.forward that OctaScribbleNet does not take (segmentor/losses.py:40-49,56-59), fp32:
+ *   mode 0  manual=False, C == 2: nn.CrossEntropyLoss()(z, ys[:,1].long()), z = y_hat*ys (y_hat when full) as logits
+ *   mode 1  num_classes == 1    : nn.BCEWithLogitsLoss()(z, ys)
+ * mean over B*H*W; scratch2: 2 doubles of device scratch; out: float[1]; gscale: device float[1] upstream gradient. */
+int octave_wpce_alt_fwd(int32_t mode, const float* yhat, const float* ys, int32_t B, int32_t C, int32_t H, int32_t W,
+                        int32_t full, double* scratch2, float* out, void* stream);
+int octave_wpce_alt_bwd(int32_t mode, const float* yhat, const float* ys, int32_t B, int32_t C, int32_t H, int32_t W,
+                        int32_t full, const float* gscale, float* g_yhat, void* stream);
+
 /* Fused single pass of the G-step (training loop): loss VALUES and GRADIENTS from one sweep over the maps.
  * total = lambdas[0]*WPCE + lambdas[1]*KLD + lambdas[2]*LSG (host float[3]); the gradients of `total` w.r.t. yhat,
  * att[k] and d_fake are written in the same pass (a labels-only pre-pass supplies the class counts of losses.py:34-38),

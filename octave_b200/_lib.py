@@ -108,6 +108,10 @@ lib.octave_loss_fused_stats_bytes.argtypes = [C.POINTER(LossDesc)]
 lib.octave_loss_fused.restype = C.c_int
 lib.octave_loss_fused.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, C.POINTER(C.c_float), _vp, _vp, _vp,
                                   C.POINTER(_vp), _vp, _vp]
+lib.octave_wpce_alt_fwd.restype = C.c_int
+lib.octave_wpce_alt_fwd.argtypes = [C.c_int32, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]
+lib.octave_wpce_alt_bwd.restype = C.c_int
+lib.octave_wpce_alt_bwd.argtypes = [C.c_int32, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]
 lib.octave_loss_scale_grads.restype = C.c_int
 lib.octave_loss_scale_grads.argtypes = [C.POINTER(LossDesc), _vp, _vp, C.POINTER(_vp), _vp, _vp]
 

@@ -13,6 +13,12 @@ compute_dtype = "bf16"
 fold_bn_inference = True
 
 
+# Backward pass: launch the weight-gradient kernels on a second stream.  wgrad(L) depends only on the saved input of conv L
+# and on dz_L, so it can run beside the rest of the chain (dgrad(L), then the HBM-bound BatchNorm backward of layer L-1):
+# tensor-pipe-bound and HBM-bound kernels then share the SMs instead of taking turns.  Joined before the gradients are used.
+overlap_wgrad = True
+
+
 def set_compute_dtype(name: str) -> None:
     global compute_dtype
     if name not in ("bf16", "fp32"):

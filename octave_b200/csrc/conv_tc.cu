@@ -81,9 +81,16 @@ __device__ __forceinline__ void pack16(const uint32_t (&v)[16], uint4& u0, uint4
 constexpr int kProducers = 4;                         // TMA producer warps (one issuing lane each)
 constexpr int kFwdThreads = (10 + kProducers - 1) * 32;  // warp 0 + warps 10.. producers, warp 1 MMA, warps 2..9 epilogue
 
-template <int BN, int BK, int STAGES>
+// EPI = 1 (plain outputs: no bias / activation / accumulate / scatter, BN <= 128): the epilogue stages the bf16 tile in the
+// TMA box layout (128 pixel rows x 64-column slabs, 16-byte units XOR-swizzled like SWIZZLE_128B/64B/32B) and ONE thread
+// per slab issues a TMA store (cp.async.bulk.tensor ... bulk_group) — the hardware clips rows / columns outside the tensor,
+// so there are no per-row offsets, shuffles or per-lane global stores left in the epilogue (ncu on the 1x1 layers: the
+// per-lane store loop, the predicated bias / activation code and the barrier spin loops were > 2/3 of the issued
+// instructions of these HBM-bound launches).
+template <int BN, int BK, int STAGES, int EPI = 0>
 __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ CUtensorMap tmC,
                                                              const ConvTcParams p) {
   constexpr int A_BYTES = 128 * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
@@ -120,12 +127,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(tc::smem_u32(&acc_full[b]), 1);
-      tc::mbar_init(tc::smem_u32(&acc_empty[b]), 8);  // one arrival per epilogue warp
+      tc::mbar_init(tc::smem_u32(&acc_empty[b]), EPI == 1 ? 4 : 8);  // one arrival per epilogue warp that reads this accumulator
     }
     tc::fence_barrier_init();
     tc::fence_proxy_async();
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
+    if (EPI == 1) tc::tma_prefetch_desc(&tmC);
+  }
+  if (EPI == 1) {
+    // staging rows beyond the patch (TW*TH < 128) are never written by the epilogue: zero them once (they feed the statistics)
+    uint8_t* st0 = smem_gen + STAGES * STAGE_BYTES;
+    for (int i = threadIdx.x * 16; i < 2 * 128 * BN * 2; i += kFwdThreads * 16) *reinterpret_cast<uint4*>(st0 + i) = make_uint4(0, 0, 0, 0);
   }
   if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_slot));
   tc::fence_before_sync();
@@ -202,6 +215,117 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       if (leader) tc::umma_commit(tc::smem_u32(&acc_full[buf]));
+    }
+  } else if (EPI == 1) {
+    // ---- TMA-store epilogue (see the kernel comment): TWO groups of four warps take alternate tiles (group = accumulator
+    // buffer), so the TMEM -> staging -> statistics -> store chain of one tile overlaps the next tile's — these launches
+    // are bound by that per-tile latency chain, not by issue slots or HBM.  A warp owns the 32 rows of its TMEM lane
+    // quarter over ALL BN columns; a slab = up to 64 columns x 128 rows in the TMA box layout.
+    constexpr int SWC = BN < 64 ? BN : 64;          // columns of one slab
+    constexpr int RB = SWC * 2;                     // bytes per staged row = swizzle span
+    constexpr int SLAB_BYTES = 128 * RB;
+    constexpr int NSL = BN / SWC;                   // slabs per tile (2 for BN = 128)
+    constexpr int CHS = SWC / 16;                   // 16-column TMEM chunks per slab
+    const int q = warp & 3;
+    const int group = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int th = r / p.TW, tw = r - th * p.TW;
+    uint8_t* const sbuf = smem_gen + STAGES * STAGE_BYTES + group * (NSL * SLAB_BYTES);
+    const uint32_t sbuf_u32 = smem_base + STAGES * STAGE_BYTES + group * (NSL * SLAB_BYTES);
+    const bool issuer = q == 0 && lane == 0;
+    const int bar_id = 1 + group;
+    auto swz = [](int row) { return RB == 128 ? (row & 7) : (RB == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1)); };
+    constexpr int CP = SWC / 2, RG = 32 / CP, RPG = 32 / RG;   // statistics of one slab: column pairs x row groups
+    float sacc[NSL][4];
+#pragma unroll
+    for (int i = 0; i < NSL; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+    int stat_col0 = -1;
+    const bool row_live = r < p.TW * p.TH;
+    const uint32_t buf = (uint32_t)group;
+    uint32_t use = 0;                                // how often this group has used its accumulator
+    for (long long t = blockIdx.x + (long long)group * gridDim.x; t < p.total_tiles; t += 2LL * gridDim.x, ++use) {
+      const int tt = (int)t;
+      const int n_tile = tt % p.n_tiles;
+      const int g = (tt / p.n_tiles) % p.groups;
+      const int m_tile = tt / ng;
+      const int img = m_tile / tiles_per_img;
+      const int trem = m_tile - img * tiles_per_img;
+      const int th_i = trem / p.tiles_w;
+      const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+      const bool valid = row_live && (h0 + th < p.H) && (w0 + tw < p.W);
+      const bool keep = p.taps == 1 || valid;   // 3x3: a row outside the image still sums in-image taps: keep it out of the statistics
+      const int cbase = g * p.cout_g + n_tile * BN;            // first channel of the tile
+      stat_col0 = cbase;
+      tc::mbar_wait(tc::smem_u32(&acc_full[buf]), use & 1u);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      // (A) the group's previous store has finished READING the staging slabs
+      if (issuer) tc::tma_store_wait_read();
+      tc::bar_sync_named(bar_id, 128);
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        uint32_t v[CHS][16];
+#pragma unroll
+        for (int c = 0; c < CHS; ++c) tc::tmem_ld16(taddr + (sl * CHS + c) * 16, v[c]);
+        tc::tmem_ld_wait();
+        if (sl == NSL - 1) {
+          // every column is in registers: hand the accumulator back to the MMA warp before packing
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+        }
+        if (row_live) {
+          uint8_t* rowp = sbuf + sl * SLAB_BYTES + r * RB;
+#pragma unroll
+          for (int c = 0; c < CHS; ++c) {
+            uint4 u0, u1;
+            pack16(v[c], u0, u1);
+            if (!keep) { u0 = make_uint4(0, 0, 0, 0); u1 = u0; }
+            *reinterpret_cast<uint4*>(rowp + (((2 * c) ^ swz(r)) << 4)) = u0;
+            *reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ swz(r)) << 4)) = u1;
+          }
+        }
+      }
+      __syncwarp();
+      if (p.stats) {
+        // lane owns the column pair cp of each slab over the rows rg, rg + RG, ... of the warp's 32 rows
+        const int cp = lane % CP, rg = lane / CP;
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < RPG; ++i) {
+            const int row = q * 32 + i * RG + rg;
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(sbuf + sl * SLAB_BYTES + row * RB + ((((cp >> 2)) ^ swz(row)) << 4) + (cp & 3) * 4);
+            float a, b;
+            bf16x2_unpack(u, a, b);
+            s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+          }
+#pragma unroll
+          for (int off = 16; off >= CP; off >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, off); q1 += __shfl_xor_sync(0xffffffffu, q1, off);
+          }
+          sacc[sl][0] += s0; sacc[sl][1] += s1; sacc[sl][2] += q0; sacc[sl][3] += q1;
+        }
+      }
+      tc::fence_proxy_async();                       // generic-proxy writes of this thread -> visible to the TMA (async proxy)
+      tc::bar_sync_named(bar_id, 128);               // (B) every row of the tile is staged
+      if (issuer) {
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) tc::tma_store_4d(&tmC, sbuf_u32 + sl * SLAB_BYTES, cbase + sl * SWC, w0, h0, img);
+        tc::tma_store_commit();
+      }
+    }
+    if (issuer) tc::tma_store_wait_all();
+    if (p.stats && stat_col0 >= 0 && lane < CP) {
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        atomicAdd(p.stats + stat_col0 + sl * SWC + 2 * lane, (double)sacc[sl][0]);
+        atomicAdd(p.stats + stat_col0 + sl * SWC + 2 * lane + 1, (double)sacc[sl][1]);
+        atomicAdd(p.stats + p.stats_stride + stat_col0 + sl * SWC + 2 * lane, (double)sacc[sl][2]);
+        atomicAdd(p.stats + p.stats_stride + stat_col0 + sl * SWC + 2 * lane + 1, (double)sacc[sl][3]);
+      }
     }
   } else {
     // ---- 8 epilogue warps: TMEM lane quarter q <-> GEMM rows [32q, 32q+32); column half hsel
@@ -733,19 +857,17 @@ void pick_patch(int H, int W, int* TW, int* TH, int max_px = 128, int quantum = 
   *TW = bw; *TH = bh;
 }
 
-template <int BN, int BK, int STAGES>
-int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int grid, cudaStream_t s) {
+template <int BN, int BK, int STAGES, int EPI = 0>
+int launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvTcParams& p, int grid, cudaStream_t s) {
   constexpr int pitch = ((BN == 256 && STAGES >= 4) || (BN == 128 && STAGES >= 6)) ? 128
                                                                                     : (BN >= 32 ? BN / 2 : BN) * 2 + 16;   // see SLAB
-  constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + 8 * 32 * pitch + 1024;
+  constexpr int staging = EPI == 1 ? 2 * 128 * BN * 2 : 8 * 32 * pitch;   // EPI 1: one staged tile per epilogue group
+  constexpr int smem = STAGES * (128 * BK * 2 + BN * BK * 2) + staging + 1024;
   static_assert(smem <= 226 * 1024, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return OCT_ERR_LAUNCH;
-    attr_done = true;
-  }
-  conv_tc_kernel<BN, BK, STAGES><<<grid, kFwdThreads, smem, s>>>(tmA, tmB, p);
+  // (the attribute is per device: set on every launch, it is cheap)
+  if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return OCT_ERR_LAUNCH;
+  conv_tc_kernel<BN, BK, STAGES, EPI><<<grid, kFwdThreads, smem, s>>>(tmA, tmB, tmC, p);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -866,34 +988,43 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
   }
   if (grid > p.total_tiles) grid = stats ? ((p.total_tiles + ng - 1) / ng) * ng : p.total_tiles;
   if (stats && grid > p.total_tiles) grid = p.total_tiles;  // total_tiles is itself a multiple of ng
+  // plain outputs of <= 128-column tiles take the TMA-store epilogue (OCTAVE_TMA_EPI=0 restores the per-lane stores)
+  static const int tma_epi = [] { const char* e = getenv("OCTAVE_TMA_EPI"); return e ? atoi(e) : 1; }();
+  const bool epi1 = tma_epi && BN <= 128 && !bias && d->relu == 0 && !d->accumulate && !convt && !s2d && !p.out_f32;
+  CUtensorMap tmC = tmA;
+  if (epi1) {
+    const int swc = BN < 64 ? BN : 64;
+    const bf16* yb = reinterpret_cast<const bf16*>(y) + d->y_coff;
+    if (!make_act_map(&tmC, yb, d->cout, Wm, Hm, B, d->y_ld, swc, p.TW, p.TH, swc * 2)) return OCT_ERR_LAUNCH;
+  }
   if (BK == 64) {
     switch (BN) {
       // pipeline depth sized to ~160-190 KB in flight per SM: the persistent CTA is alone on its SM, so the ring must
       // cover the HBM bandwidth-delay product by itself, also for the small stages of narrow layers
       case 256: {
         // four 48 KB stages with the slab epilogue (see SLAB): bit-exact with the 3-stage kernel and 2.6-3.8 % faster
-        // (profiles/slab_epilogue_ab_r01.log); OCTAVE_FWD_STAGES=3 / 2 select the padded-staging kernel / the ring probe
+        // (profiles/slab_epilogue_ab_r01.log); OCTAVE_FWD_STAGES=3 selects the padded-staging kernel
         static const int st2 = [] { const char* e = getenv("OCTAVE_FWD_STAGES"); return e ? atoi(e) : 4; }();
-        if (st2 == 2) return launch_fwd<256, 64, 2>(tmA, tmB, p, (int)grid, s);
-        if (st2 == 3) return launch_fwd<256, 64, 3>(tmA, tmB, p, (int)grid, s);
-        return launch_fwd<256, 64, 4>(tmA, tmB, p, (int)grid, s);
+        if (st2 == 3) return launch_fwd<256, 64, 3>(tmA, tmB, tmC, p, (int)grid, s);
+        return launch_fwd<256, 64, 4>(tmA, tmB, tmC, p, (int)grid, s);
       }
       case 128: {
-        // opt-in, not yet measured: six stages with the slab epilogue (plain stores only)
+        if (epi1) return launch_fwd<128, 64, 5, 1>(tmA, tmB, tmC, p, (int)grid, s);   // 5 x 32 KB ring + 2 x 32 KB staged tiles
+        // six stages with the slab epilogue (plain stores only); five with the padded staging (accumulating dgrads)
         static const int st1 = [] { const char* e = getenv("OCTAVE_FWD128_STAGES"); return e ? atoi(e) : 6; }();
-        if (st1 == 6 && !p.accumulate) return launch_fwd<128, 64, 6>(tmA, tmB, p, (int)grid, s);
-        return launch_fwd<128, 64, 5>(tmA, tmB, p, (int)grid, s);
+        if (st1 == 6 && !p.accumulate) return launch_fwd<128, 64, 6>(tmA, tmB, tmC, p, (int)grid, s);
+        return launch_fwd<128, 64, 5>(tmA, tmB, tmC, p, (int)grid, s);
       }
-      case 64: return launch_fwd<64, 64, 7>(tmA, tmB, p, (int)grid, s);
-      case 32: return launch_fwd<32, 64, 9>(tmA, tmB, p, (int)grid, s);
-      default: return launch_fwd<16, 64, 10>(tmA, tmB, p, (int)grid, s);
+      case 64: return epi1 ? launch_fwd<64, 64, 7, 1>(tmA, tmB, tmC, p, (int)grid, s) : launch_fwd<64, 64, 7>(tmA, tmB, tmC, p, (int)grid, s);
+      case 32: return epi1 ? launch_fwd<32, 64, 9, 1>(tmA, tmB, tmC, p, (int)grid, s) : launch_fwd<32, 64, 9>(tmA, tmB, tmC, p, (int)grid, s);
+      default: return epi1 ? launch_fwd<16, 64, 10, 1>(tmA, tmB, tmC, p, (int)grid, s) : launch_fwd<16, 64, 10>(tmA, tmB, tmC, p, (int)grid, s);
     }
   } else {
     switch (BN) {
-      case 128: return launch_fwd<128, 32, 10>(tmA, tmB, p, (int)grid, s);
-      case 64: return launch_fwd<64, 32, 14>(tmA, tmB, p, (int)grid, s);
-      case 32: return launch_fwd<32, 32, 16>(tmA, tmB, p, (int)grid, s);
-      default: return launch_fwd<16, 32, 18>(tmA, tmB, p, (int)grid, s);
+      case 128: return epi1 ? launch_fwd<128, 32, 10, 1>(tmA, tmB, tmC, p, (int)grid, s) : launch_fwd<128, 32, 10>(tmA, tmB, tmC, p, (int)grid, s);
+      case 64: return epi1 ? launch_fwd<64, 32, 14, 1>(tmA, tmB, tmC, p, (int)grid, s) : launch_fwd<64, 32, 14>(tmA, tmB, tmC, p, (int)grid, s);
+      case 32: return epi1 ? launch_fwd<32, 32, 16, 1>(tmA, tmB, tmC, p, (int)grid, s) : launch_fwd<32, 32, 16>(tmA, tmB, tmC, p, (int)grid, s);
+      default: return epi1 ? launch_fwd<16, 32, 18, 1>(tmA, tmB, tmC, p, (int)grid, s) : launch_fwd<16, 32, 18>(tmA, tmB, tmC, p, (int)grid, s);
     }
   }
 }

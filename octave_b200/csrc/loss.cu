@@ -1448,3 +1448,90 @@ extern "C" int octave_loss_scale_grads(const OctaveLossDesc* d, const float* g_t
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
+
+// ---- the two remaining branches of WeightedPartialCE.forward (segmentor/losses.py:40-49,56-59), fp32 maps ------------------
+//   mode 0: manual=False, C == 2   nn.CrossEntropyLoss()(z, ys[:,1]) with z = y_hat * ys (y_hat when `full`) taken as logits
+//   mode 1: num_classes == 1       nn.BCEWithLogitsLoss()(z, ys), same z
+// Both are means over all B*H*W pixels (`reduction` and the class weights are ignored by the reference there).
+namespace {
+__global__ void __launch_bounds__(256) wpce_alt_fwd_kernel(const float* __restrict__ yh, const float* __restrict__ ys, int mode, int full,
+                                                           long long npix, long long plane, double* acc, float* out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npix; i += (long long)gridDim.x * 256) {
+    if (mode == 0) {
+      const long long b = i / plane, o = b * 2 * plane + (i - b * plane);
+      const float t0 = ys[o], t1 = ys[o + plane];
+      const float z0 = full ? yh[o] : yh[o] * t0, z1 = full ? yh[o + plane] : yh[o + plane] * t1;
+      const float mx = fmaxf(z0, z1);
+      const float lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+      s += lse - (t1 != 0.f ? z1 : z0);            // target class index = (long) ys[:,1]
+    } else {
+      const float t = ys[i];
+      const float z = full ? yh[i] : yh[i] * t;
+      s += fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
+    }
+  }
+  float v[1] = {s};
+  block_sum<1>(v, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc, (double)v[0]);
+    __threadfence();
+    const unsigned long long prev = atomicAdd(reinterpret_cast<unsigned long long*>(acc + 1), 1ULL);
+    if (prev == (unsigned long long)gridDim.x - 1ULL) {
+      __threadfence();
+      out[0] = (float)(*reinterpret_cast<volatile double*>(acc) / (double)npix);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) wpce_alt_bwd_kernel(const float* __restrict__ yh, const float* __restrict__ ys, int mode, int full,
+                                                           long long npix, long long plane, const float* __restrict__ gscale,
+                                                           float* __restrict__ g) {
+  const float k = gscale[0] / (float)npix;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < npix; i += (long long)gridDim.x * 256) {
+    if (mode == 0) {
+      const long long b = i / plane, o = b * 2 * plane + (i - b * plane);
+      const float t0 = ys[o], t1 = ys[o + plane];
+      const float m0 = full ? 1.f : t0, m1 = full ? 1.f : t1;
+      const float z0 = yh[o] * m0, z1 = yh[o + plane] * m1;
+      const float mx = fmaxf(z0, z1);
+      const float e0 = expf(z0 - mx), e1 = expf(z1 - mx), inv = 1.f / (e0 + e1);
+      const bool c1 = t1 != 0.f;
+      g[o] = k * m0 * (e0 * inv - (c1 ? 0.f : 1.f));
+      g[o + plane] = k * m1 * (e1 * inv - (c1 ? 1.f : 0.f));
+    } else {
+      const float t = ys[i];
+      const float m = full ? 1.f : t;
+      const float z = yh[i] * m;
+      g[i] = k * m * (1.f / (1.f + expf(-z)) - t);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int octave_wpce_alt_fwd(int32_t mode, const float* yhat, const float* ys, int32_t B, int32_t C, int32_t H, int32_t W,
+                                   int32_t full, double* scratch2, float* out, void* stream) {
+  if (!yhat || !ys || !scratch2 || !out || B <= 0 || H <= 0 || W <= 0) return OCT_ERR_INVALID;
+  if ((mode == 0 && C != 2) || (mode == 1 && C != 1) || (mode != 0 && mode != 1)) return OCT_ERR_UNSUPPORTED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(scratch2, 0, 2 * sizeof(double), s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  const long long plane = (long long)H * W, npix = plane * B;
+  long long gx = (npix + 255) / 256;
+  if (gx > 1184) gx = 1184;
+  wpce_alt_fwd_kernel<<<(int)gx, 256, 0, s>>>(yhat, ys, mode, full, npix, plane, scratch2, out);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_wpce_alt_bwd(int32_t mode, const float* yhat, const float* ys, int32_t B, int32_t C, int32_t H, int32_t W,
+                                   int32_t full, const float* gscale, float* g_yhat, void* stream) {
+  if (!yhat || !ys || !gscale || !g_yhat || B <= 0 || H <= 0 || W <= 0) return OCT_ERR_INVALID;
+  if ((mode == 0 && C != 2) || (mode == 1 && C != 1) || (mode != 0 && mode != 1)) return OCT_ERR_UNSUPPORTED;
+  const long long plane = (long long)H * W, npix = plane * B;
+  long long gx = (npix + 255) / 256;
+  if (gx > 2368) gx = 2368;
+  wpce_alt_bwd_kernel<<<(int)gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(yhat, ys, mode, full, npix, plane, gscale, g_yhat);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}

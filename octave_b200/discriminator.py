@@ -23,7 +23,12 @@ from .ops import Act, ConvSpec
 
 
 def rand_uniform(x: Optional[Tensor] = None):
-    """reference utils.py:20-22 — CPU draw; kept on the host (the caller only compares it with a constant)."""
+    """reference utils.py:20-22: one CPU uniform draw, returned `type_as(x)` (x=None raises there too).  LabelNoise below
+    calls `_rand_uniform_host()` instead so that the comparison with `prob` needs no device read-back."""
+    return _rand_uniform_host().type_as(x)
+
+
+def _rand_uniform_host() -> Tensor:
     return torch.FloatTensor(1).uniform_(0, 1)
 
 
@@ -46,7 +51,7 @@ class LabelNoise(nn.Module):
             raise NotImplementedError("octave_b200: LabelNoise mode 'label' is not constructed by DiscriminatorBlock (blocks.py:77)")
 
     def draw_flip(self) -> bool:
-        return bool(rand_uniform() < self.prob)                               # blocks.py:165-167
+        return bool(_rand_uniform_host() < self.prob)                         # blocks.py:165-167 (same CPU draw)
 
 
 class HostRandomFeed:

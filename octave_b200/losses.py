@@ -197,12 +197,39 @@ def fused_loss(cfg: _LossCfg, yhat=None, ys=None, att: Sequence[Tensor] = (), d_
 # -------------------------------------------------------------------------------------------------
 # Reference-named modules
 # -------------------------------------------------------------------------------------------------
+class _WpceAltFn(torch.autograd.Function):
+    """WeightedPartialCE's nn.CrossEntropyLoss (manual=False, C == 2) and nn.BCEWithLogitsLoss (num_classes == 1) branches."""
+
+    @staticmethod
+    def forward(ctx, mode: int, full: bool, yhat: Tensor, ys: Tensor):
+        B, Cc, H, W = yhat.shape
+        scratch = torch.empty(2, dtype=torch.float64, device=yhat.device)
+        out = torch.empty(1, dtype=torch.float32, device=yhat.device)
+        _lib.check("octave_wpce_alt_fwd", _lib.lib.octave_wpce_alt_fwd(mode, yhat.data_ptr(), ys.data_ptr(), B, Cc, H, W, int(full),
+                                                                       scratch.data_ptr(), out.data_ptr(), _stream_ptr()))
+        ctx.mode, ctx.full = mode, full
+        ctx.save_for_backward(yhat, ys)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g_out):
+        yhat, ys = ctx.saved_tensors
+        B, Cc, H, W = yhat.shape
+        g = torch.empty_like(yhat)
+        gs = g_out.reshape(1).float().contiguous()
+        _lib.check("octave_wpce_alt_bwd", _lib.lib.octave_wpce_alt_bwd(ctx.mode, yhat.data_ptr(), ys.data_ptr(), B, Cc, H, W, int(ctx.full),
+                                                                       gs.data_ptr(), g.data_ptr(), _stream_ptr()))
+        return None, None, g, None
+
+
 class WeightedPartialCE(nn.Module):
     """Weighted partial cross-entropy on scribbles (reference: segmentor/losses.py:11-61).
 
     `y_hat` holds probabilities (the reference applies log(y_hat + 1e-12) directly, losses.py:52);
-    a pixel is unlabelled when its one-hot row in `ys` is all zero.  Only the `manual=True`,
-    `num_classes > 1` branch is on OctaScribbleNet's path (models/octa.py:52) and is ported.
+    a pixel is unlabelled when its one-hot row in `ys` is all zero.  The `manual=True`, `num_classes > 1` branch is the one
+    on OctaScribbleNet's path (models/octa.py:52) and runs in the fused K9 kernel; the constructor default `manual=False`
+    (nn.CrossEntropyLoss on ys[:,1:], losses.py:40-45,58 — well-formed for two classes only, as in the reference) and
+    `num_classes == 1` (nn.BCEWithLogitsLoss, :48-49) have their own small kernels.
     """
 
     def __init__(self, num_classes, eps=1e-12, manual: bool = False):
@@ -213,14 +240,25 @@ class WeightedPartialCE(nn.Module):
 
     def forward(self, y_hat: Tensor, ys: Tensor, ignore_bg: bool = False, reduction: str = 'mean', **kwargs) -> Tensor:
         assert y_hat.shape[1] == ys.shape[1], 'Number of class mismatch.'
-        if self.num_classes == 1 or not self.manual:
-            raise NotImplementedError(
-                "octave_b200 ports the manual=True, num_classes>1 branch used by OctaScribbleNet "
-                "(reference losses.py:51-55); the nn.CrossEntropyLoss / BCE branches are out of scope")
         if reduction not in ('mean', 'sum'):
             raise ValueError(f'Unknown reduction {reduction}')
         if ignore_bg:
             ys[:, 0] = 0  # in-place on the caller's tensor, as the reference does (losses.py:29-30)
+        if self.num_classes == 1 or not self.manual:
+            _require_cuda(y_hat, "y_hat"); _require_cuda(ys, "ys")
+            if self.num_classes == 1:
+                if not self.manual:
+                    # ys[:, 1:] of a one-channel target is empty: the reference fails inside BCEWithLogitsLoss (losses.py:40,49)
+                    raise ValueError("Target size (torch.Size([0])) must be the same as input size "
+                                     f"(torch.Size([{y_hat.numel()}, 1]))")
+                mode = 1
+            else:
+                if y_hat.shape[1] != 2:
+                    # `(b h w c)` targets have (C-1) entries per pixel: nn.CrossEntropyLoss rejects them unless C == 2 (losses.py:44,58)
+                    raise ValueError(f"Expected input batch_size ({y_hat.numel() // y_hat.shape[1]}) to match target batch_size "
+                                     f"({ys[:, 1:].numel()}).")
+                mode = 0
+            return _WpceAltFn.apply(mode, bool(kwargs.get('full', False)), y_hat.contiguous().float(), ys.contiguous().float())
         flags = _lib.LOSS_WPCE
         if kwargs.get('full', False):
             flags |= _lib.LOSS_WPCE_FULL

@@ -117,12 +117,51 @@ def conv_bn_fwd(conv: Conv2d, bn: BatchNorm2d, x: Act, training: bool, relu: boo
     return y, c
 
 
+_side_streams: Dict[torch.device, "torch.cuda.Stream"] = {}
+_side_busy = False
+
+
+def _wgrad(x: Act, dz: Act, spec: ConvSpec, zero_bias_grad: bool):
+    """Weight gradient of one conv, on the side stream when config.overlap_wgrad (see config.py).  The inputs are marked as
+    used by that stream, so the caching allocator does not hand their memory out again before the kernel has run."""
+    global _side_busy
+    if not (config.overlap_wgrad and x.buf.is_cuda and spec.tc_ok(x.dtype)):
+        return ops.conv_wgrad(x, dz, spec, zero_bias_grad)
+    side = _side_streams.get(x.device)
+    if side is None:
+        side = _side_streams[x.device] = torch.cuda.Stream(device=x.device)
+    side.wait_stream(torch.cuda.current_stream())          # dz (and x) are complete on the main stream
+    with torch.cuda.stream(side):
+        out = ops.conv_wgrad(x, dz, spec, zero_bias_grad)
+    x.buf.record_stream(side)
+    dz.buf.record_stream(side)
+    _side_busy = True
+    return out
+
+
+def join_side_stream(grads: Optional[Grads] = None) -> None:
+    """The main stream waits for every weight gradient issued on the side stream; gradients allocated there are handed to
+    the main stream's allocator bookkeeping."""
+    global _side_busy
+    if not _side_busy:
+        return
+    main = torch.cuda.current_stream()
+    side = _side_streams.get(torch.device("cuda", main.device_index))
+    if side is not None:
+        main.wait_stream(side)
+        if grads is not None:
+            for g in grads.values():
+                if g is not None and g.is_cuda:
+                    g.record_stream(main)
+    _side_busy = False
+
+
 def conv_bwd(conv: nn.Module, x: Act, dz: Act, grads: Grads, need_dx: bool = True, dx_out: Optional[Act] = None,
              accumulate: bool = False, zero_bias_grad: bool = False) -> Optional[Act]:
     """zero_bias_grad: the conv feeds a training-mode BatchNorm, whose input gradient sums to zero over every channel,
     so the bias gradient is identically zero (the reference computes rounding noise there) and its reduction is skipped."""
     spec = _spec(conv)
-    dw, db = ops.conv_wgrad(x, dz, spec, zero_bias_grad)
+    dw, db = _wgrad(x, dz, spec, zero_bias_grad)
     _acc(grads, conv.weight, dw)
     _acc(grads, conv.bias, db)
     if not need_dx:
@@ -257,11 +296,6 @@ class Bottleneck(nn.Module):
             dx = dres
         conv_bwd(self.conv1, x, dz1, grads, dx_out=dx, accumulate=True)
         return dx
-
-
-class _Stem(nn.Module):
-    """conv1 of the deep stem: 3x3 s2 3->32, 3x3 32->32, 3x3 32->64 with BN+ReLU between (resnest.py:326-334)."""
-    pass
 
 
 class ResNet(nn.Module):
@@ -441,6 +475,7 @@ class _SegmentorFn(torch.autograd.Function):
             raise RuntimeError("octave_b200: backward through the segmentor twice (tape already released)")
         grads: Grads = {}
         net._bwd(ctx.tape, gouts, grads)
+        join_side_stream(grads)
         ctx.tape = None
         return (None, None, *[grads.get(p) for p in ctx.params])
 
@@ -617,6 +652,7 @@ class ResnestUNet(nn.Module):
             hook = self._grad_ready_hook
             if hook is None:
                 return
+            join_side_stream(grads)            # the announced gradients must be complete on this stream
             new = [(p, g) for p, g in grads.items() if p not in emitted]
             emitted.update(grads.keys())
             if new:
@@ -672,6 +708,7 @@ class ResnestUNet(nn.Module):
         ops.add_inplace(dx00, dcat1.slice(0, 64))
         self._stem_bwd(tape["stem"], dx00, grads)
         emit()
+        join_side_stream(grads)
 
     def _repack(self) -> None:
         """bf16 operand packs of every tensor-core conv, refreshed in one launch when the weights have changed"""
@@ -756,6 +793,7 @@ class _BlockFn(torch.autograd.Function):
         else:
             dx = block.bwd(ctx.c, to_act(gouts[0]), grads)
         gx = ops.nhwc_to_nchw(dx) if dx is not None else None
+        join_side_stream(grads)
         return (None, None, gx, *[grads.get(p) for p in ctx.params])
 
 

@@ -225,6 +225,7 @@ class _ParallelHeadNet(nn.Module):
         dx00 = _sum_into(dx00, dcat1c.slice(0, 64) if dcat1c is not None else None)
         if dx00 is not None:
             self._stem_bwd(tape["stem"], dx00, grads)
+        _n.join_side_stream(grads)
         hook = self._grad_ready_hook
         if hook is not None and grads:
             hook(list(grads.keys()), list(grads.values()))

@@ -625,21 +625,6 @@ def conv_wgrad(x: Act, dy: Act, spec: ConvSpec, zero_bias_grad: bool = False):
     return dw, db
 
 
-def conv_wgrad_direct(x: Act, dy: Act, spec: ConvSpec):
-    dw = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
-    db = torch.empty(spec.cout, dtype=torch.float32, device=x.device) if spec.bias is not None else None
-    d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, x, dy, dy.H, dy.W)
-    _chk("octave_conv_direct_wgrad", lib.octave_conv_direct_wgrad(C.byref(d), x.buf.data_ptr(), dy.buf.data_ptr(), dw.data_ptr(), _p(db), stream_ptr()))
-    return dw, db
-
-
-def conv_dgrad_direct(dy: Act, spec: ConvSpec, H: int, W: int) -> Act:
-    out = Act.empty(dy.B, H, W, spec.cin, dy.dtype, dy.device)
-    d = _conv_desc(dy.B, H, W, spec.cin, spec.cout, spec.groups, spec.k, spec.stride, spec.pad, out, dy, dy.H, dy.W)
-    _chk("octave_conv_direct_dgrad", lib.octave_conv_direct_dgrad(C.byref(d), dy.buf.data_ptr(), _f32(spec.weight).data_ptr(), out.buf.data_ptr(), stream_ptr()))
-    return out
-
-
 def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
     """Backward of ConvTranspose2d(k=2,s=2): dy (possibly cropped view [B,Ho,Wo,cout]) -> (dx, dW [Cin,Cout,2,2], dbias)."""
     # [B,H,W,4*cout], zeros where dy was cropped; the same pass yields the bias gradient sum_pixels dy

@@ -40,6 +40,24 @@ def weighted_partial_ce(y_hat: Tensor, ys: Tensor, num_classes: int, reduction: 
     return wce.mean() if reduction == "mean" else wce.sum()   # :55
 
 
+def weighted_partial_ce_torch_ce(y_hat: Tensor, ys: Tensor, full: bool = False) -> Tensor:
+    """architectures/segmentor/losses.py:26-61 with the constructor default manual=False and two classes: the masked
+    y_hat (:31-32) is fed as LOGITS to nn.CrossEntropyLoss with the class index taken from ys[:,1:] (:40-45,58); the class
+    weights of :34-38 and `reduction` are not used on this branch."""
+    assert y_hat.shape[1] == ys.shape[1] == 2
+    z = y_hat if full else y_hat * ys
+    z = z.permute(0, 2, 3, 1).reshape(-1, 2)
+    t = ys[:, 1:].permute(0, 2, 3, 1).reshape(-1).long()
+    return torch.nn.functional.cross_entropy(z, t)
+
+
+def weighted_partial_ce_bce(y_hat: Tensor, ys: Tensor, full: bool = False) -> Tensor:
+    """architectures/segmentor/losses.py:48-49 (num_classes == 1, manual=True): nn.BCEWithLogitsLoss on the masked map."""
+    assert y_hat.shape[1] == ys.shape[1] == 1
+    z = y_hat if full else y_hat * ys
+    return torch.nn.functional.binary_cross_entropy_with_logits(z.permute(0, 2, 3, 1).reshape(-1, 1), ys.permute(0, 2, 3, 1).reshape(-1, 1))
+
+
 def dice_loss(inp: Tensor, target: Tensor, eps: float = 1e-12) -> Tensor:
     """architectures/segmentor/losses.py:70-74."""
     intersect = (inp * target).sum(dim=(1, 2, 3))

@@ -301,3 +301,27 @@ def test_fused_single_pass_falls_back_for_dice():
     close(res['total'], exp, rtol=1e-4, msg="dice fallback total")
     res['total'].backward()
     assert a_d.grad is not None and torch.isfinite(a_d.grad).all()
+
+
+def test_wpce_default_manual_false_and_single_class_branches():
+    """WeightedPartialCE(num_classes) with the constructor default manual=False (nn.CrossEntropyLoss branch, two classes) and
+    num_classes == 1 (nn.BCEWithLogitsLoss): values and gradients against the oracle restatement pinned to the reference."""
+    m = L()
+    g = torch.Generator().manual_seed(3)
+    ys = (torch.rand(3, 2, 40, 56, generator=g) < 0.2).float(); ys[:, 0] *= 1 - ys[:, 1]
+    for full in (False, True):
+        a = torch.randn(3, 2, 40, 56, generator=g)
+        ao = a.clone().requires_grad_(); lo = O.weighted_partial_ce_torch_ce(ao, ys, full=full)
+        ad = a.to(DEV).requires_grad_(); ld = m.WeightedPartialCE(2)(ad, ys.to(DEV), full=full)
+        close(ld, lo, msg="manual=False")
+        grad_close(torch.autograd.grad(2.0 * ld, ad)[0], 2.0 * torch.autograd.grad(lo, ao)[0], 1e-4, "manual=False grad")
+        a1 = torch.randn(3, 1, 40, 56, generator=g); y1 = ys[:, 1:].contiguous()
+        ao = a1.clone().requires_grad_(); lo = O.weighted_partial_ce_bce(ao, y1, full=full)
+        ad = a1.to(DEV).requires_grad_(); ld = m.WeightedPartialCE(1, manual=True)(ad, y1.to(DEV), full=full)
+        close(ld, lo, msg="num_classes=1")
+        grad_close(torch.autograd.grad(ld, ad)[0], torch.autograd.grad(lo, ao)[0], 1e-4, "num_classes=1 grad")
+    ysb = ys.to(DEV)
+    m.WeightedPartialCE(2)(torch.randn(3, 2, 40, 56, device=DEV), ysb, ignore_bg=True)
+    assert float(ysb[:, 0].abs().max()) == 0.0            # in-place side effect of ignore_bg, as in the reference
+    with pytest.raises(ValueError):
+        m.WeightedPartialCE(3)(torch.rand(2, 3, 8, 8, device=DEV), torch.zeros(2, 3, 8, 8, device=DEV))

@@ -15,6 +15,25 @@ def ref():
     return refload.load()
 
 
+def test_wpce_default_and_single_class_branches_match_reference(ref):
+    """WeightedPartialCE(manual=False) (the constructor default: nn.CrossEntropyLoss branch) and num_classes == 1
+    (nn.BCEWithLogitsLoss), losses.py:40-49,56-59 — values and gradients."""
+    g = torch.Generator().manual_seed(3)
+    ys = (torch.rand(3, 2, 12, 20, generator=g) < 0.2).float(); ys[:, 0] *= 1 - ys[:, 1]
+    for full in (False, True):
+        a = torch.randn(3, 2, 12, 20, generator=g).requires_grad_(); b = a.detach().clone().requires_grad_()
+        lr = ref.WeightedPartialCE(2)(a, ys.clone(), full=full); lo = O.weighted_partial_ce_torch_ce(b, ys, full=full)
+        assert abs(lr.item() - lo.item()) < 1e-6
+        assert torch.allclose(torch.autograd.grad(lr, a)[0], torch.autograd.grad(lo, b)[0], atol=1e-7)
+        a1 = torch.randn(3, 1, 12, 20, generator=g).requires_grad_(); b1 = a1.detach().clone().requires_grad_()
+        y1 = ys[:, 1:].contiguous()
+        lr = ref.WeightedPartialCE(1, manual=True)(a1, y1.clone(), full=full); lo = O.weighted_partial_ce_bce(b1, y1, full=full)
+        assert abs(lr.item() - lo.item()) < 1e-6
+        assert torch.allclose(torch.autograd.grad(lr, a1)[0], torch.autograd.grad(lo, b1)[0], atol=1e-7)
+    with pytest.raises(Exception):
+        ref.WeightedPartialCE(3)(torch.rand(2, 3, 4, 4), torch.zeros(2, 3, 4, 4))      # only two classes are well-formed there
+
+
 def test_known_answers_reference_and_oracle(ref):
     # closed-form known answers listed in SURVEY.md §8c
     ys = torch.zeros(1, 2, 2, 2); ys[0, 0, 0, 0] = 1; ys[0, 1, 0, 1] = 1; ys[0, 1, 1, 0] = 1
