@@ -382,6 +382,25 @@ int64_t octave_optim_job_blocks(int64_t n);
 int octave_optim_multi(const OctaveOptJob* jobs_device, int32_t n_jobs, int64_t total_blocks, const OctaveOptHyper* hyper,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-GPU input pipeline.  The reference ships no data loader (README.md:39-47); the synthetic OCTA model
+ * is the one of SURVEY.md 8d.  Counter-based random numbers: a batch is a pure function of `seed`.
+ *   octave_synth_octa          x [B,3,H,W] fp32 in [0,1] (one plane replicated), ys [B,2,H,W] one-hot scribbles / all-zero,
+ *                              vessel (nullable) [B,H,W] u8 ground truth
+ *   octave_synth_mask_pyramid  out[k] = [B,2,ceil(H/2^k),ceil(W/2^k)] one-hot "real" masks (unpaired draw), k < levels
+ *   octave_augment             per-sample flips / 90-degree rotations applied to x AND ys, photometric jitter on x only;
+ *                              out-of-place (x_out != x) */
+#define OCT_AUG_FLIP_H (1 << 0)
+#define OCT_AUG_FLIP_V (1 << 1)
+#define OCT_AUG_ROT90  (1 << 2)
+#define OCT_AUG_PHOTO  (1 << 3)
+int octave_synth_octa(uint64_t seed, int32_t B, int32_t H, int32_t W, int32_t n_ridges, float* x, float* ys, uint8_t* vessel,
+                      void* stream);
+int octave_synth_mask_pyramid(uint64_t seed, int32_t B, int32_t H, int32_t W, int32_t n_ridges, int32_t levels,
+                              float* const* out /* host array of device pointers */, void* stream);
+int octave_augment(uint64_t seed, int32_t B, int32_t C, int32_t Cy, int32_t H, int32_t W, int32_t flags, const float* x,
+                   const float* ys, float* x_out, float* ys_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
