@@ -355,6 +355,11 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     ctl = None
     if world > 1:
+        # The gradient all-reduces run beside persistent one-CTA-per-SM convolution kernels: every NCCL CTA slows the SM it
+        # lands on, and a persistent kernel finishes with its slowest SM.  A few channels carry 286 MB per step easily over
+        # NVLink 5 inside the ~28 ms backward pass (user-set values win).
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        os.environ.setdefault("NCCL_MIN_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
         # control plane (barriers, max over ranks of the timings) on gloo: the NCCL communicator only ever carries the
         # gradient all-reduces, which in graph mode are replayed from the captured step
@@ -494,9 +499,16 @@ def run_gpu(args):
     if world > 1:
         sys.stdout.flush()
         dist.barrier(group=ctl)
-        if use_graph:
-            os._exit(0)          # a communicator whose collectives live in a captured graph is not torn down here
-        dist.destroy_process_group()
+        # tear-down: drop the captured graph (it holds the NCCL work of the all-reduces) before the communicator goes
+        ts._graph = None
+        ts._sout = None
+        torch.cuda.synchronize()
+        import gc
+        gc.collect()
+        try:
+            dist.destroy_process_group()
+        except Exception as e:          # pragma: no cover - never fatal for a finished benchmark
+            sys.stderr.write(f"[bench] destroy_process_group: {e!r}\n")
 
 
 def run_reference(args):

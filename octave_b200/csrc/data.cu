@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) augment_kernel(uint64_t seed, int C, int 
   const float nz = sigma * sqrtf(-2.f * __logf(u1)) * __cosf(6.2831853f * u2);
   for (int c = 0; c < C; ++c) {
     const float v = x[((size_t)b * C + c) * plane + so];
-    xo[((size_t)b * C + c) * plane + i] = fminf(fmaxf(gain * __powf(fmaxf(v, 0.f), gamma) + nz, 0.f), 1.f);
+    xo[((size_t)b * C + c) * plane + i] = (flags & OCT_AUG_PHOTO) ? fminf(fmaxf(gain * __powf(fmaxf(v, 0.f), gamma) + nz, 0.f), 1.f) : v;
   }
   for (int c = 0; c < Cy; ++c) yo[((size_t)b * Cy + c) * plane + i] = ys[((size_t)b * Cy + c) * plane + so];
 }
