@@ -200,6 +200,9 @@ def family_rooflines(ts, batch, peaks, step_ms):
             feed.draw(); feed.upload()
         ts.step(x, ys, real)
 
+    # this profile runs on rank 0 alone: no collective may be entered (the other ranks are not stepping)
+    reducer, hook = ts.reducer, ts.net.segmentor._grad_ready_hook
+    ts.reducer, ts.net.segmentor._grad_ready_hook = None, None
     profiler.enable()
     try:
         eager()
@@ -208,6 +211,7 @@ def family_rooflines(ts, batch, peaks, step_ms):
         recs = profiler.records()
     finally:
         profiler.disable()
+        ts.reducer, ts.net.segmentor._grad_ready_hook = reducer, hook
     fam = {}
 
     def add(name, bound, ms, flop=0.0, byts=0.0):

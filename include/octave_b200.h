@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OCTAVE_ABI_VERSION 2   /* 2: OctaveLossDesc.jsd_eps; extra outputs of head_bwd / bn_bwd_apply / space_to_depth */
+#define OCTAVE_ABI_VERSION 3   /* 2: OctaveLossDesc.jsd_eps; extra outputs of head_bwd / bn_bwd_apply / space_to_depth */
 int octave_abi_version(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int octave_sm_count(void);

@@ -652,7 +652,8 @@ class ResnestUNet(nn.Module):
             hook = self._grad_ready_hook
             if hook is None:
                 return
-            join_side_stream(grads)            # the announced gradients must be complete on this stream
+            # (weight gradients may still be in flight on the side stream: the reducer's stream waits for it itself, see
+            # train.GradAllReducer._flush — the main stream is not held up here)
             new = [(p, g) for p, g in grads.items() if p not in emitted]
             emitted.update(grads.keys())
             if new:

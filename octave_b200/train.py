@@ -48,6 +48,10 @@ class GradAllReducer:
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         if self._stream is not None and grads[0].is_cuda:
             self._stream.wait_stream(torch.cuda.current_stream())
+            from . import network as _n
+            side = _n._side_streams.get(grads[0].device)
+            if side is not None:
+                self._stream.wait_stream(side)       # weight gradients are produced on the side stream (config.overlap_wgrad)
             with torch.cuda.stream(self._stream):
                 flat = torch.cat([g.reshape(-1) for g in grads])
                 work = dist.all_reduce(flat, op=op, group=self.pg, async_op=True)
