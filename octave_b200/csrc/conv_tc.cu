@@ -1009,7 +1009,9 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
         return launch_fwd<256, 64, 4>(tmA, tmB, tmC, p, (int)grid, s);
       }
       case 128: {
-        if (epi1) return launch_fwd<128, 64, 5, 1>(tmA, tmB, tmC, p, (int)grid, s);   // 5 x 32 KB ring + 2 x 32 KB staged tiles
+        // short-K tiles (1x1 layers) are bound by the epilogue chain: 5 x 32 KB ring + 2 x 32 KB staged tiles; long-K tiles
+        // (3x3) hide the epilogue behind the MMAs and want the deeper ring of the slab kernel below
+        if (epi1 && p.taps * p.kchunks <= 4) return launch_fwd<128, 64, 5, 1>(tmA, tmB, tmC, p, (int)grid, s);
         // six stages with the slab epilogue (plain stores only); five with the padded staging (accumulating dgrads)
         static const int st1 = [] { const char* e = getenv("OCTAVE_FWD128_STAGES"); return e ? atoi(e) : 6; }();
         if (st1 == 6 && !p.accumulate) return launch_fwd<128, 64, 6>(tmA, tmB, tmC, p, (int)grid, s);

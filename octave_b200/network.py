@@ -121,22 +121,28 @@ _side_streams: Dict[torch.device, "torch.cuda.Stream"] = {}
 _side_busy = False
 
 
-def _wgrad(x: Act, dz: Act, spec: ConvSpec, zero_bias_grad: bool):
-    """Weight gradient of one conv, on the side stream when config.overlap_wgrad (see config.py).  The inputs are marked as
-    used by that stream, so the caching allocator does not hand their memory out again before the kernel has run."""
+def on_side_stream(fn, *acts: Act):
+    """Run fn() on the side stream after the main stream's work so far; `acts` are the buffers it reads (marked as used by
+    that stream, so the caching allocator does not hand their memory out again before the kernels have run)."""
     global _side_busy
-    if not (config.overlap_wgrad and x.buf.is_cuda and spec.tc_ok(x.dtype)):
-        return ops.conv_wgrad(x, dz, spec, zero_bias_grad)
-    side = _side_streams.get(x.device)
+    dev = acts[0].buf.device if acts else torch.device("cuda", torch.cuda.current_device())
+    side = _side_streams.get(dev)
     if side is None:
-        side = _side_streams[x.device] = torch.cuda.Stream(device=x.device)
-    side.wait_stream(torch.cuda.current_stream())          # dz (and x) are complete on the main stream
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        out = ops.conv_wgrad(x, dz, spec, zero_bias_grad)
-    x.buf.record_stream(side)
-    dz.buf.record_stream(side)
+        out = fn()
+    for a in acts:
+        a.buf.record_stream(side)
     _side_busy = True
     return out
+
+
+def _wgrad(x: Act, dz: Act, spec: ConvSpec, zero_bias_grad: bool):
+    """Weight gradient of one conv, on the side stream when config.overlap_wgrad (see config.py)."""
+    if not (config.overlap_wgrad and x.buf.is_cuda and spec.tc_ok(x.dtype)):
+        return ops.conv_wgrad(x, dz, spec, zero_bias_grad)
+    return on_side_stream(lambda: ops.conv_wgrad(x, dz, spec, zero_bias_grad), x, dz)
 
 
 def join_side_stream(grads: Optional[Grads] = None) -> None:
@@ -422,7 +428,8 @@ class Upsampling(nn.Module):
 
     def bwd(self, ctx, dy: Act, grads: Grads) -> Act:
         (x,) = ctx
-        dx, dw, db = ops.convt_bwd(x, dy, _spec(self.up))
+        side = on_side_stream if (config.overlap_wgrad and x.buf.is_cuda and _spec(self.up).tc_ok(x.dtype)) else None
+        dx, dw, db = ops.convt_bwd(x, dy, _spec(self.up), side=side)
         _acc(grads, self.up.weight, dw); _acc(grads, self.up.bias, db)
         return dx
 

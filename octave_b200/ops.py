@@ -625,8 +625,9 @@ def conv_wgrad(x: Act, dy: Act, spec: ConvSpec, zero_bias_grad: bool = False):
     return dw, db
 
 
-def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
-    """Backward of ConvTranspose2d(k=2,s=2): dy (possibly cropped view [B,Ho,Wo,cout]) -> (dx, dW [Cin,Cout,2,2], dbias)."""
+def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True, side=None):
+    """Backward of ConvTranspose2d(k=2,s=2): dy (possibly cropped view [B,Ho,Wo,cout]) -> (dx, dW [Cin,Cout,2,2], dbias).
+    side: optional `run(fn, *acts)` that launches the weight gradient on another stream (network.on_side_stream)."""
     # [B,H,W,4*cout], zeros where dy was cropped; the same pass yields the bias gradient sum_pixels dy
     dys, dy_sum = space_to_depth(dy, x.H, x.W, want_chan_sum=spec.bias is not None) if spec.bias is not None else (space_to_depth(dy, x.H, x.W), None)
     if not spec.tc_ok(x.dtype):
@@ -643,9 +644,13 @@ def convt_bwd(x: Act, dy: Act, spec: ConvSpec, need_dx: bool = True):
             _chk("octave_conv_direct_dgrad", lib.octave_conv_direct_dgrad(C.byref(_conv_desc(x.B, x.H, x.W, spec.cin, 4 * spec.cout, 1, 1, 1, 0, dx, dys, x.H, x.W)),
                                                                           dys.buf.data_ptr(), w4.data_ptr(), dx.buf.data_ptr(), stream_ptr()))
         return dx, dw, db
-    dw = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
-    d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, 1, 1, 1, 0, x, dys, x.H, x.W, mode=_lib.CONV_MODE_CONVT)
-    _chk("octave_conv_tc_wgrad(convT)", lib.octave_conv_tc_wgrad(C.byref(d), x.buf.data_ptr(), dys.buf.data_ptr(), dw.data_ptr(), stream_ptr()))
+    def wgrad():
+        dw_ = torch.empty(spec.weight.shape, dtype=torch.float32, device=x.device)
+        d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, 1, 1, 1, 0, x, dys, x.H, x.W, mode=_lib.CONV_MODE_CONVT)
+        _chk("octave_conv_tc_wgrad(convT)", lib.octave_conv_tc_wgrad(C.byref(d), x.buf.data_ptr(), dys.buf.data_ptr(), dw_.data_ptr(), stream_ptr()))
+        return dw_
+
+    dw = side(wgrad, x, dys) if side is not None else wgrad()
     db = dy_sum.float() if spec.bias is not None else None
     dx = None
     if need_dx:

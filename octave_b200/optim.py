@@ -112,6 +112,9 @@ class _MultiTensorOptimizer:
             self._sig, self._n, self._blocks = sig, len(jobs), start
         h = self._hyper(self.steps == 0)
         _lib.check("octave_optim_multi", lib.octave_optim_multi(self._table.data_ptr(), self._n, self._blocks, C.byref(h), _stream_ptr()))
+        # the kernel wrote the parameters behind torch's back: bump their version counters, which is what invalidates the
+        # cached bf16 operand packs (ops.ConvSpec) and folded inference weights
+        torch.autograd.graph.increment_version([p for _, p in live])
         self.steps += 1
 
     # state interchange with torch.optim ---------------------------------------------------------------------------------

@@ -176,7 +176,10 @@ class TrainStep:
             for p in self.dis_params:
                 p.requires_grad_(flag)
 
-    def g_step(self, x: Tensor, ys: Tensor) -> Dict[str, Tensor]:
+    def g_step(self, x: Tensor, ys: Tensor, defer_join: bool = False) -> Dict[str, Tensor]:
+        """defer_join (used by step()): the segmentor's optimiser step and the re-pack of its bf16 conv operands are left
+        running on the side stream, beside the D-step that follows (which touches neither the segmentor's weights nor its
+        gradients); step() joins before it returns."""
         net = self.net
         self.opt_g.zero_grad(set_to_none=True)
         self._set_d_grad(False)
@@ -188,11 +191,22 @@ class TrainStep:
         total.backward()
         if self.reducer is not None:
             self.reducer.finish()
-        self.opt_g.step()
+        from . import config, network
+        if config.overlap_wgrad and total.is_cuda and config.compute_dtype == "bf16":
+            network.on_side_stream(self._update_segmentor)
+            if not defer_join:
+                network.join_side_stream()
+        else:
+            self._update_segmentor()
         self._set_d_grad(True)
         res['total'] = total.detach()
         res['attentions'] = att
         return res
+
+    def _update_segmentor(self) -> None:
+        self.opt_g.step()
+        if hasattr(self.net.segmentor, "_repack"):
+            self.net.segmentor._repack()         # bf16 operand packs of the updated conv weights (one launch)
 
     def d_step(self, real: Sequence[Tensor], fake: Sequence[Tensor]) -> Tensor:
         net = self.net
@@ -206,9 +220,11 @@ class TrainStep:
         return loss.detach()
 
     def step(self, x: Tensor, ys: Tensor, real: Optional[Sequence[Tensor]] = None) -> Dict[str, Tensor]:
-        res = self.g_step(x, ys)
+        res = self.g_step(x, ys, defer_join=True)
         if self.has_d and real is not None:
             res['discriminator'] = self.d_step(real, res['attentions'])
+        from . import network
+        network.join_side_stream()
         return res
 
     # ---- whole step as one CUDA graph ---------------------------------------------------------------------------

@@ -56,3 +56,11 @@ def test_train_step_uses_one_optimizer_launch_per_module():
     g = net.segmentor.fc.weight.grad
     torch.testing.assert_close(net.segmentor.fc.weight.detach(), w0 - 1e-2 * g, rtol=1e-6, atol=1e-8)
     assert torch.isfinite(res['total'])
+    # the update invalidates the cached bf16 operand packs: the next forward must run on the NEW weights
+    from octave_b200 import ops
+    conv = net.segmentor.decoder_2.conv[0]
+    v0 = conv.weight._version
+    ts.step(x.cuda(), ys.cuda(), real)
+    assert conv.weight._version > v0
+    fresh = ops.ConvSpec(conv.weight.detach().clone(), None, conv.in_channels, conv.out_channels, 3, 1, 1, 1).pack(ops._lib_pack.FWD)
+    assert torch.equal(conv._oct_spec.pack(ops._lib_pack.FWD), fresh)
