@@ -359,11 +359,9 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     ctl = None
     if world > 1:
-        # The gradient all-reduces run beside persistent one-CTA-per-SM convolution kernels: every NCCL CTA slows the SM it
-        # lands on, and a persistent kernel finishes with its slowest SM.  A few channels carry 286 MB per step easily over
-        # NVLink 5 inside the ~28 ms backward pass (user-set values win).
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
-        os.environ.setdefault("NCCL_MIN_CTAS", "4")
+        # optional cap of the CTAs NCCL may use per collective (they share SMs with the persistent convolution kernels)
+        if args.nccl_max_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))
         dist.init_process_group("nccl", device_id=dev)
         # control plane (barriers, max over ranks of the timings) on gloo: the NCCL communicator only ever carries the
         # gradient all-reduces, which in graph mode are replayed from the captured step
@@ -375,7 +373,7 @@ def run_gpu(args):
     config.nan_check = False
     torch.manual_seed(0)
     net = OctaScribbleNet(torch.Size((B, 3, H, W)), torch.Size((B, 2, H, W)), True, False).to(dev).train()
-    ts = TrainStep(net, distributed=world > 1)
+    ts = TrainStep(net, distributed=world > 1, bucket_bytes=args.bucket_mb << 20)
     # synthetic batches in pinned host memory (different data per rank = weak scaling)
     nb = 2
     host = []
@@ -552,6 +550,9 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: cap the number of timed steps so that the run fits this many seconds (0 = no cap)")
     ap.add_argument("--comparator", action="store_true", help="also time the reference arithmetic on stock torch CUDA ops (cuDNN) on this GPU")
+    ap.add_argument("--bucket-mb", type=int, default=25, help="gradient all-reduce bucket size (data-parallel runs)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="cap of NCCL CTAs per collective (0 = NCCL default; measured at N=2: "
+                    "default 47.2 ms/step, cap 8 48.0, one unbucketed all-reduce 48.0 - profiles/ddp_ab_r02.log)")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~1100 kernels of a step eagerly instead of replaying one CUDA graph")
     a = ap.parse_args()
     if a.impl == "reference":
