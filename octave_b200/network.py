@@ -133,9 +133,25 @@ def on_side_stream(fn, *acts: Act):
     with torch.cuda.stream(side):
         out = fn()
     for a in acts:
-        a.buf.record_stream(side)
+        (a.buf if isinstance(a, Act) else a).record_stream(side)
     _side_busy = True
     return out
+
+
+def adopt_from_side(*items) -> None:
+    """The main stream waits for the side stream and takes over tensors / Acts that were allocated there."""
+    join_side_stream()
+    main = torch.cuda.current_stream()
+    for a in items:
+        if a is None:
+            continue
+        t = a.buf if isinstance(a, Act) else a
+        if torch.is_tensor(t) and t.is_cuda:
+            t.record_stream(main)
+
+
+def _overlap(x: Act) -> bool:
+    return bool(config.overlap_wgrad and x.buf.is_cuda and x.dtype == torch.bfloat16)
 
 
 def _wgrad(x: Act, dz: Act, spec: ConvSpec, zero_bias_grad: bool):
@@ -217,12 +233,13 @@ class SplAtConv2d(nn.Module):
         datt = ops.splat_bwd_reduce(dout, mask, U)
         dlogits = ops.rsoftmax_bwd(datt, att, self.radix)
         w2 = self.fc2.weight.detach().reshape(self.fc2.out_channels, -1)
-        dh1n, dw2, db2 = ops.glinear_bwd(dlogits, h1n, w2, card, 1.0)
+        side = on_side_stream if _overlap(x) else None
+        dh1n, dw2, db2 = ops.glinear_bwd(dlogits, h1n, w2, card, 1.0, side=side)
         _acc(grads, self.fc2.weight, dw2); _acc(grads, self.fc2.bias, db2)
         dh1, dg1, dbt1 = ops.bn1d_relu_bwd(dh1n, h1, h1n, self.bn1.weight.detach(), mi1, tr)
         _acc(grads, self.bn1.weight, dg1); _acc(grads, self.bn1.bias, dbt1)
         w1 = self.fc1.weight.detach().reshape(self.fc1.out_channels, -1)
-        dgap, dw1, db1 = ops.glinear_bwd(dh1, gap, w1, card, 1.0 / hw)
+        dgap, dw1, db1 = ops.glinear_bwd(dh1, gap, w1, card, 1.0 / hw, side=side)
         _acc(grads, self.fc1.weight, dw1); _acc(grads, self.fc1.bias, db1)
         bn0, z0, mi0, ab0, tr0, _relu_self, _u = bn0ctx
         if dout.C // 8 <= 256:
@@ -260,8 +277,22 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
+    def _downsample_fwd(self, x: Act, tr: bool):
+        pool, convd, bnd = self.downsample[0], self.downsample[1], self.downsample[2]
+        pd = ops.pool_desc("avg", pool.kernel_size, pool.stride, 0, True, False)
+        r = x
+        if pool.kernel_size != 1:
+            r, _ = ops.pool_fwd(pd, x)
+        res, cbd = conv_bn_fwd(convd, bnd, r, tr, False)
+        return res, (pd, r, cbd)
+
     def fwd(self, x: Act, out: Optional[Act] = None):
         tr = self.training
+        cd, side = None, False
+        if self.downsample is not None and _overlap(x) and not _fold_active:
+            # avg-pool -> 1x1 conv -> BN shortcut: independent of the main branch, runs beside it on the side stream
+            res, cd = on_side_stream(lambda: self._downsample_fwd(x, tr), x)
+            side = True
         y1, c1 = conv_bn_fwd(self.conv1, self.bn1, x, tr, True)
         s, c2 = self.conv2.fwd(y1, relu_out=False)
         if self.avd:
@@ -269,15 +300,11 @@ class Bottleneck(nn.Module):
         else:
             sp = s
         z3, s3 = ops.conv_fwd(sp, _spec(self.conv3), want_stats=tr)
-        cd = None
-        if self.downsample is not None:
-            pool, convd, bnd = self.downsample[0], self.downsample[1], self.downsample[2]
-            pd = ops.pool_desc("avg", pool.kernel_size, pool.stride, 0, True, False)
-            r = x
-            if pool.kernel_size != 1:
-                r, _ = ops.pool_fwd(pd, x)
-            res, cbd = conv_bn_fwd(convd, bnd, r, tr, False)
-            cd = (pd, r, cbd)
+        if side:
+            pd_, r_, cbd_ = cd
+            adopt_from_side(res, r_, *( [cbd_[1], cbd_[3], cbd_[2], cbd_[6]] if cbd_ is not None else [] ))
+        elif self.downsample is not None:
+            res, cd = self._downsample_fwd(x, tr)
         else:
             res = x
         y, c3, _ = bn_fwd(self.bn3, z3, tr, True, res=res, out=out, sums=s3)
@@ -398,9 +425,15 @@ class ResNestDecoder(nn.Module):
 
     def fwd(self, x: Act, out: Optional[Act] = None):
         tr = self.training
-        zr, sr = ops.conv_fwd(x, _spec(self.downsample[0]), want_stats=tr)
+        # the 1x1 shortcut conv is independent of the 3x3 -> split-attention chain: it runs beside it on the side stream
+        if _overlap(x):
+            zr, sr = on_side_stream(lambda: ops.conv_fwd(x, _spec(self.downsample[0]), want_stats=tr), x)
+        else:
+            zr, sr = ops.conv_fwd(x, _spec(self.downsample[0]), want_stats=tr)
         y0, c0 = conv_bn_fwd(self.conv[0], self.conv[1], x, tr, True)
         s, cs = self.conv[3].fwd(y0, relu_out=True)
+        if _overlap(x):
+            adopt_from_side(zr, sr)
         y, cr, _ = bn_fwd(self.downsample[1], zr, tr, True, res=s, out=out, sums=sr)   # relu(BN(shortcut) + relu(splat))
         return y, (x, y0, c0, cs, s, cr, y)
 

@@ -268,15 +268,21 @@ def glinear_fwd(inp: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
-def glinear_bwd(dout: torch.Tensor, inp: torch.Tensor, w: torch.Tensor, groups: int, in_scale: float):
-    """-> din, dw (same shape as w), dbias"""
+def glinear_bwd(dout: torch.Tensor, inp: torch.Tensor, w: torch.Tensor, groups: int, in_scale: float, side=None):
+    """-> din, dw (same shape as w), dbias.  side: optional `run(fn, *tensors)` that launches the parameter-gradient kernel on
+    another stream (network.on_side_stream): only din is on the critical path of the backward pass."""
     B, Kt = inp.shape
     N = w.shape[0]
     din = torch.empty_like(inp)
     _chk("octave_glinear_bwd_data", lib.octave_glinear_bwd_data(dout.data_ptr(), w.data_ptr(), B, Kt, N, groups, in_scale, din.data_ptr(), stream_ptr()))
-    dw = torch.empty_like(w)
-    db = torch.empty(N, dtype=torch.float32, device=inp.device)
-    _chk("octave_glinear_bwd_weight", lib.octave_glinear_bwd_weight(dout.data_ptr(), inp.data_ptr(), B, Kt, N, groups, in_scale, dw.data_ptr(), db.data_ptr(), stream_ptr()))
+
+    def weight_part():
+        dw_ = torch.empty_like(w)
+        db_ = torch.empty(N, dtype=torch.float32, device=inp.device)
+        _chk("octave_glinear_bwd_weight", lib.octave_glinear_bwd_weight(dout.data_ptr(), inp.data_ptr(), B, Kt, N, groups, in_scale, dw_.data_ptr(), db_.data_ptr(), stream_ptr()))
+        return dw_, db_
+
+    dw, db = side(weight_part, dout, inp) if side is not None else weight_part()
     return din, dw, db
 
 
