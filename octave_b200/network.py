@@ -125,7 +125,7 @@ def on_side_stream(fn, *acts: Act):
     """Run fn() on the side stream after the main stream's work so far; `acts` are the buffers it reads (marked as used by
     that stream, so the caching allocator does not hand their memory out again before the kernels have run)."""
     global _side_busy
-    dev = acts[0].buf.device if acts else torch.device("cuda", torch.cuda.current_device())
+    dev = (acts[0].buf if isinstance(acts[0], Act) else acts[0]).device if acts else torch.device("cuda", torch.cuda.current_device())
     side = _side_streams.get(dev)
     if side is None:
         side = _side_streams[dev] = torch.cuda.Stream(device=dev)
