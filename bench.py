@@ -200,9 +200,11 @@ def family_rooflines(ts, batch, peaks, step_ms):
             feed.draw(); feed.upload()
         ts.step(x, ys, real)
 
-    # this profile runs on rank 0 alone: no collective may be entered (the other ranks are not stepping)
-    reducer, hook = ts.reducer, ts.net.segmentor._grad_ready_hook
-    ts.reducer, ts.net.segmentor._grad_ready_hook = None, None
+    # this profile runs on rank 0 alone: no collective may be entered (the other ranks are not stepping); and every kernel
+    # runs alone on one stream (config.overlap_wgrad off), so that an event pair brackets exactly one kernel's execution
+    from octave_b200 import config as _cfg
+    reducer, hook, ov = ts.reducer, ts.net.segmentor._grad_ready_hook, _cfg.overlap_wgrad
+    ts.reducer, ts.net.segmentor._grad_ready_hook, _cfg.overlap_wgrad = None, None, False
     profiler.enable()
     try:
         eager()
@@ -211,7 +213,7 @@ def family_rooflines(ts, batch, peaks, step_ms):
         recs = profiler.records()
     finally:
         profiler.disable()
-        ts.reducer, ts.net.segmentor._grad_ready_hook = reducer, hook
+        ts.reducer, ts.net.segmentor._grad_ready_hook, _cfg.overlap_wgrad = reducer, hook, ov
     fam = {}
 
     def add(name, bound, ms, flop=0.0, byts=0.0):
