@@ -318,7 +318,7 @@ def loss_rooflines(peaks, B, H, W):
         flags = _lib.LOSS_WPCE | _lib.LOSS_KLD | _lib.LOSS_FROM_LOGITS | (_lib.LOSS_LSG if with_lsg else 0)
         cfg = losses._LossCfg(flags, att_weights=[1.0] * 4, sum_weights=4.0)
         desc = losses._build_desc(cfg, sets[0][0], sets[0][2], None, fake)
-        stats = torch.empty(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        stats = torch.zeros(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)   # zero on entry, left zero by every evaluation
         outv = torch.empty(8, device=dev)
         lam = (C.c_float * 3)(1.0, 0.1, 0.1)
         sp = torch.cuda.current_stream().cuda_stream

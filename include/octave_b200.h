@@ -114,6 +114,8 @@ int octave_wpce_alt_bwd(int32_t mode, const float* yhat, const float* ys, int32_
  * att[k] and d_fake are written in the same pass (a labels-only pre-pass supplies the class counts of losses.py:34-38),
  * out[0..5] as octave_loss_fwd, out[6] = total.  Supported: C == 2 pyramids (octave_loss_fused_supported), flags within
  * WPCE | KLD | LSG | FROM_LOGITS | WPCE_FULL.  Reductions are in a fixed order (bit-reproducible).
+ * `stats` (octave_loss_fused_stats_bytes) must be ZERO before the first call; every evaluation leaves it zero again, so
+ * consecutive evaluations need no memset between them (one workspace per stream).
  * octave_loss_scale_grads multiplies the written gradients by *g_total (device) and is a no-op when it is 1. */
 int octave_loss_fused_supported(const OctaveLossDesc* d);
 size_t octave_loss_fused_stats_bytes(const OctaveLossDesc* d);

@@ -153,6 +153,7 @@ template <> struct Raw8<bf16> {
   uint4 r;
   __device__ __forceinline__ void ld(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
   __device__ __forceinline__ void zero() { r = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ bool any_nonzero() const { return ((r.x | r.y | r.z | r.w) & 0x7fff7fffu) != 0u; }   // +-0 excluded
   __device__ __forceinline__ void get(float* v) const {
     bf16x2_unpack(r.x, v[0], v[1]); bf16x2_unpack(r.y, v[2], v[3]);
     bf16x2_unpack(r.z, v[4], v[5]); bf16x2_unpack(r.w, v[6], v[7]);
@@ -165,6 +166,10 @@ template <> struct Raw8<float> {
     b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   }
   __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ bool any_nonzero() const {
+    return ((__float_as_uint(a.x) | __float_as_uint(a.y) | __float_as_uint(a.z) | __float_as_uint(a.w) | __float_as_uint(b.x) |
+             __float_as_uint(b.y) | __float_as_uint(b.z) | __float_as_uint(b.w)) & 0x7fffffffu) != 0u;
+  }
   __device__ __forceinline__ void get(float* v) const {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }

@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(256) loss_label_count_kernel(const T* __restri
                                                               double* stats) {
   __shared__ float red[2 * 8];
   float n[2] = {0.f, 0.f};
-  constexpr int U = 4;
+  constexpr int U = 8;
   for (long long g0 = (long long)blockIdx.x * 256 * U + threadIdx.x; g0 < groups; g0 += (long long)gridDim.x * 256 * U) {
     Raw8<T> r[U];
 #pragma unroll
@@ -723,47 +723,61 @@ __device__ __forceinline__ void plane_issue(const LossArgs& a, const PlaneGeo& g
   if (PYR || g.use[3]) r.q4.ld(reinterpret_cast<const T*>(a.att[4]) + r.off[4]);
 }
 
+// single-instruction base-2 logarithm / reciprocal: every argument here is >= 1e-12 (eps is added first), far above the
+// denormal range whose handling makes __log2f four instructions
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // values (sum into ksum) and gradients of one plane unit: the arithmetic of loss_bwd_cell term by term, except that the
-// logarithms stay in base 2 until one multiplication by ln 2 per pixel, and b/(b + 1e-12) is taken as exactly 1 where
-// fp32 rounds b + 1e-12 to b (b > 2e-5; a warp-uniform test keeps the general path for the rest)
+// logarithms stay in base 2 until one multiplication by ln 2 per pixel, the four coarse-level logarithms are summed once per
+// pixel PAIR (levels >= 1 are constant over a pair), the arguments w*q + eps are computed once for the logarithm and the
+// gradient, and b/(b + 1e-12) is taken as exactly 1 where fp32 rounds b + 1e-12 to b (b > 2e-5; warp-uniform test)
 template <typename T, bool PYR>
 __device__ __forceinline__ void plane_finish(const LossArgs& a, const PlaneGeo& g, int lane, const PlaneRaw<T>& r, float gk, float& ksum) {
   constexpr float kLn2 = 0.6931471805599453f;
   const int row = lane >> 1;
-  float b[8], m[8], q1[4], q2[2], q3, q4;
+  float b[8], q1[4], q2[2], q3 = 1.f, q4 = 1.f;   // q*: w*q + eps of each level (1 -> log 0 for an absent level)
   r.b.get(b);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = 0.f;
+  for (int j = 0; j < 4; ++j) q1[j] = 1.f;
+  q2[0] = q2[1] = 1.f;
   if (PYR || g.use[0]) {
     const float w = a.aw8[0];
     r.q1.get(q1);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float l = __log2f(w * q1[j] + kEps);
-      m[2 * j] += l; m[2 * j + 1] += l;
-    }
+    for (int j = 0; j < 4; ++j) q1[j] = w * q1[j] + kEps;
   }
   if (PYR || g.use[1]) {
     const float w = a.aw8[1];
     r.q2.get(q2);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float l = __log2f(w * q2[j] + kEps);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) m[4 * j + i] += l;
-    }
+    for (int j = 0; j < 2; ++j) q2[j] = w * q2[j] + kEps;
   }
   if (PYR || g.use[2]) {
     r.q3.get(&q3);
-    const float l = __log2f(a.aw8[2] * q3 + kEps);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] += l;
+    q3 = a.aw8[2] * q3 + kEps;
   }
   if (PYR || g.use[3]) {
     r.q4.get(&q4);
-    const float l = __log2f(a.aw8[3] * q4 + kEps);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] += l;
+    q4 = a.aw8[3] * q4 + kEps;
+  }
+  // m2[p] = (sum over the levels of log2(w_k q_k + eps)) / sum_w for the pixel pair p (levels >= 1 are constant over a pair)
+  float m2[4];
+  {
+    const float s34 = lg2_fast(q3) + lg2_fast(q4);
+    const float s2a = lg2_fast(q2[0]) + s34, s2b = lg2_fast(q2[1]) + s34;
+    m2[0] = (lg2_fast(q1[0]) + s2a) * a.inv_sumw;
+    m2[1] = (lg2_fast(q1[1]) + s2a) * a.inv_sumw;
+    m2[2] = (lg2_fast(q1[2]) + s2b) * a.inv_sumw;
+    m2[3] = (lg2_fast(q1[3]) + s2b) * a.inv_sumw;
   }
   {
     float gb[8];
@@ -771,14 +785,15 @@ __device__ __forceinline__ void plane_finish(const LossArgs& a, const PlaneGeo& 
 #pragma unroll
     for (int j = 1; j < 8; ++j) bmin = fminf(bmin, b[j]);
     const bool unit_ratio = __all_sync(0xffffffffu, bmin > 2e-5f);
+    const float gkl = gk * kLn2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      // d/db [ b (log(b+eps) - m) ] = log(b+eps) - m + b/(b+eps)
-      const float d = kLn2 * (__log2f(b[j] + kEps) - m[j] * a.inv_sumw);
-      ks += b[j] * d;
-      gb[j] = gk * (d + (unit_ratio ? 1.f : __fdividef(b[j], b[j] + kEps)));
+      // d/db [ b (log(b+eps) - m) ] = log(b+eps) - m + b/(b+eps);  t = the bracket in base 2
+      const float t = lg2_fast(b[j] + kEps) - m2[j >> 1];
+      ks += b[j] * t;
+      gb[j] = unit_ratio ? fmaf(gkl, t, gk) : fmaf(gkl, t, gk * b[j] * rcp_fast(b[j] + kEps));
     }
-    ksum += ks;
+    ksum += kLn2 * ks;
     VecIO<T, 8>::st(reinterpret_cast<T*>(a.g_att[0]) + r.off[0], gb);
   }
   // box sums of the basis over 2^k x 2^k blocks; d/dq_k = -gk/sum_w * w_k/(w_k q + eps) * boxsum(b)
@@ -799,34 +814,32 @@ __device__ __forceinline__ void plane_finish(const LossArgs& a, const PlaneGeo& 
   v4 = v3 + __shfl_xor_sync(0xffffffffu, v3, 1);
   v4 += __shfl_xor_sync(0xffffffffu, v4, 16);
   if ((PYR || a.n_att > 1) && (row & 1) == 0) {
-    const float w = a.aw8[0];
+    const float kw = kq * a.aw8[0];
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = (PYR || g.use[0]) ? __fdividef(kq * w * v1[j], w * q1[j] + kEps) : 0.f;
+    for (int j = 0; j < 4; ++j) o[j] = (PYR || g.use[0]) ? kw * v1[j] * rcp_fast(q1[j]) : 0.f;
     VecIO<T, 4>::st(reinterpret_cast<T*>(a.g_att[1]) + r.off[1], o);
   }
   if ((PYR || a.n_att > 2) && (row & 3) == 0) {
-    const float w = a.aw8[1];
+    const float kw = kq * a.aw8[1];
     float o[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) o[j] = (PYR || g.use[1]) ? __fdividef(kq * w * v2[j], w * q2[j] + kEps) : 0.f;
+    for (int j = 0; j < 2; ++j) o[j] = (PYR || g.use[1]) ? kw * v2[j] * rcp_fast(q2[j]) : 0.f;
     VecIO<T, 2>::st(reinterpret_cast<T*>(a.g_att[2]) + r.off[2], o);
   }
   if ((PYR || a.n_att > 3) && (row & 7) == 0) {
-    const float w = a.aw8[2];
-    float o = (PYR || g.use[2]) ? __fdividef(kq * w * v3, w * q3 + kEps) : 0.f;
+    float o = (PYR || g.use[2]) ? kq * a.aw8[2] * v3 * rcp_fast(q3) : 0.f;
     VecIO<T, 1>::st(reinterpret_cast<T*>(a.g_att[3]) + r.off[3], &o);
   }
   if ((PYR || a.n_att > 4) && lane == 0) {
-    const float w = a.aw8[3];
-    float o = (PYR || g.use[3]) ? __fdividef(kq * w * v4, w * q4 + kEps) : 0.f;
+    float o = (PYR || g.use[3]) ? kq * a.aw8[3] * v4 * rcp_fast(q4) : 0.f;
     VecIO<T, 1>::st(reinterpret_cast<T*>(a.g_att[4]) + r.off[4], &o);
   }
 }
 
 // COOP (cooperative launch, every block resident): the labels-only count runs as phase 0 of this very kernel — each block
-// counts a slice of ys, one grid-wide barrier, then the fused pass re-reads ys largely from L2 — instead of a separate
-// pre-pass launch.
+// counts a slice of ys and publishes it, does its KLD units, and only then (when every block's count has long arrived)
+// the WPCE part, which re-reads ys largely from L2 — instead of a separate pre-pass launch.
 template <typename T, bool PYR, bool COOP>
 __global__ void __launch_bounds__(256, 4) loss_fused_kernel(const LossArgs a, const PlaneGeo g) {
   __shared__ float red[3 * 8];
@@ -855,10 +868,37 @@ __global__ void __launch_bounds__(256, 4) loss_fused_kernel(const LossArgs a, co
         atomic_add_f64(a.stats + ST_N + 1, n[1]);
       }
     }
-    __threadfence();
-    cooperative_groups::this_grid().sync();
+    // publish this block's counts: the WPCE part below waits until every block has done so.  The KLD part runs in between,
+    // so in practice nobody waits (all blocks are resident: cooperative launch), and the count costs no separate launch.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(reinterpret_cast<unsigned long long*>(a.stats + ST_COUNTER + 1), 1ULL);
+    }
+  }
+  if (a.flags & OCT_LOSS_KLD) {
+    const float gk = a.lam_kld / ((float)a.B * (float)a.H * (float)a.W);
+    const unsigned stride = gridDim.x * 8u;
+    // blocks are walked in reverse here: the ones that drew an extra WPCE round above draw one KLD round less
+    unsigned u = (gridDim.x - 1 - blockIdx.x) * 8u + warp;
+    PlaneRaw<T> nxt;
+    if (u < g.units) plane_issue<T, PYR>(a, g, u, lane, nxt);
+    while (u < g.units) {
+      const PlaneRaw<T> cur = nxt;
+      u += stride;
+      if (u < g.units) plane_issue<T, PYR>(a, g, u, lane, nxt);   // next unit's loads fly while this one is computed
+      plane_finish<T, PYR>(a, g, lane, cur, gk, acc[2]);
+    }
   }
 
+  if (COOP && (a.flags & OCT_LOSS_WPCE)) {
+    if (threadIdx.x == 0) {
+      volatile unsigned long long* c = reinterpret_cast<volatile unsigned long long*>(a.stats + ST_COUNTER + 1);
+      while (*c < (unsigned long long)gridDim.x) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+  }
   if (a.flags & OCT_LOSS_WPCE) {
     // class weights exactly as finalize() forms them
     const float n0 = (float)__ldcg(a.stats + ST_N + 0), n1 = (float)__ldcg(a.stats + ST_N + 1);
@@ -889,13 +929,12 @@ __global__ void __launch_bounds__(256, 4) loss_fused_kernel(const LossArgs a, co
         noff = (size_t)b * 2 * plane + (size_t)(g - b * plane8) * 8;
         nz0.ld(yh + noff); nz1.ld(yh + noff + plane); nt0.ld(ys + noff); nt1.ld(ys + noff + plane);
       }
-      float t0[8], t1[8], q0[8], q1[8];
-      rt0.get(t0); rt1.get(t1);
-      float tsum = 0.f;
+      float q0[8], q1[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { tsum += fabsf(t0[j]) + fabsf(t1[j]); q0[j] = q1[j] = 0.f; }
-      if (tsum != 0.f) {   // an unlabelled group contributes ys * log(.) = 0 and an all-zero gradient
-        float p0[8], p1[8];
+      for (int j = 0; j < 8; ++j) q0[j] = q1[j] = 0.f;
+      if (rt0.any_nonzero() || rt1.any_nonzero()) {   // an unlabelled group contributes ys * log(.) = 0 and an all-zero gradient
+        float p0[8], p1[8], t0[8], t1[8];
+        rt0.get(t0); rt1.get(t1);
         rz0.get(p0); rz1.get(p1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -915,21 +954,6 @@ __global__ void __launch_bounds__(256, 4) loss_fused_kernel(const LossArgs a, co
       }
       VecIO<T, 8>::st(gy + off, q0);
       VecIO<T, 8>::st(gy + off + plane, q1);
-    }
-  }
-
-  if (a.flags & OCT_LOSS_KLD) {
-    const float gk = a.lam_kld / ((float)a.B * (float)a.H * (float)a.W);
-    const unsigned stride = gridDim.x * 8u;
-    // blocks are walked in reverse here: the ones that drew an extra WPCE round above draw one KLD round less
-    unsigned u = (gridDim.x - 1 - blockIdx.x) * 8u + warp;
-    PlaneRaw<T> nxt;
-    if (u < g.units) plane_issue<T, PYR>(a, g, u, lane, nxt);
-    while (u < g.units) {
-      const PlaneRaw<T> cur = nxt;
-      u += stride;
-      if (u < g.units) plane_issue<T, PYR>(a, g, u, lane, nxt);   // next unit's loads fly while this one is computed
-      plane_finish<T, PYR>(a, g, lane, cur, gk, acc[2]);
     }
   }
 
@@ -981,6 +1005,8 @@ __global__ void __launch_bounds__(256, 4) loss_fused_kernel(const LossArgs a, co
     st[ST_S + 0] = fin[0][0]; st[ST_S + 1] = fin[1][0]; st[ST_KLD] = fin[2][0];
     finalize(a);
     a.out[6] = a.lam_wpce * a.out[OCT_LOSS_OUT_WPCE] + a.lam_kld * a.out[OCT_LOSS_OUT_KLD] + a.lam_lsg * a.out[OCT_LOSS_OUT_LSG];
+    // leave the accumulators and counters zero for the next evaluation: no memset node between two launches
+    for (int i = 0; i < ST_DICE; ++i) st[i] = 0.0;
   }
 }
 
@@ -1417,7 +1443,7 @@ extern "C" int octave_loss_fused(const OctaveLossDesc* d, const void* yhat, cons
       a.g_att[k] = g_att[k];
     }
   }
-  if (cudaMemsetAsync(stats, 0, (size_t)(ST_DICE + 2 * d->B) * sizeof(double), s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  // (no memset: the first ST_DICE doubles of `stats` are zero on entry by contract and the kernel leaves them zero)
   int sms = octave_sm_count();
   if (sms <= 0) sms = 148;
   const long long plane = (long long)d->H * d->W;
@@ -1426,10 +1452,10 @@ extern "C" int octave_loss_fused(const OctaveLossDesc* d, const void* yhat, cons
   if (grid > items) grid = items;
   if (grid > kFusedMaxBlocks) grid = kFusedMaxBlocks;
   if (grid < 1) grid = 1;
-  // OCTAVE_LOSS_COOP=1: cooperative single launch (count phase + grid barrier + fused pass) when every block of the grid is
-  // resident at once.  Measured 1.5 us SLOWER per evaluation than the two launches queued back to back (the pre-pass overlaps
-  // the tail of whatever ran before; profiles/loss_k9_r02.log), so the default is the two-launch form.
-  static const int coop_env = [] { const char* e = getenv("OCTAVE_LOSS_COOP"); return e ? atoi(e) : 0; }();
+  // Cooperative single launch (count phase, KLD units, then WPCE once every block's count is in) when every block of the grid
+  // is resident at once; OCTAVE_LOSS_COOP=0 selects the two-launch form (labels pre-pass kernel + fused kernel).  (A first
+  // version with a grid-wide barrier right after the count phase was 1.5 us slower than the two launches.)
+  static const int coop_env = [] { const char* e = getenv("OCTAVE_LOSS_COOP"); return e ? atoi(e) : 1; }();
   bool coop = false;
   if (coop_env && (d->flags & OCT_LOSS_WPCE)) {
     static int per_sm_cache[2] = {-1, -1};     // resident blocks per SM of the fp32 / bf16 kernel (0: no cooperative launch)
@@ -1445,8 +1471,8 @@ extern "C" int octave_loss_fused(const OctaveLossDesc* d, const void* yhat, cons
   }
   if ((d->flags & OCT_LOSS_WPCE) && !coop) {
     const long long groups = plane / 8 * 2 * d->B;
-    long long gx = (groups + 256 * 4 - 1) / (256 * 4);
-    if (gx > 4LL * sms) gx = 4LL * sms;
+    long long gx = (groups + 256 * 8 - 1) / (256 * 8);
+    if (gx > 6LL * sms) gx = 6LL * sms;
     if (d->dtype == OCT_DTYPE_F32)
       loss_label_count_kernel<float><<<(int)gx, 256, 0, s>>>(reinterpret_cast<const float*>(ys), plane / 8, groups, a.stats);
     else

@@ -119,6 +119,20 @@ class _FusedLossFn(torch.autograd.Function):
         return (None, g_yhat, None, g_real, g_fake, *(g_att if g_att else [None] * len(att)))
 
 
+_fused_ws = {}
+
+
+def _fused_workspace(dev, nbytes: int) -> Tensor:
+    """Statistics workspace of the single-pass loss: zeroed once, left zero by every evaluation (the kernel cleans up after
+    itself), one per (device, stream) because evaluations on one stream are serialised."""
+    key = (dev, _stream_ptr())
+    ws = _fused_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=dev)
+        _fused_ws[key] = ws
+    return ws
+
+
 class _FusedTotalFn(torch.autograd.Function):
     """total = l_sup * WPCE + l_kl * KLD + l_g * LSG with values AND gradients from one sweep over the maps
     (octave_loss_fused: labels-only count pre-pass + one fused pass).  Returns (total, out[8]); `out` is not
@@ -129,7 +143,7 @@ class _FusedTotalFn(torch.autograd.Function):
     def forward(ctx, cfg: _LossCfg, lambdas, yhat, ys, d_fake, *att):
         desc = _build_desc(cfg, yhat, att, None, d_fake)
         dev = yhat.device
-        stats = torch.empty(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        stats = _fused_workspace(dev, _lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)))
         out = torch.empty(_lib.LOSS_OUT_SLOTS, dtype=torch.float32, device=dev)
         g_yhat = torch.empty_like(yhat)
         g_att = [torch.empty_like(a) for a in att]

@@ -35,7 +35,8 @@ for (B, H, dt) in [(32, 400, torch.bfloat16), (64, 304, torch.bfloat16), (8, 102
     sets = [make_set(B, H, dt, s) for s in range(nsets)]
     cfg = losses._LossCfg(_lib.LOSS_WPCE | _lib.LOSS_KLD | _lib.LOSS_FROM_LOGITS, att_weights=[1.0] * 4, sum_weights=4.0)
     desc = losses._build_desc(cfg, sets[0][0], sets[0][2], None, None)
-    stats = torch.empty(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+    stats = torch.zeros(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)   # zero on entry, left zero by every evaluation
+    stats2 = torch.empty(_lib.lib.octave_loss_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)       # two-pass form: its own workspace
     outv = torch.empty(8, device=dev); gs = torch.ones(8, device=dev)
     sp = torch.cuda.current_stream().cuda_stream
     lam = (C.c_float * 3)(1.0, 0.1, 0.1)
@@ -43,9 +44,9 @@ for (B, H, dt) in [(32, 400, torch.bfloat16), (64, 304, torch.bfloat16), (8, 102
     for agg, ys, att, g_y, g_a in sets:
         arr, garr = losses._ptr_array(att), losses._ptr_array(g_a)
         fw.append(lambda agg=agg, ys=ys, arr=arr: _lib.lib.octave_loss_fwd(C.byref(desc), agg.data_ptr(), ys.data_ptr(), arr, None, None,
-                                                                           stats.data_ptr(), outv.data_ptr(), sp))
+                                                                           stats2.data_ptr(), outv.data_ptr(), sp))
         bw.append(lambda agg=agg, ys=ys, arr=arr, g_y=g_y, garr=garr: _lib.lib.octave_loss_bwd(
-            C.byref(desc), agg.data_ptr(), ys.data_ptr(), arr, None, None, stats.data_ptr(), gs.data_ptr(), g_y.data_ptr(), garr, None, None, sp))
+            C.byref(desc), agg.data_ptr(), ys.data_ptr(), arr, None, None, stats2.data_ptr(), gs.data_ptr(), g_y.data_ptr(), garr, None, None, sp))
         fu.append(lambda agg=agg, ys=ys, arr=arr, g_y=g_y, garr=garr: _lib.lib.octave_loss_fused(
             C.byref(desc), agg.data_ptr(), ys.data_ptr(), arr, None, lam, stats.data_ptr(), outv.data_ptr(), g_y.data_ptr(), garr, None, sp))
     assert fu[0]() == 0

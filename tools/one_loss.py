@@ -13,7 +13,7 @@ att = [torch.softmax(torch.randn(B, 2, H >> k, H >> k, device=dev, generator=g),
 g_y, g_a = torch.empty_like(agg), [torch.empty_like(a) for a in att]
 cfg = losses._LossCfg(_lib.LOSS_WPCE | _lib.LOSS_KLD | _lib.LOSS_FROM_LOGITS, att_weights=[1.0] * 4, sum_weights=4.0)
 desc = losses._build_desc(cfg, agg, att, None, None)
-stats = torch.empty(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+stats = torch.zeros(_lib.lib.octave_loss_fused_stats_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)   # zero on entry, left zero by every evaluation
 outv = torch.empty(8, device=dev)
 lam = (C.c_float * 3)(1.0, 0.1, 0.1)
 arr, garr = losses._ptr_array(att), losses._ptr_array(g_a)
