@@ -403,6 +403,12 @@ int octave_synth_mask_pyramid(uint64_t seed, int32_t B, int32_t H, int32_t W, in
 int octave_augment(uint64_t seed, int32_t B, int32_t C, int32_t Cy, int32_t H, int32_t W, int32_t flags, const float* x,
                    const float* ys, float* x_out, float* ys_out, void* stream);
 
+/* Spectral norm of the critic's 4x4 convs (torch.nn.utils.spectral_norm legacy semantics, discriminator/blocks.py:101-104):
+ * one power iteration (training != 0: u, v updated in place) and sigma = u . (W v) in one launch, fixed summation order.
+ * W: weight_orig as [rows][cols] fp32, rows <= 1024; out2: device float[2] = sigma, 1/sigma. */
+int octave_spectral_sigma(const float* W, int32_t rows, int32_t cols, float* u, float* v, int32_t training, float eps,
+                          float* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

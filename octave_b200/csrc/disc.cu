@@ -210,3 +210,90 @@ extern "C" int octave_rowdot_bwd(const OctaveAct* x, const float* w, const float
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
+
+// ---- spectral norm: one power iteration and sigma in ONE launch (torch.nn.utils.spectral_norm, legacy hook semantics used by
+// DiscriminatorBlock, discriminator/blocks.py:101-104: n_power_iterations = 1, eps = 1e-12):
+//   training:  v <- normalize(W^T u);  u <- normalize(W v);  sigma = u . (W v)      (u, v updated in place)
+//   eval:      sigma = u . (W v)
+// W is [rows][cols] fp32 (weight_orig viewed as a matrix).  One block: the matrices here are at most 1024 x 240.  Fixed
+// summation order (no atomics): the critic's weights are bit-reproducible from run to run.
+namespace {
+constexpr int kSnThreads = 1024;
+__global__ void __launch_bounds__(kSnThreads) spectral_sigma_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ u,
+                                                                    float* __restrict__ v, int training, float eps,
+                                                                    float* __restrict__ out /* sigma, 1/sigma */) {
+  extern __shared__ float sm[];
+  float* us = sm;                 // [rows]
+  float* vs = sm + rows;          // [cols]
+  float* part = vs + cols;        // [4][256]
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < rows; j += kSnThreads) us[j] = u[j];
+  for (int k = tid; k < cols; k += kSnThreads) vs[k] = v[k];
+  __syncthreads();
+  auto block_total = [&](float x) {
+    x = warp_sum(x);
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < kSnThreads / 32; ++w) t += red[w];     // every thread adds the 32 warp sums in the same order
+    return t;
+  };
+  if (training) {
+    // v = W^T u: thread (c, rg) sums rows rg, rg+4, ... of column k0 + c
+    const int c = tid & 255, rg = tid >> 8;
+    for (int k0 = 0; k0 < cols; k0 += 256) {
+      const int k = k0 + c;
+      float acc = 0.f;
+      if (k < cols) {
+#pragma unroll 8
+        for (int j = rg; j < rows; j += 4) acc += __ldg(W + (size_t)j * cols + k) * us[j];
+      }
+      part[rg * 256 + c] = acc;
+      __syncthreads();
+      if (rg == 0 && k < cols) vs[k] = (part[c] + part[256 + c]) + (part[512 + c] + part[768 + c]);
+      __syncthreads();
+    }
+    float sq = 0.f;
+    for (int k = tid; k < cols; k += kSnThreads) sq += vs[k] * vs[k];
+    const float nv = fmaxf(sqrtf(block_total(sq)), eps);
+    for (int k = tid; k < cols; k += kSnThreads) { vs[k] /= nv; v[k] = vs[k]; }
+    __syncthreads();
+  }
+  // wv = W v: one warp per row
+  float dot_uw = 0.f, sq_w = 0.f;
+  for (int j = warp; j < rows; j += kSnThreads / 32) {
+    float acc = 0.f;
+    for (int k = lane; k < cols; k += 32) acc += __ldg(W + (size_t)j * cols + k) * vs[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sq_w += acc * acc;
+      dot_uw += us[j] * acc;
+      part[j & 1023] = acc;          // rows <= 1024 fit; larger matrices recompute below
+    }
+  }
+  const float nw2 = block_total(sq_w);
+  float sigma;
+  if (training) {
+    const float nu = fmaxf(sqrtf(nw2), eps);
+    if (rows <= 1024) {
+      for (int j = tid; j < rows; j += kSnThreads) u[j] = part[j] / nu;
+    }
+    sigma = nw2 / nu;                // u . (W v) with u = W v / nu
+  } else {
+    sigma = block_total(dot_uw);
+  }
+  if (tid == 0) { out[0] = sigma; out[1] = 1.f / sigma; }
+}
+}  // namespace
+
+extern "C" int octave_spectral_sigma(const float* W, int32_t rows, int32_t cols, float* u, float* v, int32_t training, float eps,
+                                     float* out2, void* stream) {
+  if (!W || !u || !v || !out2 || rows <= 0 || cols <= 0) return OCT_ERR_INVALID;
+  if (rows > 1024 || cols > 8192) return OCT_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(rows + cols + 1024) * sizeof(float);
+  spectral_sigma_kernel<<<1, kSnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(W, rows, cols, u, v, training, eps, out2);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}

@@ -187,8 +187,16 @@ class DiscriminatorBlock(nn.Module):
     def _spectral_weight(self, conv: nn.Module, need_w: bool = True):
         """-> (W_orig / sigma or None, sigma, u, v) after one power iteration in training mode."""
         w = conv.weight_orig.detach()
-        wm = w.reshape(w.shape[0], -1).float().contiguous()
+        wm = w.reshape(w.shape[0], -1)
+        if wm.dtype != torch.float32 or not wm.is_contiguous():
+            wm = wm.float().contiguous()
         u, v = conv.weight_u, conv.weight_v
+        if wm.is_cuda and wm.shape[0] <= 1024 and u.dtype == torch.float32 and v.dtype == torch.float32:
+            # one launch: power iteration (u, v in place) + sigma + 1/sigma, fixed summation order
+            sg = ops.spectral_sigma(wm, u, v, self.training)
+            sigma = sg[0]
+            self._last_inv_sigma = sg[1:2]
+            return (w.float() / sigma if need_w else None), sigma, u.clone(), v.clone()
         if self.training:
             v_new = ops.glinear_bwd_data_only(u.reshape(1, -1), wm)          # W^T u
             v_new = v_new / v_new.norm().clamp_min(1e-12)
@@ -199,6 +207,7 @@ class DiscriminatorBlock(nn.Module):
         else:
             wv = ops.glinear_fwd(v.reshape(1, -1).contiguous(), wm, None, 1, 1.0).reshape(-1)
         sigma = (u * wv).sum()
+        self._last_inv_sigma = (1.0 / sigma).reshape(1).float()
         return (w.float() / sigma if need_w else None), sigma, u.clone(), v.clone()
 
     def _padded_squeeze(self, i: int, rows: int):
@@ -282,7 +291,7 @@ class DiscriminatorBlock(nn.Module):
             ops.conv1x1_tc_s2d_store(s, spec_sq.pack(0), b16, 16, catS, 16, ops.ACT_SIGMOID)   # :121
             ops.nchw_to_s2d(yi.detach(), catS, 16, 13)                                    # :122 (overwrites pad channels 13,14)
             _, sigma, u, v = self._spectral_weight(sn, need_w=False)
-            inv_sigma = (1.0 / sigma).reshape(1).float()
+            inv_sigma = self._last_inv_sigma
             wo_ = sn.weight_orig.detach()
             ho, wo = (h + 2 - 4) // 2 + 1, (w + 2 - 4) // 2 + 1
             s_next = ops.conv4x4s2_tc_fwd(catS, ops.pack_weight_s2d(wo_, inv_sigma, 0, 16), sn.bias.detach().float(),

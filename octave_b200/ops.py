@@ -149,6 +149,8 @@ _sigs = {
 for _n, _a in _sigs.items():
     getattr(lib, _n).restype = C.c_int
     getattr(lib, _n).argtypes = _a
+lib.octave_spectral_sigma.restype = C.c_int
+lib.octave_spectral_sigma.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_float, _vp, _vp]
 lib.octave_affine_gap_ws_bytes.restype = C.c_size_t
 lib.octave_affine_gap_ws_bytes.argtypes = [_A]
 lib.octave_pack_job_blocks.restype = C.c_int64
@@ -735,3 +737,11 @@ def rowdot_bwd(x: Act, w: torch.Tensor, g: torch.Tensor, need_dw: bool):
     db = torch.empty(1, dtype=torch.float32, device=x.device) if need_dw else None
     _chk("octave_rowdot_bwd", lib.octave_rowdot_bwd(_ref(x), w.data_ptr(), g.data_ptr(), _ref(dx), _p(dw), _p(db), stream_ptr()))
     return dx, dw, db
+
+
+def spectral_sigma(w2d: torch.Tensor, u: torch.Tensor, v: torch.Tensor, training: bool, eps: float = 1e-12) -> torch.Tensor:
+    """One power iteration (training: u, v updated in place) and sigma = u . (W v) -> float32[2] = (sigma, 1/sigma)."""
+    out = torch.empty(2, dtype=torch.float32, device=w2d.device)
+    _chk("octave_spectral_sigma", lib.octave_spectral_sigma(w2d.data_ptr(), w2d.shape[0], w2d.shape[1], u.data_ptr(), v.data_ptr(),
+                                                            int(training), eps, out.data_ptr(), stream_ptr()))
+    return out
