@@ -547,14 +547,16 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, HaloParams& p, i
   if (stages < 2) return OCT_ERR_UNSUPPORTED;
   p.stages = stages;
   const int smem = fixed + stages * p.a_stage_bytes;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static unsigned long long attr_devs = 0;   // the attribute is per device: one bit per device ordinal
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  if (!(attr_devs >> (dev__ & 63) & 1ull)) {
     cudaError_t ea = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (ea != cudaSuccess) {
       if (getenv("OCTAVE_DEBUG")) fprintf(stderr, "[octave] halo: smem attribute: %s\n", cudaGetErrorString(ea));
       return OCT_ERR_LAUNCH;
     }
-    attr_smem = 226 * 1024;
+    attr_devs |= 1ull << (dev__ & 63);
   }
   conv3x3_halo_kernel<BN, CIN><<<grid, kHaloThreads, smem, s>>>(tmA, tmW, p);
   if (getenv("OCTAVE_DEBUG")) {
@@ -671,11 +673,13 @@ static int launch_halo_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, co
   constexpr int stage = 128 * ROWY + (((192 + 8) * ROWX + 1023) & ~1023);
   constexpr int smem = STAGES * stage + 1024;
   static_assert(smem <= 226 * 1024, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0;   // the attribute is per device: one bit per device ordinal
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  if (!(attr_devs >> (dev__ & 63) & 1ull)) {
     if (cudaFuncSetAttribute(conv3x3_halo_wgrad_kernel<CY, CX, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return OCT_ERR_LAUNCH;
-    attr_done = true;
+    attr_devs |= 1ull << (dev__ & 63);
   }
   conv3x3_halo_wgrad_kernel<CY, CX, STAGES><<<grid, kHwThreads, smem, s>>>(tmDY, tmX, p);
   OCT_CHECK_LAUNCH();

@@ -880,11 +880,13 @@ int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const WgradPar
   // +32 KB slack: the chunks a 128-row UMMA strides over beyond NA must stay inside the allocation
   constexpr int smem = STAGES * wgrad_stage_bytes<BN, CWA, CWB, NA, ROWS>() + (128 / CWA - NA) * ROWS * CWA * 2 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_devs = 0;   // the attribute is per device: one bit per device ordinal
+  int dev__ = 0;
+  cudaGetDevice(&dev__);
+  if (!(attr_devs >> (dev__ & 63) & 1ull)) {
     if (cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return OCT_ERR_LAUNCH;
-    attr_done = true;
+    attr_devs |= 1ull << (dev__ & 63);
   }
   conv_tc_wgrad_kernel<BN, CWA, CWB, NA, STAGES, ROWS><<<grid, kWgThreads, smem, s>>>(tmDY, tmX, p);
   OCT_CHECK_LAUNCH();
