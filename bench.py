@@ -405,6 +405,7 @@ def run_gpu(args):
         if e2e:                                 # input pipelining: next batch's H2D overlaps this step's compute
             if use_graph:
                 ts.prefetch(*host[(i + 1) % nb])
+                ts.predraw()                    # ... and so do the next step's CPU noise draws (before the blocking read below)
             else:
                 pre.put(*host[(i + 1) % nb])
         if e2e:

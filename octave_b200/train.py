@@ -263,10 +263,19 @@ class TrainStep:
         if self._feed is not None:
             # fresh CPU draws for this step: filled into the next pinned ring slot and uploaded on this stream BEFORE the
             # replay (outside the graph, so the pinned source rotates and the host never overwrites a pending upload)
-            self._feed.draw()
+            if not getattr(self, "_predrawn", False):
+                self._feed.draw()
+            self._predrawn = False
             self._feed.upload()
         self._graph.replay()
         return self._sout
+
+    def predraw(self) -> None:
+        """Make the NEXT step's CPU noise draws now (e.g. while the current replay is still running on the GPU and before the
+        caller blocks on its result): the following step_graphed() then only uploads them.  Same generator, same order."""
+        if getattr(self, "_graph", None) is not None and self._feed is not None and not getattr(self, "_predrawn", False):
+            self._feed.draw()
+            self._predrawn = True
 
     def prefetch(self, x: Tensor, ys: Tensor, real: Sequence[Tensor]) -> None:
         """Start the host-to-device upload of the NEXT batch (pinned host tensors) on a copy stream so that it overlaps
