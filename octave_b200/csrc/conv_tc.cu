@@ -616,6 +616,7 @@ struct WgradParams {
   int cout_total;
   int convt;         // 1: GEMM rows are n = t*Cout + co of a ConvTranspose k2s2
   int convt_cout;
+  int single_writer; // 1: no split-K (gridDim.z == 1): plain stores, the output needs no zero fill
 };
 
 constexpr int kWgProducers = 4;
@@ -761,21 +762,44 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int co = g * p.cout_g + co0 + r;           // global GEMM row
     const int nvalid = min(BN, p.cin_g - ci0);
+    // 1x1 layers without merged groups: dW[co][ci] is contiguous in ci, so a lane's 16 columns are four 16-byte vectors —
+    // one red.global.add.v4.f32 (or one 16-byte store when this CTA is the only writer) instead of four scalar atomics
+    const bool vec = !p.convt && p.taps == 1 && p.real_cin_g == p.cin_g && p.real_cout_g == p.cout_g && (p.cin_g & 3) == 0;
+    const bool single = p.single_writer != 0;        // no split-K: every element is written exactly once (no memset, no atomics)
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t v[16];
       tc::tmem_ld16(taddr + c0, v);
       tc::tmem_ld_wait();
       if (valid) {
+        if (vec) {
+          float* dst = p.dw + (long long)co * p.cin_g + ci0 + c0;      // (group offset is inside co: co * cin_g indexes [Cout][Cin/g])
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (c0 + i < nvalid) {
-            const int ci = g * p.cin_g + ci0 + c0 + i;  // global input channel
-            if (p.convt) {
-              const int t = co / p.convt_cout, cc = co - t * p.convt_cout;
-              atomicAdd(p.dw + ((long long)ci * p.convt_cout + cc) * 4 + t, __uint_as_float(v[i]));
-            } else if (ci / p.real_cin_g == co / p.real_cout_g) {
-              atomicAdd(p.dw + ((long long)co * p.real_cin_g + (ci % p.real_cin_g)) * p.taps + tap, __uint_as_float(v[i]));
+          for (int i = 0; i < 16; i += 4) {
+            if (c0 + i < nvalid) {
+              if (single) {
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+              } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                             "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3])) : "memory");
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (c0 + i < nvalid) {
+              const int ci = g * p.cin_g + ci0 + c0 + i;  // global input channel
+              float* dst;
+              if (p.convt) {
+                const int t = co / p.convt_cout, cc = co - t * p.convt_cout;
+                dst = p.dw + ((long long)ci * p.convt_cout + cc) * 4 + t;
+              } else if (ci / p.real_cin_g == co / p.real_cout_g) {
+                dst = p.dw + ((long long)co * p.real_cin_g + (ci % p.real_cin_g)) * p.taps + tap;
+              } else {
+                continue;
+              }
+              if (single) *dst = __uint_as_float(v[i]); else atomicAdd(dst, __uint_as_float(v[i]));
             }
           }
         }
@@ -1103,7 +1127,9 @@ extern "C" int octave_conv_tc_wgrad(const OctaveConvDesc* d, const void* x, cons
   if (!make_act_map(&tmX, xb, d->cin, W, H, B, d->x_ld, CWB, p.TW, p.TH, CWB * 2)) return OCT_ERR_LAUNCH;
   if (!make_act_map(&tmDY, dyb, cout_all, d->ksize == 1 ? W : d->Wout, d->ksize == 1 ? H : d->Hout, B, d->y_ld, CWA, p.TW, p.TH, CWA * 2)) return OCT_ERR_LAUNCH;
   const size_t wbytes = (size_t)cout_all * p.real_cin_g * p.taps * sizeof(float);
-  if (!d->accumulate && cudaMemsetAsync(dw, 0, wbytes, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  // one writer per element (no split-K) and every element of dW covered by a tile: plain stores, no zero fill
+  p.single_writer = (split == 1 && !d->accumulate) ? 1 : 0;
+  if (!d->accumulate && !p.single_writer && cudaMemsetAsync(dw, 0, wbytes, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   if (split > 65535) return OCT_ERR_UNSUPPORTED;
   dim3 grid(p.taps * n_co_tiles * p.n_ci_tiles, d->groups, split);
   const bool one_a = cout_g <= CWA;   // a single A box per pixel tile
