@@ -313,7 +313,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
       tc::bar_sync_named(bar_id, 128);               // (B) every row of the tile is staged
       if (issuer) {
 #pragma unroll
-        for (int sl = 0; sl < NSL; ++sl) tc::tma_store_4d(&tmC, sbuf_u32 + sl * SLAB_BYTES, cbase + sl * SWC, w0, h0, img);
+        for (int sl = 0; sl < NSL; ++sl) {
+          if (p.accumulate) tc::tma_reduce_add_4d(&tmC, sbuf_u32 + sl * SLAB_BYTES, cbase + sl * SWC, w0, h0, img);   // y += tile
+          else tc::tma_store_4d(&tmC, sbuf_u32 + sl * SLAB_BYTES, cbase + sl * SWC, w0, h0, img);
+        }
         tc::tma_store_commit();
       }
     }
@@ -1016,7 +1019,7 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
   if (stats && grid > p.total_tiles) grid = p.total_tiles;  // total_tiles is itself a multiple of ng
   // plain outputs of <= 128-column tiles take the TMA-store epilogue (OCTAVE_TMA_EPI=0 restores the per-lane stores)
   static const int tma_epi = [] { const char* e = getenv("OCTAVE_TMA_EPI"); return e ? atoi(e) : 1; }();
-  const bool epi1 = tma_epi && BN <= 128 && !bias && d->relu == 0 && !d->accumulate && !convt && !s2d && !p.out_f32;
+  const bool epi1 = tma_epi && BN <= 128 && !bias && d->relu == 0 && !convt && !s2d && !p.out_f32;   // accumulate: TMA reduce-add
   CUtensorMap tmC = tmA;
   if (epi1) {
     const int swc = BN < 64 ? BN : 64;
