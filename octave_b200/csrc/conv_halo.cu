@@ -60,9 +60,13 @@ __device__ __forceinline__ float halo_act(float v, int act) {
   }
 }
 
-template <int BN, int CIN>
+// EPI = 1 (plain outputs: no bias / activation): TMA-store epilogue as in conv_tc_kernel — the live rows of a tile
+// (ow < TW) are staged COMPACTLY in the TMA box layout [TH][TW][BN] (16-byte units XOR-swizzled), one cp.async.bulk.tensor
+// store (or reduce-add, for accumulating data gradients) per tile, two groups of four epilogue warps on alternate tiles.
+template <int BN, int CIN, int EPI = 0>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmW,
+                                                                       const __grid_constant__ CUtensorMap tmC,
                                                                        const HaloParams p) {
   constexpr int ROWB = CIN * 2;          // bytes per pixel row of the A tile = swizzle span
   constexpr int TAPB = BN * ROWB;        // bytes of one tap's weight tile
@@ -95,13 +99,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(tc::smem_u32(&acc_full[b]), 1);
-      tc::mbar_init(tc::smem_u32(&acc_empty[b]), 8);
+      tc::mbar_init(tc::smem_u32(&acc_empty[b]), EPI == 1 ? 4 : 8);
     }
     tc::mbar_init(tc::smem_u32(&w_bar), 1);
     tc::fence_barrier_init();
     tc::fence_proxy_async();
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
+    if (EPI == 1) tc::tma_prefetch_desc(&tmC);
   }
   if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tc::smem_u32(&tmem_slot));
   tc::fence_before_sync();
@@ -171,6 +176,103 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv3x3_halo_kernel(const __g
       }
       __syncwarp();
       if (++s == p.stages) { s = 0; ph ^= 1u; }
+    }
+  } else if (EPI == 1) {
+    // ---- TMA-store epilogue: two groups of four warps on alternate tiles (group = accumulator buffer); a warp owns the 32
+    // GEMM rows of its TMEM lane quarter over all BN columns
+    constexpr int RB = BN * 2;                      // bytes per staged row = swizzle span (128 or 64)
+    constexpr int CHS = BN / 16;
+    constexpr int CP = BN / 2, RG = 32 / CP > 0 ? 32 / CP : 1, RPG = 32 / RG;
+    const int q = warp & 3;
+    const int group = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int th = r / p.TWp, tw = r - th * p.TWp;
+    const bool live = tw < p.TW && th < p.TH;
+    const int rc = th * p.TW + tw;                  // compact row of this lane's pixel inside the staged [TH][TW] box
+    uint8_t* const sbuf = stage_gen + group * (128 * RB);
+    const uint32_t sbuf_u32 = tc::smem_u32(sbuf);
+    const bool issuer = q == 0 && lane == 0;
+    const int bar_id = 1 + group;
+    auto swz = [](int row) { return RB == 128 ? (row & 7) : ((row >> 1) & 3); };
+    float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+    int stat_col0 = -1;
+    const uint32_t buf = (uint32_t)group;
+    uint32_t use = 0;
+    for (long long t = blockIdx.x + (long long)group * gridDim.x; t < p.total_tiles; t += 2LL * gridDim.x, ++use) {
+      const int tt = (int)t;
+      const int g = tt % p.groups;
+      const int m_tile = tt / p.groups;
+      const int img = m_tile / tiles_per_img;
+      const int trem = m_tile - img * tiles_per_img;
+      const int th_i = trem / p.tiles_w;
+      const int h0 = th_i * p.TH, w0 = (trem - th_i * p.tiles_w) * p.TW;
+      const bool valid = live && (h0 + th < p.Hout) && (w0 + tw < p.Wout);
+      stat_col0 = g * BN;
+      tc::mbar_wait(tc::smem_u32(&acc_full[buf]), use & 1u);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+      uint32_t v[CHS][16];
+#pragma unroll
+      for (int c = 0; c < CHS; ++c) tc::tmem_ld16(taddr + c * 16, v[c]);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[buf]));
+      // (A) the group's previous store has finished reading the staging tile
+      if (issuer) tc::tma_store_wait_read();
+      tc::bar_sync_named(bar_id, 128);
+      if (live) {
+        uint8_t* rowp = sbuf + rc * RB;
+#pragma unroll
+        for (int c = 0; c < CHS; ++c) {
+          uint4 u0, u1;
+          u0.x = bf16x2_pack(__uint_as_float(v[c][0]), __uint_as_float(v[c][1]));   u0.y = bf16x2_pack(__uint_as_float(v[c][2]), __uint_as_float(v[c][3]));
+          u0.z = bf16x2_pack(__uint_as_float(v[c][4]), __uint_as_float(v[c][5]));   u0.w = bf16x2_pack(__uint_as_float(v[c][6]), __uint_as_float(v[c][7]));
+          u1.x = bf16x2_pack(__uint_as_float(v[c][8]), __uint_as_float(v[c][9]));   u1.y = bf16x2_pack(__uint_as_float(v[c][10]), __uint_as_float(v[c][11]));
+          u1.z = bf16x2_pack(__uint_as_float(v[c][12]), __uint_as_float(v[c][13])); u1.w = bf16x2_pack(__uint_as_float(v[c][14]), __uint_as_float(v[c][15]));
+          if (!valid) { u0 = make_uint4(0, 0, 0, 0); u1 = u0; }   // outside the image: clipped by the store, kept out of the statistics
+          *reinterpret_cast<uint4*>(rowp + (((2 * c) ^ swz(rc)) << 4)) = u0;
+          *reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ swz(rc)) << 4)) = u1;
+        }
+      }
+      __syncwarp();
+      if (p.stats) {
+        // lane owns the column pair cp over the warp's rows rg, rg + RG, ...; dead rows (ow >= TW) are skipped
+        const int cp = lane % CP, rg = lane / CP;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < RPG; ++i) {
+          const int rr = q * 32 + i * RG + rg;
+          const int th2 = rr / p.TWp, tw2 = rr - th2 * p.TWp;
+          if (tw2 < p.TW && th2 < p.TH) {
+            const int row = th2 * p.TW + tw2;
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(sbuf + row * RB + (((cp >> 2) ^ swz(row)) << 4) + (cp & 3) * 4);
+            float a, b;
+            bf16x2_unpack(u, a, b);
+            s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+          }
+        }
+#pragma unroll
+        for (int off = 16; off >= CP; off >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+          q0 += __shfl_xor_sync(0xffffffffu, q0, off); q1 += __shfl_xor_sync(0xffffffffu, q1, off);
+        }
+        sacc[0] += s0; sacc[1] += s1; sacc[2] += q0; sacc[3] += q1;
+      }
+      tc::fence_proxy_async();
+      tc::bar_sync_named(bar_id, 128);               // (B) every live row of the tile is staged
+      if (issuer) {
+        if (p.accumulate) tc::tma_reduce_add_4d(&tmC, sbuf_u32, g * BN, w0, h0, img);
+        else tc::tma_store_4d(&tmC, sbuf_u32, g * BN, w0, h0, img);
+        tc::tma_store_commit();
+      }
+    }
+    if (issuer) tc::tma_store_wait_all();
+    if (p.stats && stat_col0 >= 0 && lane < CP) {
+      atomicAdd(p.stats + stat_col0 + 2 * lane, (double)sacc[0]);
+      atomicAdd(p.stats + stat_col0 + 2 * lane + 1, (double)sacc[1]);
+      atomicAdd(p.stats + p.stats_stride + stat_col0 + 2 * lane, (double)sacc[2]);
+      atomicAdd(p.stats + p.stats_stride + stat_col0 + 2 * lane + 1, (double)sacc[3]);
     }
   } else {
     // ---- 8 epilogue warps: TMEM lane quarter q <-> GEMM rows [32q, 32q+32); column half hsel
@@ -535,13 +637,13 @@ CUtensorMapSwizzle swz_of(int bytes) {
   return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
-template <int BN, int CIN>
-int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, HaloParams& p, int grid, cudaStream_t s) {
+template <int BN, int CIN, int EPI = 0>
+int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC, HaloParams& p, int grid, cudaStream_t s) {
   constexpr int ROWB = CIN * 2;
   constexpr int PITCH = (BN / 2) * 2 + 16;
   const int w_bytes = ((p.groups * 9 * BN * ROWB) + 1023) & ~1023;
   p.a_stage_bytes = (((p.a_rows + 8) * ROWB) + 1023) & ~1023;
-  const int fixed = w_bytes + 8 * 32 * PITCH + 1024;
+  const int fixed = w_bytes + (EPI == 1 ? 2 * 128 * BN * 2 : 8 * 32 * PITCH) + 1024;   // EPI 1: one staged tile per epilogue group
   int stages = (225 * 1024 - fixed) / p.a_stage_bytes;   // static barriers + alignment slack stay below 227 KB
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return OCT_ERR_UNSUPPORTED;
@@ -551,14 +653,14 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, HaloParams& p, i
   int dev__ = 0;
   cudaGetDevice(&dev__);
   if (!(attr_devs >> (dev__ & 63) & 1ull)) {
-    cudaError_t ea = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t ea = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, CIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (ea != cudaSuccess) {
       if (getenv("OCTAVE_DEBUG")) fprintf(stderr, "[octave] halo: smem attribute: %s\n", cudaGetErrorString(ea));
       return OCT_ERR_LAUNCH;
     }
     attr_devs |= 1ull << (dev__ & 63);
   }
-  conv3x3_halo_kernel<BN, CIN><<<grid, kHaloThreads, smem, s>>>(tmA, tmW, p);
+  conv3x3_halo_kernel<BN, CIN, EPI><<<grid, kHaloThreads, smem, s>>>(tmA, tmW, tmC, p);
   if (getenv("OCTAVE_DEBUG")) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) fprintf(stderr, "[octave] halo launch<%d,%d> grid %d smem %d stages %d: %s\n", BN, CIN, grid, smem, stages, cudaGetErrorString(e));
@@ -659,12 +761,28 @@ extern "C" int octave_conv_halo_fwd(const OctaveConvDesc* d, const void* x, cons
   long long grid = sms - sms % d->groups;   // a CTA keeps one group: its statistics columns never change
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, s) != cudaSuccess) return OCT_ERR_LAUNCH;
-  if (cin_g == 64) {
-    if (cout_g == 64) return launch_halo<64, 64>(tmA, tmW, p, (int)grid, s);
-    return launch_halo<32, 64>(tmA, tmW, p, (int)grid, s);
+  // OCTAVE_HALO_TMA_EPI=1: plain outputs take the TMA-store epilogue.  Off by default: measured 5-25 % SLOWER than the
+  // per-lane stores on the five halo shapes of the c2 step (the larger staging tile costs an input stage and the
+  // K = 9 * cin_g mainloop is too short to hide a four-warp epilogue); kept as the measured alternative.
+  static const int tma_epi = [] { const char* e = getenv("OCTAVE_HALO_TMA_EPI"); return e ? atoi(e) : 0; }();
+  const bool epi1 = tma_epi && !bias && d->relu == 0;
+  CUtensorMap tmC = tmA;
+  if (epi1) {
+    const bf16* yb = reinterpret_cast<const bf16*>(y) + d->y_coff;
+    cuuint64_t dims[4] = {(cuuint64_t)d->cout, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->y_ld * 2, (cuuint64_t)d->y_ld * 2 * d->Wout, (cuuint64_t)d->y_ld * 2 * d->Wout * d->Hout};
+    cuuint32_t box[4] = {(cuuint32_t)cout_g, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(yb), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swz_of(cout_g * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return OCT_ERR_LAUNCH;
   }
-  if (cout_g == 64) return launch_halo<64, 32>(tmA, tmW, p, (int)grid, s);
-  return launch_halo<32, 32>(tmA, tmW, p, (int)grid, s);
+  if (cin_g == 64) {
+    if (cout_g == 64) return epi1 ? launch_halo<64, 64, 1>(tmA, tmW, tmC, p, (int)grid, s) : launch_halo<64, 64>(tmA, tmW, tmC, p, (int)grid, s);
+    return epi1 ? launch_halo<32, 64, 1>(tmA, tmW, tmC, p, (int)grid, s) : launch_halo<32, 64>(tmA, tmW, tmC, p, (int)grid, s);
+  }
+  if (cout_g == 64) return epi1 ? launch_halo<64, 32, 1>(tmA, tmW, tmC, p, (int)grid, s) : launch_halo<64, 32>(tmA, tmW, tmC, p, (int)grid, s);
+  return epi1 ? launch_halo<32, 32, 1>(tmA, tmW, tmC, p, (int)grid, s) : launch_halo<32, 32>(tmA, tmW, tmC, p, (int)grid, s);
 }
 
 template <int CY, int CX, int STAGES>
