@@ -292,8 +292,8 @@ def best_conv_roofline(peaks, B, H, W):
 
 
 def loss_rooflines(peaks, B, H, W):
-    """K9, the G-step loss (WPCE + KLD on logits, 5-level pyramid): single pass = labels pre-pass + fused values-and-
-    gradients kernel, through the C-ABI.  Rotating input sets larger than L2, launches queued back to back between two CUDA
+    """K9, the G-step loss (WPCE + KLD on logits, 5-level pyramid): ONE co-resident launch (label counts, then the values-and-
+    gradients sweep, then the finalisation by the last block), through the C-ABI.  Rotating input sets larger than L2, launches queued back to back between two CUDA
     events on the launching stream.  Algorithmic bytes: 17.99 elements/pixel (what a statistics pass + a
     gradient pass must move; the single pass moves 13.33).  Reported for bf16 maps (BASELINE.json's loss-kernel metric) and
     for the variant TrainStep.g_step launches (fp32 maps as the heads emit them, + LS-G on the critic logits)."""
@@ -340,8 +340,8 @@ def loss_rooflines(peaks, B, H, W):
         ms = e0.elapsed_time(e1) / reps
         nbytes = 17.99 * es * npx
         gbs = nbytes / (ms * 1e-3) / 1e9
-        out[tag] = {"kernel": f"loss_label_count_kernel + loss_fused_kernel<{'bf16' if es == 2 else 'float'}> (single pass: values and gradients"
-                              f"{', + LS-G' if with_lsg else ''})", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        out[tag] = {"kernel": f"loss_fused_kernel<{'bf16' if es == 2 else 'float'}, pyramid, co-resident> (ONE launch: label counts, KLD, WPCE, "
+                              f"values and gradients{', LS-G' if with_lsg else ''}, finalisation)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes": nbytes, "bytes_moved": 13.33 * es * npx, "us_per_evaluation": ms * 1e3,
                     "traffic": None, "peak_source": peaks["source"], "maps": f"[{B},2,{H},{W}] {'bf16' if es == 2 else 'fp32'}, {nsets} rotating sets"}
         del sets, fns
