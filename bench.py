@@ -343,7 +343,11 @@ def loss_rooflines(peaks, B, H, W):
         out[tag] = {"kernel": f"loss_fused_kernel<{'bf16' if es == 2 else 'float'}, pyramid, co-resident> (ONE launch: label counts, KLD, WPCE, "
                               f"values and gradients{', LS-G' if with_lsg else ''}, finalisation)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes": nbytes, "bytes_moved": 13.33 * es * npx, "us_per_evaluation": ms * 1e3,
-                    "traffic": None, "peak_source": peaks["source"], "maps": f"[{B},2,{H},{W}] {'bf16' if es == 2 else 'fp32'}, {nsets} rotating sets"}
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch at B=32, 400^2, bf16
+                    # (profiles/ncu_loss_fused_r02c.txt: 76.8 MB read + 13.6 MB written; most of the 68 MB of gradient writes are
+                    # still in the 126 MB L2 when the kernel ends, so DRAM traffic is BELOW the 136.5 MB the kernel moves)
+                    "traffic": 90.4e6 if (B, H, W, es, with_lsg) == (32, 400, 400, 2, False) else None,
+                    "peak_source": peaks["source"], "maps": f"[{B},2,{H},{W}] {'bf16' if es == 2 else 'fp32'}, {nsets} rotating sets"}
         del sets, fns
         torch.cuda.empty_cache()
     return out

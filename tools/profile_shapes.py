@@ -7,6 +7,7 @@ from octave_b200.train import TrainStep
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 config.set_compute_dtype("bf16"); config.nan_check = False
+config.overlap_wgrad = False        # one stream: per-launch event times are not stretched by concurrent kernels
 torch.manual_seed(0)
 net = OctaScribbleNet(torch.Size((B, 3, H, H)), torch.Size((B, 2, H, H)), True, False).cuda().train()
 ts = TrainStep(net)
