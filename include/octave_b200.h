@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OCTAVE_ABI_VERSION 3   /* 2: OctaveLossDesc.jsd_eps; extra outputs of head_bwd / bn_bwd_apply / space_to_depth */
+#define OCTAVE_ABI_VERSION 4   /* 4: octave_set_stats_prezeroed, octave_stream_capture_id; 2: OctaveLossDesc.jsd_eps; extra outputs of head_bwd / bn_bwd_apply / space_to_depth */
 int octave_abi_version(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int octave_sm_count(void);
@@ -36,6 +36,15 @@ unsigned long long octave_launch_count(void);
  * so two runs on the same inputs give bit-identical results.  Slower for the small layers; off for benchmarks. */
 void octave_set_deterministic(int on);
 int octave_get_deterministic(void);
+/* Statistics contract (process-wide, default off).  Off: every entry point that ACCUMULATES into a double-precision
+ * statistics output (`stats` of the conv forward, `sums` / `sums2` of the BatchNorm passes, `chan_sum` of
+ * octave_space_to_depth) zeroes it first with its own memset.  On: the caller guarantees those outputs are zero on entry
+ * (the Python host hands out slices of one pre-zeroed arena: ~250 memset nodes fewer per training step). */
+void octave_set_stats_prezeroed(int on);
+int octave_get_stats_prezeroed(void);
+/* id of the stream capture `stream` is part of, 0 if it is not capturing (an arena zeroed outside a capture must not be
+ * handed out inside it) */
+unsigned long long octave_stream_capture_id(void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K9 — fused loss kernel (forward statistics pass + gradient pass).

@@ -14,7 +14,8 @@
 
 // every kernel launch site is followed by exactly one OCT_CHECK_LAUNCH(): it also counts launches
 extern unsigned long long g_octave_launches;
-extern int g_octave_deterministic;   // octave_set_deterministic(): single-writer reductions, no fp32 atomics
+extern int g_octave_deterministic;
+extern int g_octave_stats_prezeroed;   // octave_set_deterministic(): single-writer reductions, no fp32 atomics
 #define OCT_CHECK_LAUNCH()                                   \
   do {                                                       \
     ++g_octave_launches;                                     \

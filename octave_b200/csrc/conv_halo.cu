@@ -760,7 +760,7 @@ extern "C" int octave_conv_halo_fwd(const OctaveConvDesc* d, const void* x, cons
   if (sms <= 0) sms = 148;
   long long grid = sms - sms % d->groups;   // a CTA keeps one group: its statistics columns never change
   if (grid > p.total_tiles) grid = p.total_tiles;
-  if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  if (stats && !g_octave_stats_prezeroed && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   // OCTAVE_HALO_TMA_EPI=1: plain outputs take the TMA-store epilogue.  Off by default: measured 5-25 % SLOWER than the
   // per-lane stores on the five halo shapes of the c2 step (the larger staging tile costs an input stage and the
   // K = 9 * cin_g mainloop is too short to hide a four-warp epilogue); kept as the measured alternative.

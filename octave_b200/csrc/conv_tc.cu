@@ -1013,7 +1013,7 @@ extern "C" int octave_conv_tc_fwd(const OctaveConvDesc* d, const void* x, const 
     // a CTA must always own the same output channels: grid is a multiple of n_tiles * groups
     if (ng > sms) return OCT_ERR_UNSUPPORTED;
     grid = (sms / ng) * ng;
-    if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+    if (!g_octave_stats_prezeroed && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   }
   if (grid > p.total_tiles) grid = stats ? ((p.total_tiles + ng - 1) / ng) * ng : p.total_tiles;
   if (stats && grid > p.total_tiles) grid = p.total_tiles;  // total_tiles is itself a multiple of ng

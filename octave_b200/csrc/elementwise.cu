@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(256, 2) splat_bn_bwd_apply_kernel(const Octave
 extern "C" int octave_chan_stats(const OctaveAct* x, double* sums, void* stream) {
   if (!view_ok(x) || !sums) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  if (!g_octave_stats_prezeroed && cudaMemsetAsync(sums, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   Geo g;
   DISPATCH_T(x->dtype, {
     auto fn = chan_stats_kernel<T>;
@@ -793,7 +793,7 @@ extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, 
   if (!view_ok(dy) || !view_ok(x) || !same_shape(dy, x) || !mean_invstd || !sums2) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, x))) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  if (!g_octave_stats_prezeroed && cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   const OctaveAct* m = mask ? mask : x;
   const int mmode = mask ? 1 : (relu_ab ? 2 : 0);
   int rc = OCT_OK;
@@ -953,7 +953,7 @@ extern "C" int octave_splat_bn_bwd(const OctaveAct* dout, const OctaveAct* omask
   if (omask && (!view_ok(omask) || !same_shape(omask, dout))) return OCT_ERR_INVALID;
   if (dout->C / 8 > 256) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * z->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  if (!g_octave_stats_prezeroed && cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * z->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   OctaveAct m = omask ? *omask : *dout;
   Geo g;
   DISPATCH_T(dout->dtype, {

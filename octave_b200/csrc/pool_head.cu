@@ -827,7 +827,7 @@ extern "C" int octave_space_to_depth(const OctaveAct* src, const OctaveAct* dst,
   const int G = src->C / 8;
   if (chan_sum && (G > 256 || 256 % G)) return OCT_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
-  if (chan_sum && cudaMemsetAsync(chan_sum, 0, sizeof(double) * src->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
+  if (chan_sum && !g_octave_stats_prezeroed && cudaMemsetAsync(chan_sum, 0, sizeof(double) * src->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   const long long total = (long long)dst->B * dst->H * dst->W * 4 * G;
   int grid = grid_for((total + 3) / 4, 256);
   if (chan_sum && grid > 148 * 8) grid = 148 * 8;    // bounds the atomics per channel

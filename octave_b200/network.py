@@ -557,7 +557,7 @@ class ResnestUNet(nn.Module):
             B, _, H, W = x.shape
             xs = Act.zeros(B, H // 2, W // 2, 32, torch.bfloat16, x.device)
             ops.nchw_to_s2d(x, xs, 8, 0)
-            s0 = torch.empty(2 * seq[0].out_channels, dtype=torch.float64, device=x.device) if tr else None
+            s0 = ops.zeros_f64(2 * seq[0].out_channels, x.device) if tr else None
             z0 = ops.conv4x4s2_tc_fwd(xs, ops.pack_weight_s2d(seq[0].weight.detach(), None, 0, 8), None, seq[0].out_channels,
                                       H // 2, W // 2, 0, stats=s0)
             x = xs

@@ -3,6 +3,7 @@ channel view of a torch buffer; torch is used for device memory and streams only
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -156,12 +157,46 @@ lib.octave_affine_gap_ws_bytes.argtypes = [_A]
 lib.octave_pack_job_blocks.restype = C.c_int64
 lib.octave_pack_job_blocks.argtypes = [C.c_int32] * 5
 
+lib.octave_set_stats_prezeroed.restype = None
+lib.octave_set_stats_prezeroed.argtypes = [C.c_int]
+lib.octave_stream_capture_id.restype = C.c_ulonglong
+lib.octave_stream_capture_id.argtypes = [_vp]
+
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+
+# --- pre-zeroed statistics arena --------------------------------------------------------------------
+# The double-precision statistics outputs (conv forward `stats`, BatchNorm `sums` / `sums2`, space-to-depth `chan_sum`)
+# are accumulated with atomics, so they must start at zero: ~250 per training step, each a memset node of a few KB in
+# front of its kernel.  They are slices of ONE chunk zeroed by one memset instead (include/octave_b200.h:
+# octave_set_stats_prezeroed).  A chunk belongs to (device, stream, capture): a slice is only ever used on the stream that
+# zeroed the chunk, and a chunk zeroed outside a graph capture is never handed out inside it (a replay would find the
+# sums of the previous replay), nor one capture's chunk in the next.  Exhausted chunks stay alive through their slices.
+_ZCHUNK = 1 << 16                  # doubles per chunk (512 KB)
+_zero_pool = {}                    # (device index, stream handle) -> [capture id, chunk, next free offset]
+_PREZERO = os.environ.get("OCTAVE_STATS_ARENA", "1") != "0"      # 0: per-call memsets (A/B switch)
+lib.octave_set_stats_prezeroed(1 if _PREZERO else 0)
+
+
+def zeros_f64(n: int, device) -> torch.Tensor:
+    if not _PREZERO:
+        return torch.empty(n, dtype=torch.float64, device=device)
+    sp = stream_ptr()
+    cap = int(lib.octave_stream_capture_id(sp))
+    key = (device.index, sp)
+    ent = _zero_pool.get(key)
+    n_al = (n + 15) & ~15          # slices start on 128-byte lines
+    if ent is None or ent[0] != cap or ent[2] + n_al > ent[1].numel():
+        ent = [cap, torch.zeros(max(_ZCHUNK, n_al), dtype=torch.float64, device=device), 0]
+        _zero_pool[key] = ent
+    out = ent[1][ent[2]:ent[2] + n]
+    ent[2] += n_al
+    return out
+
 
 
 # --- BatchNorm -------------------------------------------------------------------------------------
 def chan_stats(x: Act) -> torch.Tensor:
-    sums = torch.empty(2 * x.C, dtype=torch.float64, device=x.device)
+    sums = zeros_f64(2 * x.C, x.device)
     _chk("octave_chan_stats", lib.octave_chan_stats(_ref(x), sums.data_ptr(), stream_ptr()))
     return sums
 
@@ -204,7 +239,7 @@ def bn_bwd(dy: Act, mask: Optional[Act], x: Act, mi: torch.Tensor, gamma: Option
            out: Optional[Act] = None, relu_ab: Optional[torch.Tensor] = None, dmasked: Optional[Act] = None):
     """-> dx, dgamma, dbeta.  relu_ab (with mask None): recompute this BN's own ReLU mask from x instead of reading it.
     dmasked: also receives dy * (mask > 0) (the residual branch's gradient)."""
-    sums2 = torch.empty(2 * x.C, dtype=torch.float64, device=x.device)
+    sums2 = zeros_f64(2 * x.C, x.device)
     _chk("octave_bn_bwd_reduce", lib.octave_bn_bwd_reduce(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), sums2.data_ptr(), stream_ptr()))
     dx = out if out is not None else x.like()
     dgamma = torch.empty(x.C, dtype=torch.float32, device=x.device)
@@ -253,7 +288,7 @@ def splat_bn_bwd(dout: Act, omask: Optional[Act], att: torch.Tensor, dgap: Optio
                  ab: torch.Tensor, mi: torch.Tensor, gamma: torch.Tensor, training: bool):
     """Fused backward of the split-attention combine + bn0 + ReLU -> dz [B,H,W,2C], dgamma, dbeta (see the C header)."""
     dz = z.like()
-    sums2 = torch.empty(2 * z.C, dtype=torch.float64, device=z.device)
+    sums2 = zeros_f64(2 * z.C, z.device)
     dg = torch.empty(z.C, dtype=torch.float32, device=z.device)
     db = torch.empty(z.C, dtype=torch.float32, device=z.device)
     _chk("octave_splat_bn_bwd", lib.octave_splat_bn_bwd(_ref(dout), _ref(omask), att.data_ptr(), _p(dgap), gap_scale, _ref(z), ab.data_ptr(),
@@ -411,7 +446,7 @@ def space_to_depth(src: Act, H: int, W: int, want_chan_sum: bool = False):
     dst = Act.empty(src.B, H, W, 4 * src.C, src.dtype, src.device)
     G = src.C // 8
     fused = want_chan_sum and G <= 256 and 256 % G == 0
-    cs = torch.empty(src.C, dtype=torch.float64, device=src.device) if fused else None
+    cs = zeros_f64(src.C, src.device) if fused else None
     _chk("octave_space_to_depth", lib.octave_space_to_depth(_ref(src), _ref(dst), _p(cs), stream_ptr()))
     if want_chan_sum:
         return dst, (cs if fused else chan_stats(src)[:src.C])
@@ -570,7 +605,7 @@ def conv_fwd(x: Act, spec: ConvSpec, out: Optional[Act] = None, act: int = 0, wa
     stats = None
     if spec.tc_ok(x.dtype) and act in (0, 1):
         if want_stats and not spec.transposed:
-            stats = torch.empty(2 * spec.cout, dtype=torch.float64, device=x.device)
+            stats = zeros_f64(2 * spec.cout, x.device)
         if spec.transposed:
             d = _conv_desc(x.B, x.H, x.W, spec.cin, spec.cout, 1, 1, 1, 0, x, out, out.H, out.W, mode=_lib.CONV_MODE_CONVT, act=act)
             wp = spec.pack(_lib_pack.CONVT_FWD)

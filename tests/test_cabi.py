@@ -12,7 +12,7 @@ def test_every_declared_symbol_is_exported():
 
 
 def test_abi_version_and_struct_size():
-    assert _lib.lib.octave_abi_version() == 3
+    assert _lib.lib.octave_abi_version() == 4
     # OctaveLossDesc: 7 int32 + 5 + 5 int32 + 4 float + 3 float + 2 int32 + 1 float (jsd_eps) = 27 words
     assert ctypes.sizeof(_lib.LossDesc) == 27 * 4
 
