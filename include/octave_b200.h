@@ -329,6 +329,9 @@ int octave_rsoftmax_bwd(const float* datt, const float* att, int32_t B, int32_t 
 /* Space-to-depth formulation of the discriminator's 4x4 stride-2 pad-1 convs (discriminator/blocks.py:46-50,91-109):
  * with X'[h'][w'][(i*2+j)*qs + c] = X[2h'+i][2w'+j][c] the conv becomes a 3x3 stride-1 pad-1 conv over 4*qs channels
  * (tap dh' in {-1,0,1}, parity i: kh = 2dh'+i+1 if 0<=kh<4), which runs on the tcgen05 kernel. */
+/* Writes channels [coff, qs) of every quadrant of dst: the C source channels (+ noise[h][w], clipped to [0,1] if clip),
+ * then zeros; quadrant pixels outside the source (odd H / W) are written as zeros.  With coff = 0 and dst->C = 4*qs the
+ * whole tensor is written: no memset needed. */
 int octave_nchw_to_s2d(const float* src, int32_t B, int32_t C, int32_t H, int32_t W, const float* noise, int32_t clip,
                        const OctaveAct* dst /* [B][ceil(H/2)][ceil(W/2)][4*qs] */, int32_t qs, int32_t coff, void* stream);
 /* dst[b][c][h][w] = src quadrant channel coff+c (optionally masked by 1[0 <= x+noise <= 1], the clip backward) */
@@ -417,6 +420,23 @@ int octave_augment(uint64_t seed, int32_t B, int32_t C, int32_t Cy, int32_t H, i
  * W: weight_orig as [rows][cols] fp32, rows <= 1024; out2: device float[2] = sigma, 1/sigma. */
 int octave_spectral_sigma(const float* W, int32_t rows, int32_t cols, float* u, float* v, int32_t training, float eps,
                           float* out2, void* stream);
+/* The same for every spectral-norm layer of one critic call in ONE launch (the layers' power iterations depend on the
+ * weights only).  jobs: host array; out: device float[2 + rows + cols] = sigma, 1/sigma, then the u and the v this call
+ * leaves behind (a snapshot for the backward pass: later calls keep iterating u / v in place). */
+#define OCTAVE_SN_MAX_JOBS 8
+typedef struct OctaveSnJob {
+  const float* W;
+  float* u;
+  float* v;
+  float* out;
+  int32_t rows, cols;
+} OctaveSnJob;
+int octave_spectral_sigma_multi(const OctaveSnJob* jobs, int32_t n_jobs, int32_t training, float eps, void* stream);
+/* Weight gradient through the normalisation W = W_orig / sigma, sigma = u^T W_orig v with u, v constants (what autograd
+ * does for torch.nn.utils.spectral_norm): out (+)= dW / sigma - <dW, W_orig> / sigma^2 * u v^T.  dw, w_orig, out:
+ * [rows][cols] fp32; sigma: device float; parts: device float[64] scratch.  Two launches, fixed summation order. */
+int octave_spectral_wgrad(const float* dw, const float* w_orig, const float* u, const float* v, const float* sigma,
+                          int32_t rows, int32_t cols, float* parts, float* out, int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,20 +7,50 @@
 
 namespace {
 
+// One thread per (destination pixel, quadrant): writes channels [coff, qs) of its quadrant — the C source channels (+ noise,
+// clipped), then zeros — so the caller's pad channels need no memset; quadrant pixels outside the source (odd H / W) are
+// written as zeros.  Four neighbouring threads fill one destination row: coalesced stores, source rows read with stride 2.
 template <typename T>
 __global__ void nchw_to_s2d_kernel(const float* src, int B, int C, int H, int W, const float* noise, int clip, OctaveAct dst,
                                    int qs, int coff) {
-  const long long hw = (long long)H * W, total = (long long)B * C * hw;
+  const long long total = (long long)B * dst.H * dst.W * 4;
+  const int nw = qs - coff;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long q = idx % hw;
-    const int c = (int)((idx / hw) % C);
-    const long long n = idx / (hw * C);
-    const int h = (int)(q / W), w = (int)(q - (long long)h * W);
-    float v = src[idx];
-    if (noise) v += noise[q];
-    if (clip) v = fminf(fmaxf(v, 0.f), 1.f);
-    const long long pix = (n * dst.H + (h >> 1)) * dst.W + (w >> 1);
-    reinterpret_cast<T*>(dst.data)[pix * dst.ld + dst.coff + ((h & 1) * 2 + (w & 1)) * qs + coff + c] = from_f<T>(v);
+    const int q = (int)(idx & 3);
+    const long long pix = idx >> 2;
+    const int w2 = (int)(pix % dst.W);
+    const int h2 = (int)((pix / dst.W) % dst.H);
+    const long long n = pix / ((long long)dst.W * dst.H);
+    const int h = 2 * h2 + (q >> 1), w = 2 * w2 + (q & 1);
+    const bool in = h < H && w < W;
+    const float nz = (in && noise) ? noise[(long long)h * W + w] : 0.f;
+    T* o = reinterpret_cast<T*>(dst.data) + pix * dst.ld + dst.coff + q * qs + coff;
+    const float* sp = src + ((n * C) * H + h) * (long long)W + w;
+    if (sizeof(T) == 2 && nw == 8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      float f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v = 0.f;
+        if (in && c < C) {
+          v = sp[(long long)c * H * W] + nz;
+          if (clip) v = fminf(fmaxf(v, 0.f), 1.f);
+        }
+        f[c] = v;
+      }
+      uint4 pk;
+      pk.x = bf16x2_pack(f[0], f[1]); pk.y = bf16x2_pack(f[2], f[3]);
+      pk.z = bf16x2_pack(f[4], f[5]); pk.w = bf16x2_pack(f[6], f[7]);
+      *reinterpret_cast<uint4*>(o) = pk;
+    } else {
+      for (int c = 0; c < nw; ++c) {
+        float v = 0.f;
+        if (in && c < C) {
+          v = sp[(long long)c * H * W] + nz;
+          if (clip) v = fminf(fmaxf(v, 0.f), 1.f);
+        }
+        o[c] = from_f<T>(v);
+      }
+    }
   }
 }
 
@@ -152,7 +182,7 @@ extern "C" int octave_nchw_to_s2d(const float* src, int32_t B, int32_t C, int32_
                                   const OctaveAct* dst, int32_t qs, int32_t coff, void* stream) {
   if (!src || !dst || !dst->data || B <= 0 || C <= 0 || qs <= 0 || coff + C > qs) return OCT_ERR_INVALID;
   if (dst->H != (H + 1) / 2 || dst->W != (W + 1) / 2 || dst->C < 4 * qs || dst->B != B) return OCT_ERR_INVALID;
-  const long long total = (long long)B * C * H * W;
+  const long long total = (long long)B * dst->H * dst->W * 4;
   if (dst->dtype == OCT_DTYPE_F32)
     nchw_to_s2d_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, B, C, H, W, noise, clip, *dst, qs, coff);
   else
@@ -219,9 +249,10 @@ extern "C" int octave_rowdot_bwd(const OctaveAct* x, const float* w, const float
 // summation order (no atomics): the critic's weights are bit-reproducible from run to run.
 namespace {
 constexpr int kSnThreads = 1024;
-__global__ void __launch_bounds__(kSnThreads) spectral_sigma_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ u,
-                                                                    float* __restrict__ v, int training, float eps,
-                                                                    float* __restrict__ out /* sigma, 1/sigma */) {
+__device__ __forceinline__ void spectral_sigma_body(const float* __restrict__ W, int rows, int cols, float* __restrict__ u,
+                                                    float* __restrict__ v, int training, float eps,
+                                                    float* __restrict__ out /* sigma, 1/sigma */,
+                                                    float* __restrict__ snap_u, float* __restrict__ snap_v) {
   extern __shared__ float sm[];
   float* us = sm;                 // [rows]
   float* vs = sm + rows;          // [cols]
@@ -281,12 +312,102 @@ __global__ void __launch_bounds__(kSnThreads) spectral_sigma_kernel(const float*
       for (int j = tid; j < rows; j += kSnThreads) u[j] = part[j] / nu;
     }
     sigma = nw2 / nu;                // u . (W v) with u = W v / nu
+    if (snap_u) {
+      for (int j = tid; j < rows; j += kSnThreads) snap_u[j] = part[j] / nu;
+    }
   } else {
     sigma = block_total(dot_uw);
+    if (snap_u) {
+      for (int j = tid; j < rows; j += kSnThreads) snap_u[j] = us[j];
+    }
+  }
+  if (snap_v) {
+    for (int k = tid; k < cols; k += kSnThreads) snap_v[k] = vs[k];
   }
   if (tid == 0) { out[0] = sigma; out[1] = 1.f / sigma; }
 }
+
+__global__ void __launch_bounds__(kSnThreads) spectral_sigma_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ u,
+                                                                    float* __restrict__ v, int training, float eps,
+                                                                    float* __restrict__ out) {
+  spectral_sigma_body(W, rows, cols, u, v, training, eps, out, nullptr, nullptr);
+}
+
+// every spectral-norm layer of one critic call in ONE launch (one block per layer; the layers' power iterations are
+// independent of each other and of the activations), leaving a snapshot of the u / v this call used for the backward pass
+struct SnJobs { OctaveSnJob j[OCTAVE_SN_MAX_JOBS]; };
+__global__ void __launch_bounds__(kSnThreads) spectral_sigma_multi_kernel(const SnJobs jobs, int training, float eps) {
+  const OctaveSnJob& jb = jobs.j[blockIdx.x];
+  spectral_sigma_body(jb.W, jb.rows, jb.cols, jb.u, jb.v, training, eps, jb.out, jb.out + 2, jb.out + 2 + jb.rows);
+}
+
+// ---- spectral norm, weight gradient.  W = W_orig / sigma with sigma = u^T W_orig v (u, v constants of the backward pass):
+//   dW_orig = dW / sigma - <dW, W_orig> / sigma^2 * u v^T
+// Two launches, no atomics: fixed-order partial dot products, then every block adds the partials in the same order.
+constexpr int kSwParts = 64;
+__global__ void __launch_bounds__(256) spectral_wgrad_dot_kernel(const float* __restrict__ dw, const float* __restrict__ wo, long long n,
+                                                                 float* __restrict__ parts) {
+  __shared__ float red[8];
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
+  float acc = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += 256) acc += dw[i] * wo[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    parts[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) spectral_wgrad_apply_kernel(const float* __restrict__ dw, const float* __restrict__ u,
+                                                                   const float* __restrict__ v, const float* __restrict__ sigma1,
+                                                                   const float* __restrict__ parts, int nparts, int rows, int cols,
+                                                                   float* __restrict__ out, int accumulate) {
+  float dot = 0.f;
+  for (int i = 0; i < nparts; ++i) dot += parts[i];
+  const float sigma = sigma1[0];
+  const float coef = dot / (sigma * sigma);
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    const float g = dw[i] / sigma - coef * (u[r] * v[c]);
+    out[i] = accumulate ? out[i] + g : g;
+  }
+}
 }  // namespace
+
+extern "C" int octave_spectral_sigma_multi(const OctaveSnJob* jobs, int32_t n_jobs, int32_t training, float eps, void* stream) {
+  if (!jobs || n_jobs <= 0 || n_jobs > OCTAVE_SN_MAX_JOBS) return OCT_ERR_INVALID;
+  SnJobs js;
+  size_t smem = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const OctaveSnJob& jb = jobs[i];
+    if (!jb.W || !jb.u || !jb.v || !jb.out || jb.rows <= 0 || jb.cols <= 0) return OCT_ERR_INVALID;
+    if (jb.rows > 1024 || jb.cols > 8192) return OCT_ERR_UNSUPPORTED;
+    js.j[i] = jb;
+    const size_t need = (size_t)(jb.rows + jb.cols + 1024) * sizeof(float);
+    smem = need > smem ? need : smem;
+  }
+  spectral_sigma_multi_kernel<<<n_jobs, kSnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(js, training, eps);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_spectral_wgrad(const float* dw, const float* w_orig, const float* u, const float* v, const float* sigma,
+                                     int32_t rows, int32_t cols, float* parts, float* out, int32_t accumulate, void* stream) {
+  if (!dw || !w_orig || !u || !v || !sigma || !parts || !out || rows <= 0 || cols <= 0) return OCT_ERR_INVALID;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = (long long)rows * cols;
+  int nparts = (int)((n + 4095) / 4096);
+  nparts = nparts < 1 ? 1 : (nparts > kSwParts ? kSwParts : nparts);
+  spectral_wgrad_dot_kernel<<<nparts, 256, 0, s>>>(dw, w_orig, n, parts);
+  OCT_CHECK_LAUNCH();
+  spectral_wgrad_apply_kernel<<<grid_for(n, 256), 256, 0, s>>>(dw, u, v, sigma, parts, nparts, rows, cols, out, accumulate);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
 
 extern "C" int octave_spectral_sigma(const float* W, int32_t rows, int32_t cols, float* u, float* v, int32_t training, float eps,
                                      float* out2, void* stream) {

@@ -210,6 +210,36 @@ class DiscriminatorBlock(nn.Module):
         self._last_inv_sigma = (1.0 / sigma).reshape(1).float()
         return (w.float() / sigma if need_w else None), sigma, u.clone(), v.clone()
 
+    @staticmethod
+    def _spectral_wgrad(dwsn: Tensor, sn: nn.Module, sigma: Tensor, u: Tensor, v: Tensor) -> Tensor:
+        """W = W_orig / sigma, sigma = u^T W_orig v (u, v constants): dW_orig = dW/sigma - <dW, W_orig>/sigma^2 * u v^T."""
+        wo = sn.weight_orig.detach()
+        if (dwsn.is_cuda and dwsn.dtype == torch.float32 and wo.dtype == torch.float32 and dwsn.is_contiguous() and wo.is_contiguous()
+                and dwsn.shape == wo.shape and u.dtype == torch.float32 and v.dtype == torch.float32 and sigma.dtype == torch.float32
+                and u.is_contiguous() and v.is_contiguous()):
+            return ops.spectral_wgrad(dwsn, wo, u, v, sigma)           # two launches instead of nine torch ops
+        wo = wo.float()
+        coef = (dwsn * wo).sum() / (sigma * sigma)
+        uv = (u.reshape(-1, 1) * v.reshape(1, -1)).reshape(wo.shape)
+        return dwsn / sigma - coef * uv
+
+    def _spectral_all(self):
+        """Every spectral-norm layer of this critic call at once -> per level (sigma, inv_sigma, u, v): ONE launch instead of
+        one per level in front of its conv (the power iterations depend on the weights only), u / v snapshots included."""
+        sns = [self.spectral_dict[f'spectral_{i}'][0] for i in range(self.depth)]
+        ws = [sn.weight_orig.detach().reshape(sn.weight_orig.shape[0], -1) for sn in sns]
+        ok = 0 < len(sns) <= ops.SN_MAX_JOBS and all(
+            w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[0] <= 1024 and w.shape[1] <= 8192
+            and sn.weight_u.dtype == torch.float32 and sn.weight_v.dtype == torch.float32 for w, sn in zip(ws, sns))
+        if not ok:
+            return None
+        outs = ops.spectral_sigma_multi(ws, [sn.weight_u for sn in sns], [sn.weight_v for sn in sns], self.training)
+        res = []
+        for w, o in zip(ws, outs):
+            r, c = w.shape
+            res.append((o[0], o[1:2], o[2:2 + r], o[2 + r:2 + r + c]))
+        return res
+
     def _padded_squeeze(self, i: int, rows: int):
         """13-row squeeze conv weight / bias zero-padded to `rows` output channels for the tensor-core kernels; rebuilt
         only when the parameter changes (once per optimiser step, not once per critic call)."""
@@ -270,7 +300,7 @@ class DiscriminatorBlock(nn.Module):
         noise_dev, clip, flip = self._noise_and_flip(dev)
         tape = {"tc": True}
         y0c = y0.detach().contiguous().float()
-        X0 = Act.zeros(B, (H + 1) // 2, (W + 1) // 2, 32, dt, dev)                         # quadrant stride 8
+        X0 = Act.empty(B, (H + 1) // 2, (W + 1) // 2, 32, dt, dev)                         # quadrant stride 8; nchw_to_s2d writes every channel
         ops.nchw_to_s2d(y0c, X0, 8, 0, noise_dev, clip)                                   # blocks.py:149-154
         c0 = self._conv0
         nf = c0.out_channels
@@ -279,6 +309,7 @@ class DiscriminatorBlock(nn.Module):
                                  ops.ACT_LEAKY)                                           # :46-50
         tape["in"] = (y0c, noise_dev, clip, X0, s, (H, W))
         levels = []
+        sn_all = self._spectral_all()
         for i in range(self.depth):
             sq = self.squeeze_dict[f'squeeze_{i}'][0]
             sn = self.spectral_dict[f'spectral_{i}'][0]
@@ -286,12 +317,17 @@ class DiscriminatorBlock(nn.Module):
             if yi.shape[2] != s.H or yi.shape[3] != s.W:
                 raise Exception(f'Exception raised in depth = {i}')
             h, w = s.H, s.W
-            catS = Act.zeros(B, (h + 1) // 2, (w + 1) // 2, 64, dt, dev)                   # quadrant stride 16: 13 + Cin (+pad)
+            # quadrant stride 16: 13 + Cin (+pad).  Even sizes: the squeeze conv and nchw_to_s2d write every channel of every
+            # pixel; odd sizes leave the quadrant pixels outside the map to the memset
+            catS = (Act.zeros if (h | w) & 1 else Act.empty)(B, (h + 1) // 2, (w + 1) // 2, 64, dt, dev)
             spec_sq, b16 = self._padded_squeeze(i, 16)
             ops.conv1x1_tc_s2d_store(s, spec_sq.pack(0), b16, 16, catS, 16, ops.ACT_SIGMOID)   # :121
             ops.nchw_to_s2d(yi.detach(), catS, 16, 13)                                    # :122 (overwrites pad channels 13,14)
-            _, sigma, u, v = self._spectral_weight(sn, need_w=False)
-            inv_sigma = self._last_inv_sigma
+            if sn_all is not None:
+                sigma, inv_sigma, u, v = sn_all[i]
+            else:
+                _, sigma, u, v = self._spectral_weight(sn, need_w=False)
+                inv_sigma = self._last_inv_sigma
             wo_ = sn.weight_orig.detach()
             ho, wo = (h + 2 - 4) // 2 + 1, (w + 2 - 4) // 2 + 1
             s_next = ops.conv4x4s2_tc_fwd(catS, ops.pack_weight_s2d(wo_, inv_sigma, 0, 16), sn.bias.detach().float(),
@@ -333,10 +369,7 @@ class DiscriminatorBlock(nn.Module):
             dz = ops.act_bwd(s_out, ds, ops.ACT_TANH, out=ds)
             if need_params:
                 dwsn = ops.conv4x4s2_tc_wgrad(catS, dz, 13 + Cin, 16)
-                wo = sn.weight_orig.detach().float()
-                coef = (dwsn * wo).sum() / (sigma * sigma)
-                uv = (u.reshape(-1, 1) * v.reshape(1, -1)).reshape(wo.shape)
-                _acc(grads, sn.weight_orig, dwsn / sigma - coef * uv)
+                _acc(grads, sn.weight_orig, self._spectral_wgrad(dwsn, sn, sigma, u, v))
                 _acc(grads, sn.bias, ops.chan_stats(dz)[:dz.C].float())
             dcatS = ops.conv4x4s2_tc_dgrad(dz, ops.pack_weight_s2d(sn.weight_orig.detach(), inv_sigma, 1, 16), catS.H, catS.W, 64)
             if need_maps:
@@ -436,11 +469,7 @@ class DiscriminatorBlock(nn.Module):
             dz = ops.act_bwd(s_out, ds, ops.ACT_TANH, out=ds)
             if need_params:
                 dwsn, dbsn = ops.conv_wgrad(catv, dz, spec_sn)
-                wo = sn.weight_orig.detach().float()
-                # W = W_orig / sigma, sigma = u^T W_orig v (u, v constants): dW_orig = dW/sigma - <dW, W_orig>/sigma^2 * u v^T
-                coef = (dwsn * wo).sum() / (sigma * sigma)
-                uv = (u.reshape(-1, 1) * v.reshape(1, -1)).reshape(wo.shape)
-                _acc(grads, sn.weight_orig, dwsn / sigma - coef * uv)
+                _acc(grads, sn.weight_orig, self._spectral_wgrad(dwsn, sn, sigma, u, v))
                 _acc(grads, sn.bias, dbsn)
             dcat = Act.zeros(cat.B, cat.H, cat.W, 16, cat.dtype, cat.device)
             dcatv = dcat.slice(0, 13 + Cin)

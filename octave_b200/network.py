@@ -555,7 +555,7 @@ class ResnestUNet(nn.Module):
             z0 = ops.conv_fwd(x, _spec(seq[0]))
         else:
             B, _, H, W = x.shape
-            xs = Act.zeros(B, H // 2, W // 2, 32, torch.bfloat16, x.device)
+            xs = Act.empty(B, H // 2, W // 2, 32, torch.bfloat16, x.device)      # nchw_to_s2d writes every channel (pads as zeros)
             ops.nchw_to_s2d(x, xs, 8, 0)
             s0 = ops.zeros_f64(2 * seq[0].out_channels, x.device) if tr else None
             z0 = ops.conv4x4s2_tc_fwd(xs, ops.pack_weight_s2d(seq[0].weight.detach(), None, 0, 8), None, seq[0].out_channels,

@@ -152,6 +152,15 @@ for _n, _a in _sigs.items():
     getattr(lib, _n).argtypes = _a
 lib.octave_spectral_sigma.restype = C.c_int
 lib.octave_spectral_sigma.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_float, _vp, _vp]
+class OctaveSnJob(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32)]
+
+
+SN_MAX_JOBS = 8
+lib.octave_spectral_sigma_multi.restype = C.c_int
+lib.octave_spectral_sigma_multi.argtypes = [C.POINTER(OctaveSnJob), C.c_int32, C.c_int32, C.c_float, _vp]
+lib.octave_spectral_wgrad.restype = C.c_int
+lib.octave_spectral_wgrad.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp]
 lib.octave_affine_gap_ws_bytes.restype = C.c_size_t
 lib.octave_affine_gap_ws_bytes.argtypes = [_A]
 lib.octave_pack_job_blocks.restype = C.c_int64
@@ -779,4 +788,34 @@ def spectral_sigma(w2d: torch.Tensor, u: torch.Tensor, v: torch.Tensor, training
     out = torch.empty(2, dtype=torch.float32, device=w2d.device)
     _chk("octave_spectral_sigma", lib.octave_spectral_sigma(w2d.data_ptr(), w2d.shape[0], w2d.shape[1], u.data_ptr(), v.data_ptr(),
                                                             int(training), eps, out.data_ptr(), stream_ptr()))
+    return out
+
+
+def spectral_sigma_multi(ws, us, vs, training: bool, eps: float = 1e-12):
+    """The power iteration + sigma of every spectral-norm layer of one critic call in ONE launch.  ws: [rows, cols] fp32
+    matrices; us / vs: the layers' weight_u / weight_v (updated in place when training).  -> per layer a float32 tensor
+    [2 + rows + cols] = sigma, 1/sigma, snapshot of u, snapshot of v (what the backward pass of THIS call needs)."""
+    n = len(ws)
+    assert 0 < n <= SN_MAX_JOBS
+    sizes = [2 + w.shape[0] + w.shape[1] for w in ws]
+    offs = [0]
+    for sz in sizes:
+        offs.append(offs[-1] + ((sz + 3) & ~3))
+    buf = torch.empty(offs[-1], dtype=torch.float32, device=ws[0].device)
+    outs = [buf[offs[i]:offs[i] + sizes[i]] for i in range(n)]
+    jobs = (OctaveSnJob * n)()
+    for i in range(n):
+        jobs[i] = OctaveSnJob(ws[i].data_ptr(), us[i].data_ptr(), vs[i].data_ptr(), outs[i].data_ptr(), ws[i].shape[0], ws[i].shape[1])
+    _chk("octave_spectral_sigma_multi", lib.octave_spectral_sigma_multi(jobs, n, int(training), eps, stream_ptr()))
+    return outs
+
+
+def spectral_wgrad(dw: torch.Tensor, w_orig: torch.Tensor, u: torch.Tensor, v: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+    """dW_orig = dW / sigma - <dW, W_orig> / sigma^2 * u v^T (spectral norm backward with u, v constant); fp32, shape of W_orig."""
+    rows = w_orig.shape[0]
+    cols = w_orig.numel() // rows
+    out = torch.empty_like(w_orig)
+    parts = torch.empty(64, dtype=torch.float32, device=dw.device)
+    _chk("octave_spectral_wgrad", lib.octave_spectral_wgrad(dw.data_ptr(), w_orig.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
+                                                            rows, cols, parts.data_ptr(), out.data_ptr(), 0, stream_ptr()))
     return out
