@@ -379,7 +379,7 @@ def run_gpu(args):
     config.nan_check = False
     torch.manual_seed(0)
     net = OctaScribbleNet(torch.Size((B, 3, H, W)), torch.Size((B, 2, H, W)), True, False).to(dev).train()
-    ts = TrainStep(net, distributed=world > 1, bucket_bytes=args.bucket_mb << 20)
+    ts = TrainStep(net, distributed=world > 1, bucket_bytes=args.bucket_mb << 20, grad_dtype=None if args.grad_dtype == "auto" else args.grad_dtype)
     # synthetic batches in pinned host memory (different data per rank = weak scaling)
     nb = 2
     host = []
@@ -558,6 +558,8 @@ if __name__ == "__main__":
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: cap the number of timed steps so that the run fits this many seconds (0 = no cap)")
     ap.add_argument("--comparator", action="store_true", help="also time the reference arithmetic on stock torch CUDA ops (cuDNN) on this GPU")
     ap.add_argument("--bucket-mb", type=int, default=25, help="gradient all-reduce bucket size (data-parallel runs)")
+    ap.add_argument("--grad-dtype", default="auto", choices=["auto", "fp32", "bf16"],
+                    help="dtype of the all-reduced gradient buckets (auto: bf16 with --dtype bf16, fp32 otherwise)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0, help="cap of NCCL CTAs per collective (0 = NCCL default; measured at N=2: "
                     "default 47.2 ms/step, cap 8 48.0, one unbucketed all-reduce 48.0 - profiles/ddp_ab_r02.log)")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~1100 kernels of a step eagerly instead of replaying one CUDA graph")

@@ -396,6 +396,21 @@ int64_t octave_optim_job_blocks(int64_t n);
 int octave_optim_multi(const OctaveOptJob* jobs_device, int32_t n_jobs, int64_t total_blocks, const OctaveOptHyper* hyper,
                        void* stream);
 
+/* Data-parallel gradient buckets in bf16 (half the all-reduce bytes).  pack: flat[flat_off + i] = bf16(g[i]) for every
+ * job — the gather-and-cast of a bucket's fp32 gradient tensors into one flat bf16 buffer; unpack: g[i] = float(flat[..]),
+ * the averaged values written back into the gradient tensors.  jobs: HOST array, at most OCTAVE_GRAD_MAX_JOBS per call
+ * (passed to the kernel by value: no table upload, capture-safe); flat_off in elements, multiples of 8;
+ * block_start = sum of octave_optim_job_blocks(n) of the jobs before. */
+#define OCTAVE_GRAD_MAX_JOBS 128
+typedef struct OctaveGradJob {
+  float* g;
+  int64_t flat_off;
+  int32_t n;
+  int32_t block_start;
+} OctaveGradJob;
+int octave_grad_pack_bf16(const OctaveGradJob* jobs, int32_t n_jobs, void* flat_bf16, void* stream);
+int octave_grad_unpack_bf16(const OctaveGradJob* jobs, int32_t n_jobs, const void* flat_bf16, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * On-GPU input pipeline.  The reference ships no data loader (README.md:39-47); the synthetic OCTA model
  * is the one of SURVEY.md 8d.  Counter-based random numbers: a batch is a pure function of `seed`.

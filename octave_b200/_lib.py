@@ -141,3 +141,16 @@ lib.octave_conv_tc_wgrad_supported.restype = C.c_int
 lib.octave_conv_tc_wgrad_supported.argtypes = [C.POINTER(ConvDesc)]
 lib.octave_conv_tc_wgrad.restype = C.c_int
 lib.octave_conv_tc_wgrad.argtypes = [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]
+
+
+# ---- bf16 gradient buckets (include/octave_b200.h: octave_grad_pack_bf16 / octave_grad_unpack_bf16) ----
+class OctaveGradJob(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("flat_off", C.c_int64), ("n", C.c_int32), ("block_start", C.c_int32)]
+
+
+GRAD_MAX_JOBS = 128
+lib.octave_optim_job_blocks.restype = C.c_int64
+lib.octave_optim_job_blocks.argtypes = [C.c_int64]
+for _n in ("octave_grad_pack_bf16", "octave_grad_unpack_bf16"):
+    getattr(lib, _n).restype = C.c_int
+    getattr(lib, _n).argtypes = [C.POINTER(OctaveGradJob), C.c_int32, C.c_void_p, C.c_void_p]

@@ -70,7 +70,71 @@ __global__ void __launch_bounds__(256) optim_multi_kernel(const OctaveOptJob* __
   }
 }
 
+// ---- bf16 gradient buckets: gather-and-cast / scatter-and-cast of a bucket's tensors, the job table passed by value
+struct GradJobs { OctaveGradJob j[OCTAVE_GRAD_MAX_JOBS]; int n; };
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) grad_bucket_kernel(const __grid_constant__ GradJobs jobs, bf16* __restrict__ flat) {
+  int lo = 0, hi = jobs.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs.j[mid].block_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const OctaveGradJob& j = jobs.j[lo];
+  const long long base = ((long long)blockIdx.x - j.block_start) * kOptElemsPerBlock;
+  float* __restrict__ g = j.g;
+  bf16* __restrict__ f = flat + j.flat_off;
+  const int n = j.n;
+  if ((n % 8 == 0) && (reinterpret_cast<uintptr_t>(g) % 16 == 0)) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = base + ((long long)u * 256 + threadIdx.x) * 8;
+      if (i >= n) break;
+      if (PACK) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(g + i)), b = __ldg(reinterpret_cast<const float4*>(g + i + 4));
+        uint4 pk;
+        pk.x = bf16x2_pack(a.x, a.y); pk.y = bf16x2_pack(a.z, a.w); pk.z = bf16x2_pack(b.x, b.y); pk.w = bf16x2_pack(b.z, b.w);
+        *reinterpret_cast<uint4*>(f + i) = pk;
+      } else {
+        const uint4 pk = *reinterpret_cast<const uint4*>(f + i);
+        float4 a, b;
+        bf16x2_unpack(pk.x, a.x, a.y); bf16x2_unpack(pk.y, a.z, a.w); bf16x2_unpack(pk.z, b.x, b.y); bf16x2_unpack(pk.w, b.z, b.w);
+        *reinterpret_cast<float4*>(g + i) = a;
+        *reinterpret_cast<float4*>(g + i + 4) = b;
+      }
+    }
+  } else {
+    for (long long i = base + threadIdx.x; i < n && i < base + kOptElemsPerBlock; i += 256) {
+      if (PACK) f[i] = __float2bfloat16_rn(g[i]); else g[i] = __bfloat162float(f[i]);
+    }
+  }
+}
+
+template <bool PACK>
+int launch_grad_bucket(const OctaveGradJob* jobs, int32_t n_jobs, void* flat, void* stream) {
+  if (!jobs || !flat || n_jobs <= 0 || n_jobs > OCTAVE_GRAD_MAX_JOBS) return OCT_ERR_INVALID;
+  GradJobs js;
+  js.n = n_jobs;
+  long long blocks = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    if (!jobs[i].g || jobs[i].n <= 0 || (jobs[i].flat_off & 7) || jobs[i].block_start != blocks) return OCT_ERR_INVALID;
+    js.j[i] = jobs[i];
+    blocks += (jobs[i].n + kOptElemsPerBlock - 1) / kOptElemsPerBlock;
+  }
+  if (blocks > 0x7fffffffLL) return OCT_ERR_INVALID;
+  grad_bucket_kernel<PACK><<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(js, reinterpret_cast<bf16*>(flat));
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
 }  // namespace
+
+extern "C" int octave_grad_pack_bf16(const OctaveGradJob* jobs, int32_t n_jobs, void* flat_bf16, void* stream) {
+  return launch_grad_bucket<true>(jobs, n_jobs, flat_bf16, stream);
+}
+extern "C" int octave_grad_unpack_bf16(const OctaveGradJob* jobs, int32_t n_jobs, const void* flat_bf16, void* stream) {
+  return launch_grad_bucket<false>(jobs, n_jobs, const_cast<void*>(flat_bf16), stream);
+}
 
 extern "C" int64_t octave_optim_job_blocks(int64_t n) { return n <= 0 ? 0 : (n + kOptElemsPerBlock - 1) / kOptElemsPerBlock; }
 

@@ -493,6 +493,11 @@ class _SegmentorFn(torch.autograd.Function):
         net._bwd(ctx.tape, gouts, grads)
         join_side_stream(grads)
         ctx.tape = None
+        if net._grad_ready_hook is not None:
+            # Every gradient has been handed to the hook (the data-parallel reducer), whose owner assigns param.grad when the
+            # exchange is done (GradAllReducer.finish).  Returning the tensors as well would make autograd's AccumulateGrad
+            # CLONE each of them (the reducer still holds references, so it cannot steal them): ~400 copy kernels per step.
+            return (None, None, *[None for _ in ctx.params])
         return (None, None, *[grads.get(p) for p in ctx.params])
 
 

@@ -26,9 +26,17 @@ class GradAllReducer:
     with disjoint lists (in the order the gradients become ready): every ~bucket_bytes the gradients gathered so far are
     packed into ONE flat buffer (a single concat kernel) whose all-reduce starts at once on a side stream, overlapping the
     rest of the backward pass.  `finish()` waits for the buckets and re-points each `param.grad` at its slice of the
-    averaged flat buffer — no copy back, no per-tensor kernels."""
+    averaged flat buffer — no copy back, no per-tensor kernels.
 
-    def __init__(self, bucket_bytes: int = 25 << 20, process_group=None):
+    grad_dtype="bf16" (NCCL on CUDA only): a bucket is gathered AND cast to bf16 by one kernel (octave_grad_pack_bf16), the
+    all-reduce moves half the bytes, and one kernel writes the averaged values back into the fp32 gradient tensors
+    (octave_grad_unpack_bf16).  The averaged gradient then carries one bf16 rounding of each rank's contribution plus NCCL's
+    bf16 accumulation (relative error ~2^-8): the mode of the bf16 product path, whose gradients are bf16-accurate anyway."""
+
+    def __init__(self, bucket_bytes: int = 25 << 20, process_group=None, grad_dtype: str = "fp32"):
+        if grad_dtype not in ("fp32", "bf16"):
+            raise ValueError(f"grad_dtype must be 'fp32' or 'bf16', got {grad_dtype!r}")
+        self.grad_dtype = grad_dtype
         self.bucket_bytes = bucket_bytes
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -52,15 +60,41 @@ class GradAllReducer:
             side = _n._side_streams.get(grads[0].device)
             if side is not None:
                 self._stream.wait_stream(side)       # weight gradients are produced on the side stream (config.overlap_wgrad)
+            offs = None
+            if (self.grad_dtype == "bf16" and self._avg
+                    and all(g.dtype == torch.float32 and g.is_contiguous() and g.numel() < (1 << 31) for g in grads)):
+                offs, off = [], 0
+                for g in grads:
+                    offs.append(off)
+                    off += (g.numel() + 7) & ~7              # 16-byte slots; the padding is never read back
             with torch.cuda.stream(self._stream):
-                flat = torch.cat([g.reshape(-1) for g in grads])
+                if offs is not None:
+                    flat = torch.empty(off, dtype=torch.bfloat16, device=grads[0].device)
+                    self._bucket_kernel("octave_grad_pack_bf16", grads, offs, flat)
+                else:
+                    flat = torch.cat([g.reshape(-1) for g in grads])
                 work = dist.all_reduce(flat, op=op, group=self.pg, async_op=True)
             for g in grads:
                 g.record_stream(self._stream)
-        else:
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            work = dist.all_reduce(flat, op=op, group=self.pg, async_op=True)
-        self._pending.append((flat, params, grads, work))
+            self._pending.append((flat, params, grads, work, offs))
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        work = dist.all_reduce(flat, op=op, group=self.pg, async_op=True)
+        self._pending.append((flat, params, grads, work, None))
+
+    @staticmethod
+    def _bucket_kernel(name: str, grads, offs, flat) -> None:
+        """octave_grad_pack_bf16 / octave_grad_unpack_bf16 on the current stream, at most OCTAVE_GRAD_MAX_JOBS tensors per launch."""
+        from . import _lib, ops
+        fn = getattr(_lib.lib, name)
+        for c0 in range(0, len(grads), _lib.GRAD_MAX_JOBS):
+            chunk = list(zip(grads[c0:c0 + _lib.GRAD_MAX_JOBS], offs[c0:c0 + _lib.GRAD_MAX_JOBS]))
+            arr = (_lib.OctaveGradJob * len(chunk))()
+            blocks = 0
+            for k, (g, o) in enumerate(chunk):
+                arr[k] = _lib.OctaveGradJob(g.data_ptr(), o, g.numel(), blocks)
+                blocks += _lib.lib.octave_optim_job_blocks(g.numel())
+            _lib.check(name, fn(arr, len(chunk), flat.data_ptr(), ops.stream_ptr()))
 
     def reduce(self, params, grads: Optional[Sequence[Optional[Tensor]]] = None):
         """reduce(params, grads) — or reduce(grads): gradients without an owning parameter are averaged in place."""
@@ -84,12 +118,20 @@ class GradAllReducer:
             return
         self._flush()
         on_side = self._stream is not None and self._pending and self._pending[0][0].is_cuda
-        for flat, params, grads, work in self._pending:
+        for flat, params, grads, work, offs in self._pending:
             work.wait()
             ctxm = torch.cuda.stream(self._stream) if on_side else _null()
             with ctxm:
                 if not self._avg:
                     flat.div_(self.world)
+                if offs is not None:
+                    # bf16 bucket: the averaged values go back into the fp32 gradient tensors (param.grad is unchanged)
+                    self._bucket_kernel("octave_grad_unpack_bf16", grads, offs, flat)
+            if offs is not None:
+                for p, g in zip(params, grads):
+                    if p is not None:
+                        p.grad = g.view_as(p)
+                continue
             off = 0
             for p, g in zip(params, grads):
                 n = g.numel()
@@ -150,7 +192,8 @@ class TrainStep:
     harness' choice (the mounted branch of the reference specifies none)."""
 
     def __init__(self, net: OctaScribbleNet, lr: float = 1e-3, momentum: float = 0.9, lambda_kl: float = 0.1,
-                 lambda_g: float = 0.1, distributed: bool = False, bucket_bytes: int = 25 << 20, fused_optimizer: bool = True):
+                 lambda_g: float = 0.1, distributed: bool = False, bucket_bytes: int = 25 << 20, fused_optimizer: bool = True,
+                 grad_dtype: Optional[str] = None):
         self.net = net
         self.lambda_kl, self.lambda_g = lambda_kl, lambda_g
         self.seg_params = [p for n, p in net.segmentor.named_parameters() if not n.startswith("linear_head_")]
@@ -166,7 +209,11 @@ class TrainStep:
         self.loss = FusedSegmentorLoss(weakly_supervise=isinstance(net.supervised_loss, nn.Module)
                                        and net.supervised_loss.__class__.__name__ == "WeightedPartialCE")
         self.lsd = LSDiscriminatorialLoss()
-        self.reducer = GradAllReducer(bucket_bytes) if distributed else None
+        if grad_dtype is None:
+            # bf16 gradient buckets go with the bf16 product path (whose gradients are bf16-accurate anyway); fp32 mode keeps fp32
+            from . import config
+            grad_dtype = "bf16" if (config.compute_dtype == "bf16" and all(p.is_cuda for p in self.seg_params)) else "fp32"
+        self.reducer = GradAllReducer(bucket_bytes, grad_dtype=grad_dtype) if distributed else None
         if self.reducer is not None:
             red = self.reducer
             net.segmentor._grad_ready_hook = lambda params, grads: red.reduce(params, grads)

@@ -64,3 +64,27 @@ def test_train_step_uses_one_optimizer_launch_per_module():
     assert conv.weight._version > v0
     fresh = ops.ConvSpec(conv.weight.detach().clone(), None, conv.in_channels, conv.out_channels, 3, 1, 1, 1).pack(ops._lib_pack.FWD)
     assert torch.equal(conv._oct_spec.pack(ops._lib_pack.FWD), fresh)
+
+
+def test_bf16_gradient_bucket_pack_and_unpack_round_trip():
+    """octave_grad_pack_bf16 / octave_grad_unpack_bf16 (data-parallel bf16 buckets): the flat bucket holds exactly
+    torch's round-to-nearest bf16 cast of every tensor at its 16-byte slot, the way back is the exact widening; sizes cover
+    the scalar path (13, 1, odd), block boundaries (4096 k + 5) and more tensors than one launch carries (300 > 128)."""
+    from octave_b200.train import GradAllReducer
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sizes = [13, 1, 8, 4096 * 3 + 5, 8192, 77, 64 * 3 * 3 * 3] + [16 + (i % 7) for i in range(300)]
+    grads = [torch.randn(n, device="cuda", generator=g) * (10.0 ** ((i % 5) - 2)) for i, n in enumerate(sizes)]
+    keep = [t.clone() for t in grads]
+    offs, off = [], 0
+    for t in grads:
+        offs.append(off)
+        off += (t.numel() + 7) & ~7
+    flat = torch.full((off,), float("nan"), dtype=torch.bfloat16, device="cuda")
+    GradAllReducer._bucket_kernel("octave_grad_pack_bf16", grads, offs, flat)
+    for t, o in zip(keep, offs):
+        assert torch.equal(flat[o:o + t.numel()], t.bfloat16())
+    for t in grads:
+        t.fill_(-1.0)
+    GradAllReducer._bucket_kernel("octave_grad_unpack_bf16", grads, offs, flat)
+    for t, k in zip(grads, keep):
+        assert torch.equal(t, k.bfloat16().float())
