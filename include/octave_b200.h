@@ -322,6 +322,23 @@ int octave_bn1d_relu_fwd(const float* x, int32_t B, int32_t C, const float* gamm
                          float* y, float* mean_invstd /* [2C] */, void* stream);
 int octave_bn1d_relu_bwd(const float* dy, const float* x, const float* y, int32_t B, int32_t C, const float* gamma,
                          const float* mean_invstd, int32_t training, float* dx, float* dgamma, float* dbeta, void* stream);
+/* The attention branch of SplAtConv2d (resnest.py:116-127) in two launches per direction instead of four, for a batch that
+ * fits one 32-row slab (octave_attn_fused_supported: B <= 32, one group, radix 2):
+ *   octave_glinear_bn_relu_fwd      x_out = fc1(in * in_scale), y = relu(BatchNorm1d(x_out)) (+ running statistics), mean_invstd
+ *   octave_glinear_rsoftmax_fwd     att = softmax over the radix pair (c, C + c) of fc2(in); the logits are not stored
+ *   octave_rsoftmax_glinear_bn_bwd  dlogits = r-softmax backward of datt; dh = dlogits . W2; dx = BatchNorm1d+ReLU backward of
+ *                                   dh (+ dgamma, dbeta).  W2 is [2C][Kt]; x / y are fc1's output before / after bn1 + relu.
+ * Same summation orders as the unfused entry points: results are bit-identical to them. */
+int octave_attn_fused_supported(int32_t B, int32_t C, int32_t inter, int32_t groups, int32_t radix);
+int octave_glinear_bn_relu_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t K_total, int32_t N,
+                               float in_scale, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float eps, float momentum, int32_t training, float* x_out, float* y,
+                               float* mean_invstd /* [2N] */, void* stream);
+int octave_glinear_rsoftmax_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t K_total, int32_t C,
+                                float* att /* [B][2C] */, void* stream);
+int octave_rsoftmax_glinear_bn_bwd(const float* datt, const float* att, const float* w, int32_t B, int32_t K_total, int32_t C,
+                                   const float* x, const float* y, const float* gamma, const float* mean_invstd, int32_t training,
+                                   float* dlogits, float* dx, float* dgamma, float* dbeta, void* stream);
 /* att[b][r*C+c] = softmax_r(logits[b][r*C+c]), radix R */
 int octave_rsoftmax_fwd(const float* logits, int32_t B, int32_t R, int32_t C, float* att, void* stream);
 int octave_rsoftmax_bwd(const float* datt, const float* att, int32_t B, int32_t R, int32_t C, float* dlogits, void* stream);

@@ -1,4 +1,5 @@
 """Run-time switches of the host layer (no effect on numerics of a given mode)."""
+import os
 
 # InterlayerDivergence raises Exception('Divergence is NaN') like the reference (losses.py:140-142).
 # The check is a device->host read; the benchmark and FusedSegmentorLoss read the flag lazily instead.
@@ -17,6 +18,12 @@ fold_bn_inference = True
 # and on dz_L, so it can run beside the rest of the chain (dgrad(L), then the HBM-bound BatchNorm backward of layer L-1):
 # tensor-pipe-bound and HBM-bound kernels then share the SMs instead of taking turns.  Joined before the gradients are used.
 overlap_wgrad = True
+# The attention branch of SplAtConv2d (fc1 -> bn1 -> relu -> fc2 -> r-softmax) when the batch fits one 32-row slab
+# (octave_attn_fused_supported).  Forward: two launches instead of four (-0.35 ms per c2 step).  Backward: the single-launch
+# form (r-softmax backward + fc2 data gradient + bn1/relu backward) is bit-identical too but its 1-8 blocks walk all 2C
+# outputs serially, +0.7 ms per step against the split-K kernels: off unless OCTAVE_FUSE_ATTN=2.  OCTAVE_FUSE_ATTN=0: all separate.
+fuse_attention_branch = os.environ.get("OCTAVE_FUSE_ATTN", "1") != "0"
+fuse_attention_branch_bwd = os.environ.get("OCTAVE_FUSE_ATTN", "1") == "2"
 
 
 def set_compute_dtype(name: str) -> None:

@@ -10,19 +10,31 @@ namespace {
 // loads in flight, split the contraction over the warps of a block and reuse the activation rows across output columns.
 constexpr int kJB = 8;   // output columns per block of glinear_fwd (= warps per block)
 
-// block: kJB columns j0.. of one group; lane = batch row (blockIdx.y selects the 32-row slab); warp w = K slice w
+// Epilogues fused into glinear_fwd_kernel (the whole batch column of an output is in one warp when B <= 32):
+//   1  BatchNorm1d over the batch + ReLU  (fc1 -> bn1 -> relu, resnest.py:118-122): out = pre-BN values (kept for backward),
+//      e.y = activations, e.mi = mean / invstd, running statistics updated; same summation order as bn1d_relu_fwd_kernel
+//   2  r-softmax over radix 2 (fc2 -> view(B,2,C) softmax, resnest.py:125-127): the block's 8 columns are the 4 channels
+//      c0..c0+3 of both radix halves (j = r*C + c); out = attention weights, the logits are not stored
+struct GlinearEpi {
+  const float* gamma; const float* beta; float* rm; float* rv; long long* nbt; float eps, mom; int training;
+  float* y; float* mi; int C;
+};
+
+// block: kJB columns of one group; lane = batch row (blockIdx.y selects the 32-row slab); warp w = K slice w
+template <int EPI>
 __global__ void __launch_bounds__(256) glinear_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                           const float* __restrict__ bias, int B, int Kt, int N, int groups,
-                                                          float scale, float* __restrict__ out) {
+                                                          float scale, float* __restrict__ out, const GlinearEpi e) {
   __shared__ float red[8][kJB][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Kg = Kt / groups, Ng = N / groups;
-  const int j0 = blockIdx.x * kJB, g = j0 / Ng;
+  const int j0 = blockIdx.x * kJB, g = EPI == 2 ? 0 : j0 / Ng;
+  auto col = [&](int jj) { return EPI == 2 ? (jj >> 2) * e.C + (int)blockIdx.x * 4 + (jj & 3) : j0 + jj; };
   const int b = blockIdx.y * 32 + lane;
   const int bb = b < B ? b : B - 1;
   const int Ks = Kg / 8;                    // floats of this warp's K slice (multiple of 4)
   const float* arow = in + (long long)bb * Kt + g * Kg + warp * Ks;
-  const float* wrow = w + (long long)j0 * Kg + warp * Ks;
+  const float* wbase = w + warp * Ks;
   float acc[kJB];
 #pragma unroll
   for (int jj = 0; jj < kJB; ++jj) acc[jj] = 0.f;
@@ -31,27 +43,80 @@ __global__ void __launch_bounds__(256) glinear_fwd_kernel(const float* __restric
     const float4 a = *reinterpret_cast<const float4*>(arow + i);
 #pragma unroll
     for (int jj = 0; jj < kJB; ++jj) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + (long long)jj * Kg + i));
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wbase + (long long)col(jj) * Kg + i));
       acc[jj] += a.x * wv.x + a.y * wv.y + a.z * wv.z + a.w * wv.w;
     }
   }
 #pragma unroll
   for (int jj = 0; jj < kJB; ++jj) red[warp][jj][lane] = acc[jj];
   __syncthreads();
-  // warp w finalises column j0 + w
+  // warp w finalises column col(w)
   float sum = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) sum += red[k][warp][lane];
-  const int j = j0 + warp;
-  if (b < B) out[(long long)b * N + j] = sum * scale + (bias ? bias[j] : 0.f);
+  const int j = col(warp);
+  const float val = sum * scale + (bias ? bias[j] : 0.f);
+  if (EPI == 0) {
+    if (b < B) out[(long long)b * N + j] = val;
+    return;
+  }
+  __syncthreads();                          // every warp has read its partial sums: red is reused for the column values
+  float* fin = &red[0][0][0];               // [8 columns][32 batch rows]
+  fin[warp * 32 + lane] = val;
+  __syncthreads();
+  if (EPI == 1) {
+    if (b < B) out[(long long)b * N + j] = val;
+    float mean, invstd;
+    if (e.training) {
+      double sd = 0.0, qd = 0.0;
+      for (int r = 0; r < B; ++r) { const double v = fin[warp * 32 + r]; sd += v; qd += v * v; }
+      const double m = sd / B;
+      double var = qd / B - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)e.eps));
+      if (lane == 0) {
+        if (e.rm) e.rm[j] = (1.f - e.mom) * e.rm[j] + e.mom * mean;
+        if (e.rv) e.rv[j] = (1.f - e.mom) * e.rv[j] + e.mom * (float)(B > 1 ? var * B / (B - 1.0) : var);
+        if (j == 0 && e.nbt) *e.nbt += 1;
+      }
+    } else {
+      mean = e.rm[j];
+      invstd = 1.f / sqrtf(e.rv[j] + e.eps);
+    }
+    if (lane == 0) { e.mi[j] = mean; e.mi[N + j] = invstd; }
+    if (b < B) e.y[(long long)b * N + j] = fmaxf((val - mean) * invstd * e.gamma[j] + e.beta[j], 0.f);
+  } else {
+    if (warp < 4 && b < B) {
+      const float l0 = fin[warp * 32 + lane], l1 = fin[(4 + warp) * 32 + lane];
+      const float mx = fmaxf(fmaxf(-INFINITY, l0), l1);
+      float sm = 0.f;
+      sm += expf(l0 - mx);
+      sm += expf(l1 - mx);
+      const int c = blockIdx.x * 4 + warp;
+      out[(long long)b * N + c] = expf(l0 - mx) / sm;
+      out[(long long)b * N + e.C + c] = expf(l1 - mx) / sm;
+    }
+  }
 }
 
 // din[b][i] = scale * sum_{j in group(i)} dout[b][j] * w[j][i_local]
 // block: 32 consecutive inputs i (lane) x 8 j slices (warp); all 32 batch rows of the slab are accumulators of a thread
+// FUSED (the fc2 -> bn1 -> relu part of the split-attention backward, B <= 32, one group, gridDim.z = 1):
+//   prologue  dout is not read: dlogits = att * (datt - sum_r datt*att) (r-softmax backward, radix 2) is computed while
+//             staging, and written out by block column 0 for the weight-gradient kernel;
+//   epilogue  din is not written: the BatchNorm1d + ReLU backward of bn1d_relu_bwd_kernel (same summation order) is applied
+//             to the block's 32 columns -> f.dx, f.dgamma, f.dbeta.
+struct GlinearBwdFuse {
+  const float* att; const float* datt; float* dlogits; int C;
+  const float* x; const float* y; const float* gamma; const float* mi; int training;
+  float* dx; float* dgamma; float* dbeta;
+};
 constexpr int kJC = 64;   // outputs staged per pass
+template <bool FUSED>
 __global__ void __launch_bounds__(256) glinear_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
                                                                int B, int Kt, int N, int groups, float scale,
-                                                               float* __restrict__ din) {
+                                                               float* __restrict__ din, const GlinearBwdFuse f) {
   __shared__ __align__(16) float tile[kJC][32];     // dout^T of the current pass: [j][b]
   __shared__ float red[8][32][33];                  // [warp][b][i]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,7 +136,22 @@ __global__ void __launch_bounds__(256) glinear_bwd_data_kernel(const float* __re
     for (int e = threadIdx.x; e < kJC * 32; e += 256) {
       const int jj = e >> 5, r = e & 31;
       const int bq = b0 + r;
-      tile[jj][r] = (bq < B && jc + jj < jend) ? __ldg(dout + (long long)bq * N + g * Ng + jc + jj) : 0.f;
+      float dv = 0.f;
+      if (bq < B && jc + jj < jend) {
+        if (FUSED) {
+          const int j = jc + jj, c = j < f.C ? j : j - f.C;
+          const long long base = (long long)bq * N + c;
+          const float a0 = f.att[base], a1 = f.att[base + f.C], d0 = f.datt[base], d1 = f.datt[base + f.C];
+          float dot = 0.f;
+          dot += d0 * a0;
+          dot += d1 * a1;
+          dv = j < f.C ? a0 * (d0 - dot) : a1 * (d1 - dot);
+          if (blockIdx.x == 0) f.dlogits[(long long)bq * N + j] = dv;
+        } else {
+          dv = __ldg(dout + (long long)bq * N + g * Ng + jc + jj);
+        }
+      }
+      tile[jj][r] = dv;
     }
     __syncthreads();
     const int jn = min(kJC, jend - jc);
@@ -91,6 +171,40 @@ __global__ void __launch_bounds__(256) glinear_bwd_data_kernel(const float* __re
 #pragma unroll
   for (int r = 0; r < 32; ++r) red[warp][r][lane] = acc[r];
   __syncthreads();
+  if (FUSED) {
+    // dh[r][lane] of the block's 32 columns -> shared memory (the staging tile is free now), then bn1d_relu_bwd per column
+    float* fin = &tile[0][0];                 // [32 rows][32 columns]
+    __shared__ float kk[2][32];
+    for (int r = warp; r < 32; r += 8) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += red[k][r][lane];
+      fin[r * 32 + lane] = sum * scale;
+    }
+    __syncthreads();
+    const float mean = f.mi[i], invstd = f.mi[Kt + i];
+    if (warp == 0) {
+      float sd = 0.f, sdx = 0.f;
+      for (int b = 0; b < B; ++b) {
+        const long long o = (long long)b * Kt + i;
+        const float d = f.y[o] > 0.f ? fin[b * 32 + lane] : 0.f;
+        sd += d;
+        sdx += d * (f.x[o] - mean) * invstd;
+      }
+      if (f.dgamma) f.dgamma[i] = sdx;
+      if (f.dbeta) f.dbeta[i] = sd;
+      kk[0][lane] = f.training ? sd / B : 0.f;
+      kk[1][lane] = f.training ? sdx / B : 0.f;
+    }
+    __syncthreads();
+    const float k1 = kk[0][lane], k2 = kk[1][lane], ag = f.gamma[i] * invstd;
+    for (int r = warp; r < 32 && r < B; r += 8) {
+      const long long o = (long long)r * Kt + i;
+      const float d = f.y[o] > 0.f ? fin[r * 32 + lane] : 0.f;
+      f.dx[o] = ag * (d - k1 - (f.x[o] - mean) * invstd * k2);
+    }
+    return;
+  }
   // thread (warp, lane): rows r = warp, warp + 8, ... ; column lane
   for (int r = warp; r < 32; r += 8) {
     float sum = 0.f;
@@ -355,9 +469,50 @@ extern "C" int octave_glinear_fwd(const float* in, const float* w, const float* 
   if (!in || !w || !out || B <= 0 || Kt <= 0 || N <= 0 || groups <= 0 || Kt % groups || N % groups) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   if (glinear_tiled_ok(Kt, N, groups))
-    glinear_fwd_kernel<<<dim3(N / kJB, (B + 31) / 32), 256, 0, s>>>(in, w, bias, B, Kt, N, groups, in_scale, out);
+    glinear_fwd_kernel<0><<<dim3(N / kJB, (B + 31) / 32), 256, 0, s>>>(in, w, bias, B, Kt, N, groups, in_scale, out, GlinearEpi{});
   else
     glinear_fwd_ref_kernel<<<(unsigned)(((long long)B * N * 32 + 255) / 256), 256, 0, s>>>(in, w, bias, B, Kt, N, groups, in_scale, out);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_attn_fused_supported(int32_t B, int32_t C, int32_t inter, int32_t groups, int32_t radix) {
+  // whole batch in one 32-row slab; one group; radix pairs (c, C + c); the tiled kernels' shape rules for both linears
+  return B > 0 && B <= 32 && groups == 1 && radix == 2 && C % 32 == 0 && inter % 32 == 0 && glinear_tiled_ok(C, inter, 1) &&
+         glinear_tiled_ok(inter, 2 * C, 1);
+}
+
+extern "C" int octave_glinear_bn_relu_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t Kt, int32_t N,
+                                          float in_scale, const float* gamma, const float* beta, float* rm, float* rv, int64_t* nbt,
+                                          float eps, float momentum, int32_t training, float* x_out, float* y, float* mean_invstd,
+                                          void* stream) {
+  if (!in || !w || !gamma || !beta || !x_out || !y || !mean_invstd || B <= 0 || Kt <= 0 || N <= 0) return OCT_ERR_INVALID;
+  if (!training && (!rm || !rv)) return OCT_ERR_INVALID;
+  if (B > 32 || !glinear_tiled_ok(Kt, N, 1)) return OCT_ERR_UNSUPPORTED;
+  GlinearEpi e{gamma, beta, rm, rv, (long long*)nbt, eps, momentum, training, y, mean_invstd, 0};
+  glinear_fwd_kernel<1><<<dim3(N / kJB, 1), 256, 0, (cudaStream_t)stream>>>(in, w, bias, B, Kt, N, 1, in_scale, x_out, e);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_glinear_rsoftmax_fwd(const float* in, const float* w, const float* bias, int32_t B, int32_t Kt, int32_t C,
+                                           float* att, void* stream) {
+  if (!in || !w || !att || B <= 0 || Kt <= 0 || C <= 0) return OCT_ERR_INVALID;
+  if (B > 32 || C % 4 || !glinear_tiled_ok(Kt, 2 * C, 1)) return OCT_ERR_UNSUPPORTED;
+  GlinearEpi e{};
+  e.C = C;
+  glinear_fwd_kernel<2><<<dim3(2 * C / kJB, 1), 256, 0, (cudaStream_t)stream>>>(in, w, bias, B, Kt, 2 * C, 1, 1.f, att, e);
+  OCT_CHECK_LAUNCH();
+  return OCT_OK;
+}
+
+extern "C" int octave_rsoftmax_glinear_bn_bwd(const float* datt, const float* att, const float* w, int32_t B, int32_t Kt, int32_t C,
+                                              const float* x, const float* y, const float* gamma, const float* mean_invstd,
+                                              int32_t training, float* dlogits, float* dx, float* dgamma, float* dbeta, void* stream) {
+  if (!datt || !att || !w || !x || !y || !gamma || !mean_invstd || !dlogits || !dx || B <= 0 || Kt <= 0 || C <= 0) return OCT_ERR_INVALID;
+  if (B > 32 || Kt % 32) return OCT_ERR_UNSUPPORTED;
+  GlinearBwdFuse f{att, datt, dlogits, C, x, y, gamma, mean_invstd, training, dx, dgamma, dbeta};
+  glinear_bwd_data_kernel<true><<<dim3(Kt / 32, 1, 1), 256, 0, (cudaStream_t)stream>>>(nullptr, w, B, Kt, 2 * C, 1, 1.f, nullptr, f);
   OCT_CHECK_LAUNCH();
   return OCT_OK;
 }
@@ -372,7 +527,7 @@ extern "C" int octave_glinear_bwd_data(const float* dout, const float* w, int32_
     int split = 1;
     while (!g_octave_deterministic && split < 16 && (Kt / 32) * split < 96 && Ng / (split * 2) >= kJC) split *= 2;
     if (split > 1 && cudaMemsetAsync(din, 0, sizeof(float) * (size_t)B * Kt, s) != cudaSuccess) return OCT_ERR_LAUNCH;
-    glinear_bwd_data_kernel<<<dim3(Kt / 32, (B + 31) / 32, split), 256, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din);
+    glinear_bwd_data_kernel<false><<<dim3(Kt / 32, (B + 31) / 32, split), 256, 0, s>>>(dout, w, B, Kt, N, groups, in_scale, din, GlinearBwdFuse{});
   }
   else {
     if (B > 65535) return OCT_ERR_UNSUPPORTED;

@@ -205,13 +205,20 @@ class SplAtConv2d(nn.Module):
         hw = float(x.H * x.W)
         card = self.cardinality
         w1 = self.fc1.weight.detach().reshape(self.fc1.out_channels, -1)
-        h1 = ops.glinear_fwd(gap, w1, self.fc1.bias.detach(), card, 1.0 / hw)   # :118
-        bn1 = self.bn1
-        h1n, mi1 = ops.bn1d_relu_fwd(h1, bn1.weight.detach(), bn1.bias.detach(), bn1.running_mean, bn1.running_var,
-                                     bn1.num_batches_tracked if tr else None, bn1.eps, bn1.momentum, tr)  # :120-122
         w2 = self.fc2.weight.detach().reshape(self.fc2.out_channels, -1)
-        logits = ops.glinear_fwd(h1n, w2, self.fc2.bias.detach(), card, 1.0)    # :125
-        att = ops.rsoftmax_fwd(logits, self.radix)                              # :125-127 view(B,radix,C) softmax(dim=1)
+        bn1 = self.bn1
+        if ops.attn_fused_ok(gap.shape[0], gap.shape[1], w1.shape[0], card, self.radix) and w2.shape[0] == 2 * gap.shape[1]:
+            # two launches: fc1 + bn1 + relu, fc2 + r-softmax (the whole batch column of an output sits in one warp)
+            h1, h1n, mi1 = ops.glinear_bn_relu_fwd(gap, w1, self.fc1.bias.detach(), 1.0 / hw, bn1.weight.detach(), bn1.bias.detach(),
+                                                   bn1.running_mean, bn1.running_var, bn1.num_batches_tracked if tr else None,
+                                                   bn1.eps, bn1.momentum, tr)             # :118-122
+            att = ops.glinear_rsoftmax_fwd(h1n, w2, self.fc2.bias.detach(), gap.shape[1])   # :125-127
+        else:
+            h1 = ops.glinear_fwd(gap, w1, self.fc1.bias.detach(), card, 1.0 / hw)   # :118
+            h1n, mi1 = ops.bn1d_relu_fwd(h1, bn1.weight.detach(), bn1.bias.detach(), bn1.running_mean, bn1.running_var,
+                                         bn1.num_batches_tracked if tr else None, bn1.eps, bn1.momentum, tr)  # :120-122
+            logits = ops.glinear_fwd(h1n, w2, self.fc2.bias.detach(), card, 1.0)    # :125
+            att = ops.rsoftmax_fwd(logits, self.radix)                              # :125-127 view(B,radix,C) softmax(dim=1)
         o = ops.splat_combine(U, att, relu_out, out)                            # :133-135
         return o, (x, z, U, bn0ctx, gap, h1, h1n, mi1, att, o if relu_out else None, tr, hw)
 
@@ -219,12 +226,16 @@ class SplAtConv2d(nn.Module):
         x, z, U, bn0ctx, gap, h1, h1n, mi1, att, mask, tr, hw = ctx
         card = self.cardinality
         datt = ops.splat_bwd_reduce(dout, mask, U)
-        dlogits = ops.rsoftmax_bwd(datt, att, self.radix)
         w2 = self.fc2.weight.detach().reshape(self.fc2.out_channels, -1)
         side = on_side_stream if _overlap(x) else None
-        dh1n, dw2, db2 = ops.glinear_bwd(dlogits, h1n, w2, card, 1.0, side=side)
+        if (config.fuse_attention_branch_bwd and ops.attn_fused_ok(gap.shape[0], gap.shape[1], h1.shape[1], card, self.radix)
+                and w2.shape[0] == 2 * gap.shape[1]):
+            dh1, dg1, dbt1, dw2, db2 = ops.attn_bwd_fused(datt, att, w2, h1, h1n, self.bn1.weight.detach(), mi1, tr, card, side=side)
+        else:
+            dlogits = ops.rsoftmax_bwd(datt, att, self.radix)
+            dh1n, dw2, db2 = ops.glinear_bwd(dlogits, h1n, w2, card, 1.0, side=side)
+            dh1, dg1, dbt1 = ops.bn1d_relu_bwd(dh1n, h1, h1n, self.bn1.weight.detach(), mi1, tr)
         _acc(grads, self.fc2.weight, dw2); _acc(grads, self.fc2.bias, db2)
-        dh1, dg1, dbt1 = ops.bn1d_relu_bwd(dh1n, h1, h1n, self.bn1.weight.detach(), mi1, tr)
         _acc(grads, self.bn1.weight, dg1); _acc(grads, self.bn1.bias, dbt1)
         w1 = self.fc1.weight.detach().reshape(self.fc1.out_channels, -1)
         dgap, dw1, db1 = ops.glinear_bwd(dh1, gap, w1, card, 1.0 / hw, side=side)

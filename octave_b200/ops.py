@@ -144,6 +144,11 @@ _sigs = {
     "octave_bn1d_relu_bwd": [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp],
     "octave_rsoftmax_fwd": [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
     "octave_rsoftmax_bwd": [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+    "octave_attn_fused_supported": [C.c_int32] * 5,
+    "octave_glinear_bn_relu_fwd": [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float,
+                                   C.c_int32, _vp, _vp, _vp, _vp],
+    "octave_glinear_rsoftmax_fwd": [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
+    "octave_rsoftmax_glinear_bn_bwd": [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp],
     "octave_pack_weight": [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp],
     "octave_pack_weight_multi": [_vp, C.c_int32, C.c_int64, _vp],
 }
@@ -330,6 +335,55 @@ def glinear_bwd(dout: torch.Tensor, inp: torch.Tensor, w: torch.Tensor, groups: 
 
     dw, db = side(weight_part, dout, inp) if side is not None else weight_part()
     return din, dw, db
+
+
+def attn_fused_ok(B: int, C_: int, inter: int, groups: int, radix: int) -> bool:
+    from . import config
+    return bool(config.fuse_attention_branch and lib.octave_attn_fused_supported(B, C_, inter, groups, radix))
+
+
+def glinear_bn_relu_fwd(inp, w, bias, in_scale: float, gamma, beta, rm, rv, nbt, eps: float, momentum: float, training: bool):
+    """fc1 + BatchNorm1d + ReLU in one launch -> x (pre-BN, kept for backward), y, mean_invstd."""
+    B, Kt = inp.shape
+    N = w.shape[0]
+    x = torch.empty((B, N), dtype=torch.float32, device=inp.device)
+    y = torch.empty_like(x)
+    mi = torch.empty(2 * N, dtype=torch.float32, device=inp.device)
+    _chk("octave_glinear_bn_relu_fwd", lib.octave_glinear_bn_relu_fwd(
+        inp.data_ptr(), w.data_ptr(), _p(bias), B, Kt, N, in_scale, gamma.data_ptr(), beta.data_ptr(), _p(rm), _p(rv), _p(nbt), eps, momentum,
+        int(training), x.data_ptr(), y.data_ptr(), mi.data_ptr(), stream_ptr()))
+    return x, y, mi
+
+
+def glinear_rsoftmax_fwd(inp, w, bias, C_: int) -> torch.Tensor:
+    """fc2 + r-softmax over the radix pair (c, C + c) in one launch -> att [B, 2C]."""
+    B, Kt = inp.shape
+    att = torch.empty((B, 2 * C_), dtype=torch.float32, device=inp.device)
+    _chk("octave_glinear_rsoftmax_fwd", lib.octave_glinear_rsoftmax_fwd(inp.data_ptr(), w.data_ptr(), _p(bias), B, Kt, C_, att.data_ptr(), stream_ptr()))
+    return att
+
+
+def attn_bwd_fused(datt, att, w2, h1, h1n, gamma, mi, training: bool, groups: int, side=None):
+    """r-softmax backward + fc2 data gradient + BatchNorm1d/ReLU backward in one launch; fc2's parameter gradients from the
+    dlogits it leaves behind (on `side`, see glinear_bwd).  -> dx (gradient of fc1's output), dgamma, dbeta, dw2, db2"""
+    B, Kt = h1.shape
+    C_ = att.shape[1] // 2
+    dlogits = torch.empty_like(att)
+    dx = torch.empty_like(h1)
+    dg = torch.empty(Kt, dtype=torch.float32, device=h1.device)
+    db = torch.empty(Kt, dtype=torch.float32, device=h1.device)
+    _chk("octave_rsoftmax_glinear_bn_bwd", lib.octave_rsoftmax_glinear_bn_bwd(
+        datt.data_ptr(), att.data_ptr(), w2.data_ptr(), B, Kt, C_, h1.data_ptr(), h1n.data_ptr(), gamma.data_ptr(), mi.data_ptr(), int(training),
+        dlogits.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), stream_ptr()))
+
+    def weight_part():
+        dw_ = torch.empty_like(w2)
+        db_ = torch.empty(2 * C_, dtype=torch.float32, device=h1.device)
+        _chk("octave_glinear_bwd_weight", lib.octave_glinear_bwd_weight(dlogits.data_ptr(), h1n.data_ptr(), B, Kt, 2 * C_, groups, 1.0, dw_.data_ptr(), db_.data_ptr(), stream_ptr()))
+        return dw_, db_
+
+    dw2, db2 = side(weight_part, dlogits, h1n) if side is not None else weight_part()
+    return dx, dg, db, dw2, db2
 
 
 def glinear_bwd_data_only(dout: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
