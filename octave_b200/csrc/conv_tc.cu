@@ -292,15 +292,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
         const int cp = lane % CP, rg = lane / CP;
 #pragma unroll
         for (int sl = 0; sl < NSL; ++sl) {
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          unsigned long long s01 = 0ull, q01 = 0ull;
 #pragma unroll 8
           for (int i = 0; i < RPG; ++i) {
             const int row = q * 32 + i * RG + rg;
             const uint32_t u = *reinterpret_cast<const uint32_t*>(sbuf + sl * SLAB_BYTES + row * RB + ((((cp >> 2)) ^ swz(row)) << 4) + (cp & 3) * 4);
-            float a, b;
-            bf16x2_unpack(u, a, b);
-            s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+            stat_acc_bf16x2(u, s01, q01);
           }
+          float s0, s1, q0, q1;
+          unpack_f32x2(s01, s0, s1);
+          unpack_f32x2(q01, q0, q1);
 #pragma unroll
           for (int off = 16; off >= CP; off >>= 1) {
             s0 += __shfl_xor_sync(0xffffffffu, s0, off); s1 += __shfl_xor_sync(0xffffffffu, s1, off);
@@ -432,14 +433,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_kernel(const __grid_co
           __syncwarp();
           if (p.stats) {
             // lane owns the column pair `lane` of this slab (unit lane/4, word lane%4) over the 32 rows
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            unsigned long long s01 = 0ull, q01 = 0ull;
 #pragma unroll 8
             for (int row = 0; row < 32; ++row) {
               const uint32_t u = *reinterpret_cast<const uint32_t*>(stage + row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + (lane & 3) * 4);
-              float a, b;
-              bf16x2_unpack(u, a, b);
-              s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+              stat_acc_bf16x2(u, s01, q01);
             }
+            float s0, s1, q0, q1;
+            unpack_f32x2(s01, s0, s1);
+            unpack_f32x2(q01, q0, q1);
             sacc[h2][0] += s0; sacc[h2][1] += s1; sacc[h2][2] += q0; sacc[h2][3] += q1;
           }
           {
