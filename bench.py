@@ -238,8 +238,8 @@ def family_rooflines(ts, batch, peaks, step_ms):
             pres = d["present"]
             if n == "octave_affine_act":          # x, res?, y
                 passes = 2 + (1 if 2 in pres else 0)
-            elif n == "octave_bn_bwd_reduce":     # dy, mask?, x
-                passes = 2 + (1 if 1 in pres else 0)
+            elif n == "octave_bn_bwd_reduce":     # dy, mask?, x, dmasked?
+                passes = 2 + (1 if 1 in pres else 0) + (1 if 6 in pres else 0)
             else:                                 # dy, mask?, x, dx, dmasked?
                 passes = 3 + (1 if 1 in pres else 0) + (1 if 11 in pres else 0)
             add({"octave_affine_act": "BatchNorm apply (+residual, +ReLU) (affine_act_kernel)",

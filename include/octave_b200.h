@@ -226,9 +226,11 @@ size_t octave_affine_gap_ws_bytes(const OctaveAct* x);
 int octave_affine_act(const OctaveAct* x, const float* ab, const OctaveAct* res, int32_t relu, const OctaveAct* y,
                       float* gap, void* gap_ws, void* stream);
 /* dz = dy * (mask > 0) (mask nullable); or, with mask NULL and relu_ab != NULL (the [2C] scale/shift of this very BN),
- * the ReLU mask is recomputed from x as (x*a+b > 0) instead of being read.  sums2[c] = sum dz, sums2[C+c] = sum dz * xhat. */
+ * the ReLU mask is recomputed from x as (x*a+b > 0) instead of being read.  sums2[c] = sum dz, sums2[C+c] = sum dz * xhat.
+ * dmasked (nullable): dz itself is stored too — it is the gradient of the residual branch added before the ReLU
+ * (resnest.py:42,264-265), and octave_bn_bwd_apply can then be given dz as its dy with no mask (one tensor pass less). */
 int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
-                         const float* mean_invstd, double* sums2, void* stream);
+                         const float* mean_invstd, double* sums2, const OctaveAct* dmasked, void* stream);
 /* dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (training) or gamma*invstd*dz (eval, mean_invstd then
  * holds the running statistics).  dgamma = sum dz*xhat, dbeta = sum dz (nullable) are overwritten.
  * dmasked (nullable): also store dz = dy * (mask > 0) itself — the gradient of the residual branch that was added

@@ -272,7 +272,7 @@ constexpr int U_BNR = 4;
 template <typename T, int MASK>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const OctaveAct dy, const OctaveAct mask, int Gb,
                                                                const float* ab, const OctaveAct x, const float* mi,
-                                                               double* sums2) {
+                                                               double* sums2, const OctaveAct dmasked, int has_dm) {
   extern __shared__ float sm[];
   const Tix t = make_tix<U_BNR>(x, Gb);
   float mean[8], v[16], aa[8], bb[8];
@@ -312,6 +312,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const OctaveAct d
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = to_f(from_f<T>(f[i] * aa[i] + bb[i])) > 0.f ? d[i] : 0.f;
       }
+      // dy * (mask > 0) leaves with this pass (it is the residual branch's gradient, and the apply pass then reads it
+      // instead of dy AND the mask: one tensor pass less per BatchNorm backward)
+      if (has_dm && p + (long long)u * t.ppb < t.n) VecIO<T, 8>::st(at<T>(dmasked, t.base + p + (long long)u * t.ppb, t.cg * 8), d);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         v[i] += d[i];
@@ -780,27 +783,28 @@ extern "C" int octave_affine_act(const OctaveAct* x, const float* ab, const Octa
 
 template <typename T, int MASK>
 static int launch_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* m, const float* relu_ab, const OctaveAct* x,
-                                const float* mi, double* sums2, cudaStream_t s) {
+                                const float* mi, double* sums2, const OctaveAct* dmasked, cudaStream_t s) {
   auto fn = bn_bwd_reduce_kernel<T, MASK>;
   Geo g;
   if (!make_geo(x, &g, U_BNR, false, ONE_WAVE(fn, 256, 16 * 256 * sizeof(float)), 4)) return OCT_ERR_UNSUPPORTED;
-  fn<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*dy, *m, g.Gb, relu_ab, *x, mi, sums2);
+  fn<<<g.grid, g.bs, 16 * g.bs * sizeof(float), s>>>(*dy, *m, g.Gb, relu_ab, *x, mi, sums2, dmasked ? *dmasked : *dy, dmasked != nullptr);
   return OCT_OK;
 }
 
 extern "C" int octave_bn_bwd_reduce(const OctaveAct* dy, const OctaveAct* mask, const float* relu_ab, const OctaveAct* x,
-                                    const float* mean_invstd, double* sums2, void* stream) {
+                                    const float* mean_invstd, double* sums2, const OctaveAct* dmasked, void* stream) {
   if (!view_ok(dy) || !view_ok(x) || !same_shape(dy, x) || !mean_invstd || !sums2) return OCT_ERR_INVALID;
   if (mask && (!view_ok(mask) || !same_shape(mask, x))) return OCT_ERR_INVALID;
+  if (dmasked && (!view_ok(dmasked) || !same_shape(dmasked, x))) return OCT_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   if (!g_octave_stats_prezeroed && cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * x->C, s) != cudaSuccess) return OCT_ERR_LAUNCH;
   const OctaveAct* m = mask ? mask : x;
   const int mmode = mask ? 1 : (relu_ab ? 2 : 0);
   int rc = OCT_OK;
   DISPATCH_T(x->dtype, {
-    if (mmode == 0) rc = launch_bn_bwd_reduce<T, 0>(dy, m, relu_ab, x, mean_invstd, sums2, s);
-    else if (mmode == 1) rc = launch_bn_bwd_reduce<T, 1>(dy, m, relu_ab, x, mean_invstd, sums2, s);
-    else rc = launch_bn_bwd_reduce<T, 2>(dy, m, relu_ab, x, mean_invstd, sums2, s);
+    if (mmode == 0) rc = launch_bn_bwd_reduce<T, 0>(dy, m, relu_ab, x, mean_invstd, sums2, dmasked, s);
+    else if (mmode == 1) rc = launch_bn_bwd_reduce<T, 1>(dy, m, relu_ab, x, mean_invstd, sums2, dmasked, s);
+    else rc = launch_bn_bwd_reduce<T, 2>(dy, m, relu_ab, x, mean_invstd, sums2, dmasked, s);
   });
   if (rc != OCT_OK) return rc;
   OCT_CHECK_LAUNCH();

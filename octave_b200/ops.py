@@ -110,7 +110,7 @@ _sigs = {
     "octave_chan_stats": [_A, _vp, _vp],
     "octave_bn_prepare": [C.c_int32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_int32, _vp, _vp, _vp],
     "octave_affine_act": [_A, _vp, _A, C.c_int32, _A, _vp, _vp, _vp],
-    "octave_bn_bwd_reduce": [_A, _A, _vp, _A, _vp, _vp, _vp],
+    "octave_bn_bwd_reduce": [_A, _A, _vp, _A, _vp, _vp, _A, _vp],
     "octave_bn_bwd_apply": [_A, _A, _vp, _A, _vp, _vp, _vp, C.c_int32, _A, _vp, _vp, _A, _vp],
     "octave_add_inplace": [_A, _A, _vp],
     "octave_relu_bwd": [_A, _A, _A, _vp],
@@ -254,12 +254,16 @@ def bn_bwd(dy: Act, mask: Optional[Act], x: Act, mi: torch.Tensor, gamma: Option
     """-> dx, dgamma, dbeta.  relu_ab (with mask None): recompute this BN's own ReLU mask from x instead of reading it.
     dmasked: also receives dy * (mask > 0) (the residual branch's gradient)."""
     sums2 = zeros_f64(2 * x.C, x.device)
-    _chk("octave_bn_bwd_reduce", lib.octave_bn_bwd_reduce(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), sums2.data_ptr(), stream_ptr()))
+    # dmasked leaves with the reduction pass; the apply pass then reads it in place of dy AND the mask
+    _chk("octave_bn_bwd_reduce", lib.octave_bn_bwd_reduce(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), sums2.data_ptr(),
+                                                          _ref(dmasked), stream_ptr()))
     dx = out if out is not None else x.like()
     dgamma = torch.empty(x.C, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(x.C, dtype=torch.float32, device=x.device)
+    if dmasked is not None:
+        dy, mask, relu_ab = dmasked, None, None
     _chk("octave_bn_bwd_apply", lib.octave_bn_bwd_apply(_ref(dy), _ref(mask), _p(relu_ab), _ref(x), mi.data_ptr(), _p(gamma), sums2.data_ptr(),
-                                                        int(training), _ref(dx), dgamma.data_ptr(), dbeta.data_ptr(), _ref(dmasked), stream_ptr()))
+                                                        int(training), _ref(dx), dgamma.data_ptr(), dbeta.data_ptr(), None, stream_ptr()))
     return dx, dgamma, dbeta
 
 
