@@ -99,6 +99,12 @@ class GradAllReducer:
     def reduce(self, params, grads: Optional[Sequence[Optional[Tensor]]] = None):
         """reduce(params, grads) — or reduce(grads): gradients without an owning parameter are averaged in place."""
         if self.world == 1:
+            # nothing to exchange; the caller (the segmentor's autograd node with a hook installed) still expects the
+            # reducer to own param.grad
+            if grads is not None:
+                for p, g in zip(params, grads):
+                    if p is not None and g is not None:
+                        p.grad = g.view_as(p)
             return
         if grads is None:
             params, grads = None, params

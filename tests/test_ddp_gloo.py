@@ -59,3 +59,22 @@ def test_single_process_is_a_no_op():
     g = [torch.ones(3)]
     red.reduce(g); red.finish()
     assert torch.equal(g[0], torch.ones(3))
+
+
+def test_single_process_reducer_still_owns_param_grad():
+    """With a grad-ready hook installed the segmentor's autograd node hands its gradients to the hook only (returning them
+    to autograd as well would make AccumulateGrad clone every tensor the reducer references): a reducer of world size 1
+    must therefore assign param.grad itself."""
+    from octave_b200.train import GradAllReducer
+    red = GradAllReducer()
+    p = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4))]
+    g = [torch.full((2, 3), 2.0), torch.full((4,), 3.0)]
+    red.reduce(p, g); red.finish()
+    assert torch.equal(p[0].grad, g[0]) and torch.equal(p[1].grad, g[1])
+
+
+def test_reducer_rejects_unknown_bucket_dtype():
+    import pytest
+    from octave_b200.train import GradAllReducer
+    with pytest.raises(ValueError, match="grad_dtype"):
+        GradAllReducer(grad_dtype="fp8")
