@@ -46,3 +46,46 @@ def test_new_entry_points_validate_arguments_without_gpu():
     assert _lib.lib.octave_conv_halo_supported(ctypes.byref(d)) == 1
     assert _lib.lib.octave_pack_job_blocks(0, 32, 64, 1, 3) == (32 * 64 + 1023) // 1024
     assert _lib.lib.octave_pack_weight_multi(None, 0, 0, None) == _lib.ERR_INVALID
+
+
+def test_integration_table_line_references_point_at_the_named_declarations():
+    """INTEGRATION.md cites header line ranges for every C-ABI group: each entry point a row names (wildcards and a/b
+    alternatives expanded) must be declared inside one of the ranges the row cites."""
+    import fnmatch
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "octave_b200.h")).read().split("\n")
+    decl = {}
+    for i, line in enumerate(header):
+        m = re.match(r"^(?:int|size_t|void|int64_t|unsigned long long|int32_t)\s+(octave_\w+)\(", line)
+        if m:
+            decl.setdefault(m.group(1), i + 1)
+    rows = [r for r in open(os.path.join(root, "INTEGRATION.md")).read().split("\n") if r.startswith("| `octave_")]
+    assert len(rows) >= 12
+    checked = 0
+    for row in rows:
+        first = row.split("|")[1]
+        cite = re.findall(r"\(`:([\d,\-]+)`\)", first)
+        assert cite, first
+        ranges = [tuple(int(x) for x in part.split("-")) for part in cite[-1].split(",")]
+        names = re.findall(r"`(octave_[\w\*/\(\)]+)`", first)
+        pats = []
+        for n in names:
+            if n.endswith("(_multi)"):                     # `octave_pack_weight(_multi)`: the name with and without the suffix
+                pats += [n[:-8], n[:-8] + "_multi"]
+                continue
+            if "/" in n:                                   # `octave_loss_fwd/bwd`, `..._supported/_stats_bytes`
+                base = n.split("/")[0]
+                pats.append(base)
+                for suf in n.split("/")[1:]:
+                    pats.append(base.rsplit("_", 1)[0] + ("" if suf.startswith("_") else "_") + suf if not suf.startswith("_")
+                                else base.rsplit("_", 1)[0] + suf)
+            else:
+                pats.append(n)
+        for pat in pats:
+            hits = [k for k in decl if fnmatch.fnmatch(k, pat)]
+            for k in hits:
+                assert any(a <= decl[k] <= b for a, b in ranges), (k, decl[k], ranges)
+                checked += 1
+    assert checked >= 60
